@@ -1,0 +1,22 @@
+"""Drop-in for pytorch/GNNResidual.py: r = b - A x."""
+import torch
+
+from . import _runtime as rt
+from ._io import Placement, float_dtype
+
+
+class GNNResidual(torch.nn.Module):
+    """GNNResidual.py:121-132.  forward(vertex_attr=[b,x], edgeij_pair, edge_attr=[A_ij])
+    -> r [n,1].  Extension: vertex_attr = [b (k cols) | x (k cols)] gives r [n,k]."""
+
+    def forward(self, vertex_attr, edgeij_pair, edge_attr, batch=None):
+        io = Placement(vertex_attr, edgeij_pair, edge_attr)
+        dt = float_dtype(vertex_attr, edge_attr)
+        n, F = vertex_attr.shape
+        k = F // 2
+        plan = rt.get_plan(edgeij_pair, n)
+        vals = rt.get_vals(plan, edge_attr, 0, dt)
+        va = io.up(vertex_attr, dt)
+        b = rt.dense(va[:, :k])
+        x = rt.dense(va[:, k:2 * k])
+        return io.down(rt.residual(plan, vals, x, b))

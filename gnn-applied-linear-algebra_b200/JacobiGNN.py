@@ -1,0 +1,41 @@
+"""Drop-in for pytorch/JacobiGNN.py: weighted Jacobi x <- x + w (b - A x) / A_ii."""
+import torch
+
+from . import _runtime as rt
+from ._io import Placement, float_dtype
+
+
+class JacobiGNN(torch.nn.Module):
+    """JacobiGNN.py:125-148.  vertex_attr=[A_ii, b, x], edge_attr=[A_ij, c_ij] (edges INCLUDE
+    the diagonal), g=[w].  Each sweep is one launch of glab_jacobi (gather + multiply +
+    row sum + update fused); sweeps ping-pong between two x buffers.
+    Extension: vertex_attr = [A_ii | b (k cols) | x (k cols)] smooths k right-hand sides."""
+
+    def _setup(self, vertex_attr, edgeij_pair, edge_attr, g):
+        io = Placement(vertex_attr, edgeij_pair, edge_attr)
+        dt = float_dtype(vertex_attr, edge_attr)
+        n, F = vertex_attr.shape
+        k = (F - 1) // 2
+        plan = rt.get_plan(edgeij_pair, n)
+        vals = rt.get_vals(plan, edge_attr, 0, dt)
+        va = io.up(vertex_attr, dt)
+        diag = rt.column(va, 0)
+        b = rt.dense(va[:, 1:1 + k])
+        x = rt.dense(va[:, 1 + k:1 + 2 * k])
+        w = rt.scalar(g[0] if isinstance(g, torch.Tensor) else g, io.device, dt)
+        return io, dt, plan, vals, va, diag, b, x, w
+
+    def iterate(self, vertex_attr, edgeij_pair, edge_attr, g, batch=None):
+        io, dt, plan, vals, va, diag, b, x, w = self._setup(vertex_attr, edgeij_pair, edge_attr, g)
+        x_new = rt.jacobi(plan, vals, diag, b, x, torch.empty_like(x), w)
+        e_out = rt.with_messages(plan, vals, x, io.up(edge_attr, dt)[:, 0])
+        v_out = torch.cat([diag.view(-1, 1), b, x_new], 1)
+        return io.down(v_out), io.down(e_out), g
+
+    def forward(self, n_iters, vertex_attr, edgeij_pair, edge_attr, g, batch=None):
+        io, dt, plan, vals, va, diag, b, x, w = self._setup(vertex_attr, edgeij_pair, edge_attr, g)
+        other = torch.empty_like(x)
+        for _ in range(n_iters):
+            rt.jacobi(plan, vals, diag, b, x, other, w)
+            x, other = other, x
+        return io.down(x.reshape(x.shape[0], -1))

@@ -1,0 +1,398 @@
+"""Host-side runtime above the C ABI: plans (int64 COO -> int32 CSR), value arrays, scalar
+staging and one thin Python wrapper per C entry point.  torch is used for device memory,
+streams and (elsewhere) torch.distributed -- plumbing only; every numerical operation on the
+hot path is a kernel of libglab_b200.so.  Nothing here falls back to PyTorch math or the CPU.
+"""
+import collections
+import ctypes
+import weakref
+
+import torch
+
+from ._lib import GlabError, P, check, lib
+
+SUPPORTED_K = (1, 2, 4, 8)
+_SUF = {torch.float32: "f32", torch.float64: "f64"}
+
+
+def _require_cuda():
+    if not torch.cuda.is_available():
+        raise GlabError("glab_b200 needs a CUDA device (B200 / sm_100a); there is no CPU path")
+
+
+def suffix(dtype):
+    try:
+        return _SUF[dtype]
+    except KeyError:
+        raise GlabError("unsupported dtype %s (float32 / float64 only)" % dtype)
+
+
+def ptr(t):
+    return None if t is None else ctypes.c_void_p(t.data_ptr())
+
+
+def stream_ptr():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def compute_device(*tensors):
+    """Device the step runs on: the first CUDA tensor's device, else the current CUDA device
+    (host tensors are uploaded, results are returned to the host -- the reference's users hold
+    CPU tensors)."""
+    _require_cuda()
+    for t in tensors:
+        if isinstance(t, torch.Tensor) and t.is_cuda:
+            return t.device
+    return torch.device("cuda", torch.cuda.current_device())
+
+
+def to_device(t, device, dtype=None):
+    if t is None:
+        return None
+    if t.device != device:
+        t = t.to(device, non_blocking=True)
+    if dtype is not None and t.dtype != dtype:
+        t = t.to(dtype)
+    return t
+
+
+def dense(t):
+    """Contiguous, 16-byte aligned view/copy (vector loads in the kernels need it)."""
+    t = t.contiguous()
+    if t.data_ptr() % 16:
+        t = t.clone(memory_format=torch.contiguous_format)
+    return t
+
+
+def column(t, j):
+    """Column j of a row-major [n, F] tensor as a dense [n] tensor."""
+    return dense(t[:, j])
+
+
+class _DevArray:
+    """Exposes a raw device pointer owned by a plan to torch (zero-copy) via the CUDA array
+    interface; keeps the owner alive."""
+
+    def __init__(self, pointer, n, typestr, owner):
+        self.owner = owner
+        self.__cuda_array_interface__ = {"shape": (n,), "typestr": typestr, "data": (pointer, False),
+                                         "version": 2}
+
+
+class Plan:
+    """Opaque int32 CSR structure of one operator on one GPU (glab_plan)."""
+
+    def __init__(self, handle, device):
+        self._h = handle
+        self.device = device
+        n_rows, n_cols, nnz = ctypes.c_int64(), ctypes.c_int64(), ctypes.c_int64()
+        mx, ident = ctypes.c_int32(), ctypes.c_int32()
+        check(lib.glab_plan_info(self._h, ctypes.byref(n_rows), ctypes.byref(n_cols),
+                                 ctypes.byref(nnz), ctypes.byref(mx), ctypes.byref(ident)),
+              "glab_plan_info")
+        self.n_rows, self.n_cols, self.nnz = n_rows.value, n_cols.value, nnz.value
+        self.max_row_nnz, self.identity = mx.value, bool(ident.value)
+
+    @property
+    def handle(self):
+        return self._h
+
+    def __del__(self):
+        h, self._h = getattr(self, "_h", None), None
+        if h:
+            try:
+                lib.glab_plan_destroy(h)
+            except Exception:
+                pass
+
+    @classmethod
+    def from_coo(cls, edge_index, n_rows, n_cols=None):
+        """edge_index: int64 [2, z]; row 0 = aggregation target i, row 1 = source j
+        (the reference's edgeij_pair, UtilsGNN.py:74-78)."""
+        device = compute_device(edge_index)
+        if edge_index.dtype != torch.int64 or edge_index.dim() != 2 or edge_index.shape[0] != 2:
+            raise GlabError("edgeij_pair must be an int64 [2, nnz] tensor")
+        ei = to_device(edge_index, device).contiguous()
+        n_cols = n_rows if n_cols is None else n_cols
+        z = ei.shape[1]
+        h = P()
+        with torch.cuda.device(device):
+            check(lib.glab_plan_create(n_rows, n_cols, z, ptr(ei[0]), ptr(ei[1]), stream_ptr(),
+                                       ctypes.byref(h)), "glab_plan_create")
+        return cls(h, device)
+
+    @classmethod
+    def from_csr(cls, rowptr, colidx, n_rows, n_cols):
+        device = compute_device(rowptr)
+        rp = to_device(rowptr, device, torch.int32).contiguous()
+        ci = to_device(colidx, device, torch.int32).contiguous()
+        h = P()
+        with torch.cuda.device(device):
+            check(lib.glab_plan_create_csr(n_rows, n_cols, ci.numel(), ptr(rp), ptr(ci), stream_ptr(),
+                                           ctypes.byref(h)), "glab_plan_create_csr")
+        return cls(h, device)
+
+    def csr(self):
+        """(rowptr, colidx, perm-or-None) as zero-copy int32 torch tensors."""
+        rp, ci, pm = P(), P(), P()
+        check(lib.glab_plan_csr(self._h, ctypes.byref(rp), ctypes.byref(ci), ctypes.byref(pm)),
+              "glab_plan_csr")
+
+        def wrap(p, n):
+            if not p.value or n == 0:
+                return torch.empty(0, dtype=torch.int32, device=self.device)
+            with torch.cuda.device(self.device):
+                return torch.as_tensor(_DevArray(p.value, n, "<i4", self), device=self.device)
+
+        return wrap(rp, self.n_rows + 1), wrap(ci, self.nnz), (wrap(pm, self.nnz) if pm.value else None)
+
+
+# --------------------------------------------------------------------------- caches
+class _Cache:
+    """Small LRU keyed on (storage pointer, shape, strides, version, extra).  An entry is valid
+    only while the tensor object that created it is alive (an alive tensor pins its storage, so
+    the address cannot have been recycled for different data) and unmodified (_version)."""
+
+    def __init__(self, capacity=8):
+        self.capacity = capacity
+        self.d = collections.OrderedDict()
+
+    @staticmethod
+    def key(t, extra=()):
+        return (t.data_ptr(), tuple(t.shape), tuple(t.stride()), t.dtype, str(t.device), t._version) + tuple(extra)
+
+    def get(self, t, extra=()):
+        k = self.key(t, extra)
+        hit = self.d.get(k)
+        if hit is None:
+            return None
+        ref, value = hit
+        if ref() is None:
+            del self.d[k]
+            return None
+        self.d.move_to_end(k)
+        return value
+
+    def put(self, t, value, extra=()):
+        k = self.key(t, extra)
+        self.d[k] = (weakref.ref(t), value)
+        self.d.move_to_end(k)
+        while len(self.d) > self.capacity:
+            self.d.popitem(last=False)
+
+    def clear(self):
+        self.d.clear()
+
+
+_plan_cache = _Cache(8)
+_vals_cache = _Cache(8)
+
+
+def clear_caches():
+    _plan_cache.clear()
+    _vals_cache.clear()
+
+
+def get_plan(edge_index, n_rows, n_cols=None):
+    """Cached plan for the caller's edgeij_pair tensor (device or host)."""
+    extra = (n_rows, n_cols)
+    plan = _plan_cache.get(edge_index, extra)
+    if plan is None:
+        plan = Plan.from_coo(edge_index, n_rows, n_cols)
+        _plan_cache.put(edge_index, plan, extra)
+    return plan
+
+
+def get_vals(plan, edge_attr, col=0, dtype=None):
+    """A_ij in CSR slot order as a dense device array of `dtype` (default: edge_attr's).
+    Zero-copy when the caller's edge order is already the CSR order and the column is dense."""
+    dtype = dtype or edge_attr.dtype
+    extra = (id(plan), col, dtype)
+    hit = _vals_cache.get(edge_attr, extra)
+    if hit is not None and hit[0] is plan:
+        return hit[1]
+    ea = to_device(edge_attr, plan.device)
+    if ea.dim() == 1:
+        ea = ea.view(-1, 1)
+    if ea.shape[0] != plan.nnz:
+        raise GlabError("edge_attr has %d rows, plan has %d edges" % (ea.shape[0], plan.nnz))
+    if ea.dtype != dtype:
+        ea = ea[:, col:col + 1].to(dtype)
+        col = 0
+    if plan.identity and ea.shape[1] == 1 and ea.is_contiguous() and ea.data_ptr() % 16 == 0:
+        v = ea.view(-1)
+    else:
+        ea = ea if ea.stride(1) == 1 else ea.contiguous()
+        v = torch.empty(plan.nnz, dtype=dtype, device=plan.device)
+        with torch.cuda.device(plan.device):
+            check(getattr(lib, "glab_gather_vals_" + suffix(dtype))(
+                plan.handle, ptr(ea), ea.stride(0), col, ptr(v), stream_ptr()), "glab_gather_vals")
+    _vals_cache.put(edge_attr, (plan, v), extra)
+    return v
+
+
+def slot_order(plan, per_edge, dtype=None):
+    """Any per-edge 1-D array (S_ij ...) -> CSR slot order, dense."""
+    return get_vals(plan, per_edge.view(-1, 1) if per_edge.dim() == 1 else per_edge, 0, dtype)
+
+
+def scalar(value, device, dtype):
+    """A 1-element device tensor holding `value` (python number or 0-d/1-element tensor),
+    rounded to `dtype` the way torch rounds a 0-d operand of a tensor op.  No host sync."""
+    if isinstance(value, torch.Tensor):
+        return value.reshape(-1)[:1].to(device=device, dtype=dtype, non_blocking=True)
+    return torch.tensor([value], dtype=dtype).to(device, non_blocking=True)
+
+
+_workspaces = {}
+
+
+def reduce_workspace(device):
+    """Zero-initialised scratch for the deterministic grid reductions (one per device+stream)."""
+    key = (device.index, torch.cuda.current_stream(device).cuda_stream)
+    ws = _workspaces.get(key)
+    if ws is None:
+        ws = torch.zeros(int(lib.glab_reduce_workspace_bytes()) // 8 + 1, dtype=torch.float64, device=device)
+        _workspaces[key] = ws
+    return ws
+
+
+# --------------------------------------------------------------------------- op wrappers
+def _k_of(x):
+    k = 1 if x.dim() == 1 else x.shape[1]
+    if k not in SUPPORTED_K:
+        raise GlabError("number of right-hand-side columns must be one of %s, got %d" % (SUPPORTED_K, k))
+    return k
+
+
+def _rows(plan, rows):
+    return (0, plan.n_rows) if rows is None else (int(rows[0]), int(rows[1]))
+
+
+def _call(name, dtype, device, *args):
+    with torch.cuda.device(device):
+        check(getattr(lib, "glab_%s_%s" % (name, suffix(dtype)))(*args), "glab_" + name)
+
+
+def spmm(plan, vals, x, out=None, rows=None):
+    k = _k_of(x)
+    if out is None:
+        out = torch.empty((plan.n_rows,) + tuple(x.shape[1:]), dtype=x.dtype, device=x.device)
+    rb, re = _rows(plan, rows)
+    _call("spmm", x.dtype, plan.device, plan.handle, ptr(vals), ptr(x), k, ptr(out), rb, re, stream_ptr())
+    return out
+
+
+def residual(plan, vals, x, b, out=None, rows=None):
+    k = _k_of(x)
+    if out is None:
+        out = torch.empty_like(b)
+    rb, re = _rows(plan, rows)
+    _call("residual", x.dtype, plan.device, plan.handle, ptr(vals), ptr(x), ptr(b), k, ptr(out), rb, re,
+          stream_ptr())
+    return out
+
+
+def spmm_add(plan, vals, x, b, out=None, rows=None):
+    k = _k_of(x)
+    if out is None:
+        out = torch.empty_like(b)
+    rb, re = _rows(plan, rows)
+    _call("spmm_add", x.dtype, plan.device, plan.handle, ptr(vals), ptr(x), ptr(b), k, ptr(out), rb, re,
+          stream_ptr())
+    return out
+
+
+def jacobi(plan, vals, diag, b, x_in, x_out, omega_dev, rows=None):
+    k = _k_of(x_in)
+    rb, re = _rows(plan, rows)
+    _call("jacobi", x_in.dtype, plan.device, plan.handle, ptr(vals), ptr(diag), ptr(b), ptr(x_in),
+          ptr(x_out), ptr(omega_dev), k, rb, re, stream_ptr())
+    return x_out
+
+
+def cheby_first(plan, vals, b, x_in, x_out, r, p, alpha_dev, rows=None):
+    k = _k_of(x_in)
+    rb, re = _rows(plan, rows)
+    _call("cheby_first", x_in.dtype, plan.device, plan.handle, ptr(vals), ptr(b), ptr(x_in), ptr(x_out),
+          ptr(r), ptr(p), ptr(alpha_dev), k, rb, re, stream_ptr())
+
+
+def cheby_next(plan, vals, p_in, p_out, r, x, alpha_old_dev, alpha_dev, beta_dev, rows=None):
+    k = _k_of(p_in)
+    rb, re = _rows(plan, rows)
+    _call("cheby_next", p_in.dtype, plan.device, plan.handle, ptr(vals), ptr(p_in), ptr(p_out), ptr(r),
+          ptr(x), ptr(alpha_old_dev), ptr(alpha_dev), ptr(beta_dev), k, rb, re, stream_ptr())
+
+
+def power_step(plan, vals, b_in, y, sumsq_in, sumsq_out, rows=None):
+    rb, re = _rows(plan, rows)
+    ws = reduce_workspace(plan.device)
+    _call("power_step", b_in.dtype, plan.device, plan.handle, ptr(vals), ptr(b_in), ptr(y), ptr(sumsq_in),
+          ptr(sumsq_out), ptr(ws), rb, re, stream_ptr())
+
+
+def rayleigh(plan, vals, b_in, b_out, y_out, sumsq_in, sums_out, rows=None):
+    rb, re = _rows(plan, rows)
+    ws = reduce_workspace(plan.device)
+    _call("rayleigh", b_in.dtype, plan.device, plan.handle, ptr(vals), ptr(b_in), ptr(b_out), ptr(y_out),
+          ptr(sumsq_in), ptr(sums_out), ptr(ws), rb, re, stream_ptr())
+
+
+def xtax(plan, vals, x, sums_out, rows=None):
+    rb, re = _rows(plan, rows)
+    ws = reduce_workspace(plan.device)
+    _call("xtax", x.dtype, plan.device, plan.handle, ptr(vals), ptr(x), ptr(sums_out), ptr(ws), rb, re,
+          stream_ptr())
+
+
+def edge_messages(plan, vals, x, out_edges, col):
+    """out_edges[:, col:col+k] = A_ij * x_j in the caller's edge order (out_edges is [z, ld])."""
+    k = _k_of(x)
+    _call("edge_messages", x.dtype, plan.device, plan.handle, ptr(vals), ptr(x), k, ptr(out_edges),
+          out_edges.stride(0), col, stream_ptr())
+
+
+def with_messages(plan, vals, x, A_col):
+    """The reference's returned edge_attr = cat([A_ij, c_ij], 1) (e.g. MatVecGNN.py:84)."""
+    k = _k_of(x)
+    out = torch.empty((plan.nnz, 1 + k), dtype=x.dtype, device=plan.device)
+    out[:, 0] = A_col.reshape(-1)
+    edge_messages(plan, vals, x, out, 1)
+    return out
+
+
+def segment_sum(plan, src_slots, out=None):
+    k = _k_of(src_slots)
+    if out is None:
+        out = torch.empty((plan.n_rows,) + tuple(src_slots.shape[1:]), dtype=src_slots.dtype,
+                          device=plan.device)
+    _call("segment_sum", src_slots.dtype, plan.device, plan.handle, ptr(src_slots), k, ptr(out), stream_ptr())
+    return out
+
+
+def segment_max(plan, src_slots, out=None):
+    if out is None:
+        out = torch.empty(plan.n_rows, dtype=src_slots.dtype, device=plan.device)
+    _call("segment_max", src_slots.dtype, plan.device, plan.handle, ptr(src_slots), ptr(out), stream_ptr())
+    return out
+
+
+def soc_classic(plan, vals, theta, rowmax=None):
+    S = torch.empty(plan.nnz, dtype=vals.dtype, device=plan.device)
+    _call("soc_classic", vals.dtype, plan.device, plan.handle, ptr(vals), float(theta), ptr(S), ptr(rowmax),
+          stream_ptr())
+    return S
+
+
+def soc_sa(plan, vals, diag):
+    S = torch.empty(plan.nnz, dtype=vals.dtype, device=plan.device)
+    _call("soc_sa", vals.dtype, plan.device, plan.handle, ptr(vals), ptr(diag), ptr(S), stream_ptr())
+    return S
+
+
+def direct_interp(plan, vals, S_slots, diag, cflag):
+    w = torch.empty(plan.nnz, dtype=vals.dtype, device=plan.device)
+    _call("direct_interp", vals.dtype, plan.device, plan.handle, ptr(vals), ptr(S_slots), ptr(diag),
+          ptr(cflag), ptr(w), stream_ptr())
+    return w

@@ -1,0 +1,204 @@
+// glab_amg.cu -- AMG setup kernels: classical / smoothed-aggregation strength of connection,
+// direct-interpolation weights, and the per-edge message column.  All are row-local single
+// passes over the CSR slots with bit-exact element-wise chains (IEEE div, no FMA contraction,
+// the reference's operation order); citations are in include/glab.h.
+#include "glab_tiles.cuh"
+
+namespace glab {
+
+// S_ij = relu(((-1*A_ij)/v_i) - theta),  v_i = max_k(-A_ik)  (SOCClassicGNN.py:69, :125)
+template <typename T> struct OpSocClassic {
+  static constexpr bool kReduce = true;
+  static constexpr int kNarr = 1;
+  T theta;
+  T* rowmax;  // optional [n_rows]
+  struct RowState { T v; bool any; };
+  __device__ void begin_row(RowState& s, int) const { s.v = T(0); s.any = false; }
+  __device__ void accumulate(RowState& s, T a, T, int) const {
+    const T m = T(-1) * a;
+    // amax semantics of scatter_reduce_: NaN propagates
+    if (!s.any) { s.v = m; s.any = true; }
+    else if (m > s.v || m != m) s.v = m;
+  }
+  __device__ void end_row(RowState& s, int r) const {
+    if (!s.any) s.v = T(0);  // torch_scatter: rows without edges -> 0
+    if (rowmax) rowmax[r] = s.v;
+  }
+  __device__ T edge(const RowState& s, T a, T, int) const {
+    const T q = (T(-1) * a) / s.v;
+    const T d = q - theta;
+    return (d <= T(0)) ? T(0) : d;  // relu; NaN stays NaN like torch.relu
+  }
+};
+
+// S_ij = (A_ij*A_ij)/(A_ii*A_jj)  (SOCSAGNN.py:67)
+template <typename T> struct OpSocSA {
+  static constexpr bool kReduce = false;
+  static constexpr int kNarr = 1;
+  const T* diag;
+  struct RowState { T dii; };
+  __device__ void begin_row(RowState& s, int r) const { s.dii = __ldg(diag + r); }
+  __device__ void accumulate(RowState&, T, T, int) const {}
+  __device__ void end_row(RowState&, int) const {}
+  __device__ T edge(const RowState& s, T a, T, int col) const {
+    return (a * a) / (s.dii * __ldg(diag + col));
+  }
+};
+
+// DirectInterpGNN.py:89-94, :127, :150
+template <typename T> struct OpDirectInterp {
+  static constexpr bool kReduce = true;
+  static constexpr int kNarr = 2;
+  const T* diag;
+  const T* cflag;
+  struct RowState { T num, den, alpha, omc; };
+  __device__ void begin_row(RowState& s, int) const { s.num = T(0); s.den = T(0); }
+  __device__ void accumulate(RowState& s, T a, T sij, int col) const {
+    s.num = s.num + a;
+    s.den = s.den + (a * sij) * __ldg(cflag + col);
+  }
+  __device__ void end_row(RowState& s, int r) const {
+    const T gamma = s.num / s.den;
+    s.alpha = (T(1) / __ldg(diag + r)) * gamma;
+    s.omc = T(1) - __ldg(cflag + r);
+  }
+  __device__ T edge(const RowState& s, T a, T, int) const { return s.omc * ((-a) * s.alpha); }
+};
+
+template <typename T, class Op>
+static int launch_edge_tiles(const glab_plan* p, const T* vals, const T* aux, const Op& op, T* out,
+                             void* stream) {
+  if (!p || !out || (p->nnz > 0 && !vals)) return GLAB_E_ARG;
+  if (p->n_rows == 0) return 0;
+  const int ntiles = (int)((p->n_rows + kThreads - 1) / kThreads);
+  int64_t want = (int64_t)kThreads * (p->max_row_nnz > 0 ? p->max_row_nnz : 1);
+  int cap = (int)(want < 4096 ? want : 4096);
+  cap = (cap + 31) & ~31;
+  const size_t smem = tile_smem_bytes<T>(cap, Op::kNarr);
+  auto kern = k_edge_tiles<T, Op>;
+  static bool attr_done = false;
+  if (!attr_done) {
+    GLAB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024));
+    attr_done = true;
+  }
+  TileArgs<T> a{p->rowptr, p->colidx, vals, 0, (int)p->n_rows, cap};
+  kern<<<ntiles, kThreads, smem, as_stream(stream)>>>(a, aux, p->perm, op, out, ntiles);
+  return (int)cudaGetLastError();
+}
+
+// c[e, column + c] = A_slot * x[col(slot), c]
+template <typename T, int K>
+__global__ void k_edge_messages(const int32_t* __restrict__ colidx, const T* __restrict__ vals,
+                                const int32_t* __restrict__ perm, const T* __restrict__ x,
+                                int64_t nnz, T* __restrict__ out, int64_t ld, int64_t column) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < nnz;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    const int col = __ldg(colidx + i);
+    const T v = __ldg(vals + i);
+    T xv[K];
+    load_vec<T, K>(xv, x + (size_t)col * K);
+    const int64_t e = perm ? (int64_t)__ldg(perm + i) : i;
+#pragma unroll
+    for (int c = 0; c < K; ++c) out[e * ld + column + c] = v * xv[c];
+  }
+}
+
+template <typename T>
+static int edge_messages(const glab_plan* p, const T* vals, const T* x, int k, T* out, int64_t ld,
+                         int64_t column, void* stream) {
+  if (!p || !x || !out || (p->nnz > 0 && !vals) || ld < 1 || column < 0 || column + k > ld)
+    return GLAB_E_ARG;
+  if (p->nnz == 0) return 0;
+  int64_t b = (p->nnz + 255) / 256;
+  const int64_t capb = (int64_t)p->sm_count * 32;
+  const int grid = (int)(b < capb ? b : capb);
+  cudaStream_t st = as_stream(stream);
+  switch (k) {
+    case 1: k_edge_messages<T, 1><<<grid, 256, 0, st>>>(p->colidx, vals, p->perm, x, p->nnz, out, ld, column); break;
+    case 2: k_edge_messages<T, 2><<<grid, 256, 0, st>>>(p->colidx, vals, p->perm, x, p->nnz, out, ld, column); break;
+    case 4: k_edge_messages<T, 4><<<grid, 256, 0, st>>>(p->colidx, vals, p->perm, x, p->nnz, out, ld, column); break;
+    case 8: k_edge_messages<T, 8><<<grid, 256, 0, st>>>(p->colidx, vals, p->perm, x, p->nnz, out, ld, column); break;
+    default: return GLAB_E_ARG;
+  }
+  return (int)cudaGetLastError();
+}
+
+// The bare seam: out[i,:] = reduce over the row's slots of src[slot,:]  (scatter sum / max).
+template <typename T, int K, bool IsMax>
+__global__ void k_segment_reduce(const int32_t* __restrict__ rowptr, const T* __restrict__ src,
+                                 int64_t n_rows, T* __restrict__ out) {
+  for (int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; r < n_rows;
+       r += (int64_t)gridDim.x * blockDim.x) {
+    const int rs = __ldg(rowptr + r), re = __ldg(rowptr + r + 1);
+    T acc[K];
+#pragma unroll
+    for (int c = 0; c < K; ++c) acc[c] = T(0);
+    for (int j = rs; j < re; ++j) {
+      T v[K];
+      load_vec<T, K>(v, src + (size_t)j * K);
+#pragma unroll
+      for (int c = 0; c < K; ++c) {
+        if (IsMax) acc[c] = (j == rs || v[c] > acc[c] || v[c] != v[c]) ? v[c] : acc[c];
+        else acc[c] = acc[c] + v[c];
+      }
+    }
+    store_vec<T, K>(out + (size_t)r * K, acc);
+  }
+}
+
+template <typename T, bool IsMax>
+static int segment_reduce(const glab_plan* p, const T* src, int k, T* out, void* stream) {
+  if (!p || !out || (p->nnz > 0 && !src)) return GLAB_E_ARG;
+  if (p->n_rows == 0) return 0;
+  int64_t b = (p->n_rows + 255) / 256;
+  const int64_t capb = (int64_t)p->sm_count * 32;
+  const int grid = (int)(b < capb ? b : capb);
+  cudaStream_t st = as_stream(stream);
+  switch (k) {
+    case 1: k_segment_reduce<T, 1, IsMax><<<grid, 256, 0, st>>>(p->rowptr, src, p->n_rows, out); break;
+    case 2: k_segment_reduce<T, 2, IsMax><<<grid, 256, 0, st>>>(p->rowptr, src, p->n_rows, out); break;
+    case 4: k_segment_reduce<T, 4, IsMax><<<grid, 256, 0, st>>>(p->rowptr, src, p->n_rows, out); break;
+    case 8: k_segment_reduce<T, 8, IsMax><<<grid, 256, 0, st>>>(p->rowptr, src, p->n_rows, out); break;
+    default: return GLAB_E_ARG;
+  }
+  return (int)cudaGetLastError();
+}
+
+}  // namespace glab
+
+using namespace glab;
+
+#define GLAB_AMG_INST(SUF, T)                                                                      \
+  extern "C" int glab_soc_classic_##SUF(const glab_plan* p, const T* v, T theta, T* S, T* rowmax,  \
+                                        void* s) {                                                 \
+    OpSocClassic<T> op{theta, rowmax};                                                             \
+    return launch_edge_tiles<T>(p, v, (const T*)nullptr, op, S, s);                                \
+  }                                                                                                \
+  extern "C" int glab_soc_sa_##SUF(const glab_plan* p, const T* v, const T* diag, T* S, void* s) { \
+    if (!diag) return GLAB_E_ARG;                                                                  \
+    OpSocSA<T> op{diag};                                                                           \
+    return launch_edge_tiles<T>(p, v, (const T*)nullptr, op, S, s);                                \
+  }                                                                                                \
+  extern "C" int glab_direct_interp_##SUF(const glab_plan* p, const T* v, const T* S,              \
+                                          const T* diag, const T* cflag, T* w, void* s) {          \
+    if (!diag || !cflag || (p && p->nnz > 0 && !S)) return GLAB_E_ARG;                             \
+    OpDirectInterp<T> op{diag, cflag};                                                             \
+    return launch_edge_tiles<T>(p, v, S, op, w, s);                                                \
+  }                                                                                                \
+  extern "C" int glab_edge_messages_##SUF(const glab_plan* p, const T* v, const T* x, int k,       \
+                                          T* out, int64_t ld, int64_t column, void* s) {           \
+    return edge_messages<T>(p, v, x, k, out, ld, column, s);                                       \
+  }
+
+#define GLAB_SEG_INST(SUF, T)                                                                      \
+  extern "C" int glab_segment_sum_##SUF(const glab_plan* p, const T* src, int k, T* out, void* s) { \
+    return segment_reduce<T, false>(p, src, k, out, s);                                            \
+  }                                                                                                \
+  extern "C" int glab_segment_max_##SUF(const glab_plan* p, const T* src, T* out, void* s) {       \
+    return segment_reduce<T, true>(p, src, 1, out, s);                                             \
+  }
+
+GLAB_SEG_INST(f32, float)
+GLAB_SEG_INST(f64, double)
+GLAB_AMG_INST(f32, float)
+GLAB_AMG_INST(f64, double)

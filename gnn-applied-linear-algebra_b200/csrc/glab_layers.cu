@@ -1,0 +1,407 @@
+// glab_layers.cu -- fused SpMV-bearing layer steps (MatVec, residual, Jacobi, Chebyshev,
+// power method, Rayleigh quotient, x^T W x) on the row-tile machinery of glab_tiles.cuh.
+// Each extern "C" entry is ONE kernel launch that replaces one or more reference GN blocks
+// (gathers + edge update + scatter + vertex update); citations are in include/glab.h.
+#include <cstdlib>
+#include "glab_tiles.cuh"
+
+namespace glab {
+
+// ---------------------------------------------------------------- epilogues (row sums in regs)
+struct NoState {};
+
+template <typename T, int K> struct EpiSpmm {  // y = A x            (MatVecGNN.py:109-114)
+  T* y;
+  using State = NoState;
+  __device__ void init(State&) const {}
+  __device__ void row(State&, int r, const T (&acc)[K]) const { store_vec<T, K>(y + (size_t)r * K, acc); }
+  __device__ void finish(State&) const {}
+};
+
+template <typename T, int K> struct EpiResidual {  // r = b - A x  (GNNResidual.py:115)
+  const T* b;
+  T* out;
+  using State = NoState;
+  __device__ void init(State&) const {}
+  __device__ void row(State&, int r, const T (&acc)[K]) const {
+    T bb[K], o[K];
+    load_vec<T, K>(bb, b + (size_t)r * K);
+#pragma unroll
+    for (int c = 0; c < K; ++c) o[c] = bb[c] - acc[c];
+    store_vec<T, K>(out + (size_t)r * K, o);
+  }
+  __device__ void finish(State&) const {}
+};
+
+template <typename T, int K> struct EpiAdd {  // out = b + A x  (coarse-grid correction x + P xc, VCycle.py:226)
+  const T* b;
+  T* out;
+  using State = NoState;
+  __device__ void init(State&) const {}
+  __device__ void row(State&, int r, const T (&acc)[K]) const {
+    T bb[K], o[K];
+    load_vec<T, K>(bb, b + (size_t)r * K);
+#pragma unroll
+    for (int c = 0; c < K; ++c) o[c] = bb[c] + acc[c];
+    store_vec<T, K>(out + (size_t)r * K, o);
+  }
+  __device__ void finish(State&) const {}
+};
+
+template <typename T, int K> struct EpiJacobi {  // x + w*(b - Ax)/d  (JacobiGNN.py:119)
+  const T* diag;
+  const T* b;
+  const T* x;
+  T* xo;
+  const T* omega;
+  struct State { T w; };
+  __device__ void init(State& s) const { s.w = __ldg(omega); }
+  __device__ void row(State& s, int r, const T (&acc)[K]) const {
+    T bb[K], xx[K], o[K];
+    const T d = __ldg(diag + r);
+    load_vec<T, K>(bb, b + (size_t)r * K);
+    load_vec<T, K>(xx, x + (size_t)r * K);
+#pragma unroll
+    for (int c = 0; c < K; ++c) o[c] = xx[c] + (s.w * (bb[c] - acc[c])) / d;
+    store_vec<T, K>(xo + (size_t)r * K, o);
+  }
+  __device__ void finish(State&) const {}
+};
+
+template <typename T, int K> struct EpiChebyFirst {  // ChebyGNN.py:117, :160-161
+  const T* b;
+  const T* x;
+  T* xo;
+  T* r_;
+  T* p_;
+  const T* alpha;
+  struct State { T a; };
+  __device__ void init(State& s) const { s.a = __ldg(alpha); }
+  __device__ void row(State& s, int r, const T (&acc)[K]) const {
+    T bb[K], xx[K], rr[K], o[K];
+    load_vec<T, K>(bb, b + (size_t)r * K);
+    load_vec<T, K>(xx, x + (size_t)r * K);
+#pragma unroll
+    for (int c = 0; c < K; ++c) {
+      rr[c] = bb[c] - acc[c];
+      o[c] = xx[c] + s.a * rr[c];
+    }
+    store_vec<T, K>(r_ + (size_t)r * K, rr);
+    store_vec<T, K>(p_ + (size_t)r * K, rr);
+    store_vec<T, K>(xo + (size_t)r * K, o);
+  }
+  __device__ void finish(State&) const {}
+};
+
+template <typename T, int K> struct EpiChebyNext {  // ChebyGNN.py:214, :240-241
+  const T* p_in;
+  T* p_out;
+  T* r_;
+  T* x_;
+  const T* alpha_old;
+  const T* alpha;
+  const T* beta;
+  struct State { T ao, a, b; };
+  __device__ void init(State& s) const {
+    s.ao = __ldg(alpha_old);
+    s.a = __ldg(alpha);
+    s.b = __ldg(beta);
+  }
+  __device__ void row(State& s, int r, const T (&acc)[K]) const {
+    T pp[K], rr[K], xx[K];
+    load_vec<T, K>(pp, p_in + (size_t)r * K);
+    load_vec_rw<T, K>(rr, r_ + (size_t)r * K);
+    load_vec_rw<T, K>(xx, x_ + (size_t)r * K);
+#pragma unroll
+    for (int c = 0; c < K; ++c) {
+      rr[c] = rr[c] - s.ao * acc[c];
+      pp[c] = rr[c] + s.b * pp[c];
+      xx[c] = xx[c] + s.a * pp[c];
+    }
+    store_vec<T, K>(r_ + (size_t)r * K, rr);
+    store_vec<T, K>(p_out + (size_t)r * K, pp);
+    store_vec<T, K>(x_ + (size_t)r * K, xx);
+  }
+  __device__ void finish(State&) const {}
+};
+
+template <typename T> struct EpiPower {  // PowerMethodGNN.py:156, :124, :183, :205
+  T* y;
+  const double* sumsq_in;
+  double* sumsq_out;
+  void* ws;
+  struct State { T n; bool scale; double s; };
+  __device__ void init(State& s) const {
+    s.scale = sumsq_in != nullptr;
+    s.n = s.scale ? (T)sqrt(__ldg(sumsq_in)) : T(1);
+    s.s = 0.0;
+  }
+  __device__ void row(State& s, int r, const T (&acc)[1]) const {
+    const T v = s.scale ? acc[0] / s.n : acc[0];
+    y[r] = v;
+    const T sq = v * v;
+    s.s += (double)sq;
+  }
+  __device__ void finish(State& s) const { grid_reduce2(s.s, 0.0, ws, sumsq_out); }
+};
+
+template <typename T> struct EpiRayleigh {  // PowerMethodGNN.py:205, :235, :264, :124, :292
+  const T* b_in;
+  T* b_out;
+  T* y_out;
+  const double* sumsq_in;
+  double* sums_out;
+  void* ws;
+  struct State { T n; bool scale; double s0, s1; };
+  __device__ void init(State& s) const {
+    s.scale = sumsq_in != nullptr;
+    s.n = s.scale ? (T)sqrt(__ldg(sumsq_in)) : T(1);
+    s.s0 = s.s1 = 0.0;
+  }
+  __device__ void row(State& s, int r, const T (&acc)[1]) const {
+    const T bi = __ldg(b_in + r);
+    const T bn = s.scale ? bi / s.n : bi;
+    const T ab = s.scale ? acc[0] / s.n : acc[0];
+    const T yA = bn * ab;
+    const T sq = bn * bn;
+    b_out[r] = bn;
+    y_out[r] = sq;
+    s.s0 += (double)yA;
+    s.s1 += (double)sq;
+  }
+  __device__ void finish(State& s) const { grid_reduce2(s.s0, s.s1, ws, sums_out); }
+};
+
+template <typename T> struct EpiXtAx {  // MatrixWeightedNorm.py:107-109
+  const T* x;
+  double* sums_out;
+  void* ws;
+  struct State { double s; };
+  __device__ void init(State& s) const { s.s = 0.0; }
+  __device__ void row(State& s, int r, const T (&acc)[1]) const {
+    const T v = __ldg(x + r) * acc[0];
+    s.s += (double)v;
+  }
+  __device__ void finish(State& s) const { grid_reduce2(s.s, 0.0, ws, sums_out); }
+};
+
+// ---------------------------------------------------------------- launch
+struct Tuning {
+  int rpt;        // rows per thread for K == 1 kernels (1 or 2)
+  int cap_max;    // staging capacity upper bound in slots
+  int persist;    // CTAs per SM for persistent (reducing) kernels
+};
+
+static const Tuning& tuning() {
+  static Tuning t = [] {
+    Tuning v{1, 4096, 8};
+    if (const char* e = getenv("GLAB_RPT")) v.rpt = atoi(e) == 2 ? 2 : 1;
+    if (const char* e = getenv("GLAB_CAP")) { int c = atoi(e); if (c >= 256 && c <= 8192) v.cap_max = c & ~31; }
+    if (const char* e = getenv("GLAB_PERSIST")) { int c = atoi(e); if (c >= 1 && c <= 16) v.persist = c; }
+    return v;
+  }();
+  return t;
+}
+
+template <typename T, int K, int RPT, class Epi>
+static int launch_tiles(const glab_plan* p, const T* vals, const T* x, const Epi& epi,
+                        int64_t row_begin, int64_t row_end, bool persistent, void* stream) {
+  constexpr int R = kThreads * RPT;
+  const int64_t nrows = row_end - row_begin;
+  const int ntiles = (int)((nrows + R - 1) / R);
+  int64_t want = (int64_t)R * (p->max_row_nnz > 0 ? p->max_row_nnz : 1);
+  int cap = (int)(want < tuning().cap_max ? want : tuning().cap_max);
+  cap = (cap + 31) & ~31;
+  const size_t smem = tile_smem_bytes<T>(cap, 1);
+  auto kern = k_row_tiles<T, K, RPT, Epi>;
+  static bool attr_done = false;  // one per template instantiation
+  if (!attr_done) {
+    GLAB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024));
+    attr_done = true;
+  }
+  int grid = ntiles;
+  if (persistent) {
+    int g = p->sm_count * tuning().persist;
+    if (g > kMaxReduceBlocks) g = kMaxReduceBlocks;
+    if (grid > g) grid = g;
+  }
+  if (grid < 1) grid = 1;
+  TileArgs<T> a{p->rowptr, p->colidx, vals, (int)row_begin, (int)row_end, cap};
+  kern<<<grid, kThreads, smem, as_stream(stream)>>>(a, x, epi, ntiles);
+  return (int)cudaGetLastError();
+}
+
+static int check_common(const glab_plan* p, const void* vals, const void* x, int64_t rb, int64_t re) {
+  if (!p || !x) return GLAB_E_ARG;
+  if (p->nnz > 0 && !vals) return GLAB_E_ARG;
+  if (rb < 0 || re < rb || re > p->n_rows) return GLAB_E_ARG;
+  return 0;
+}
+
+// dispatch on K (and RPT for K == 1)
+template <typename T, template <typename, int> class EpiK, class Make>
+static int dispatch_k(const glab_plan* p, const T* vals, const T* x, int k, int64_t rb, int64_t re,
+                      void* stream, Make make) {
+  if (rb == re) return 0;
+  switch (k) {
+    case 1:
+      if (tuning().rpt == 2) return launch_tiles<T, 1, 2>(p, vals, x, make(EpiK<T, 1>{}), rb, re, false, stream);
+      return launch_tiles<T, 1, 1>(p, vals, x, make(EpiK<T, 1>{}), rb, re, false, stream);
+    case 2: return launch_tiles<T, 2, 1>(p, vals, x, make(EpiK<T, 2>{}), rb, re, false, stream);
+    case 4: return launch_tiles<T, 4, 1>(p, vals, x, make(EpiK<T, 4>{}), rb, re, false, stream);
+    case 8: return launch_tiles<T, 8, 1>(p, vals, x, make(EpiK<T, 8>{}), rb, re, false, stream);
+    default: return GLAB_E_ARG;
+  }
+}
+
+template <typename T>
+static int spmm(const glab_plan* p, const T* vals, const T* x, int k, T* y, int64_t rb, int64_t re,
+                void* stream) {
+  int rc = check_common(p, vals, x, rb, re);
+  if (rc) return rc;
+  if (!y || (const void*)y == (const void*)x) return GLAB_E_ARG;
+  return dispatch_k<T, EpiSpmm>(p, vals, x, k, rb, re, stream, [&](auto e) { e.y = y; return e; });
+}
+
+template <typename T>
+static int residual(const glab_plan* p, const T* vals, const T* x, const T* b, int k, T* r,
+                    int64_t rb, int64_t re, void* stream) {
+  int rc = check_common(p, vals, x, rb, re);
+  if (rc) return rc;
+  if (!b || !r || (const void*)r == (const void*)x) return GLAB_E_ARG;
+  return dispatch_k<T, EpiResidual>(p, vals, x, k, rb, re, stream, [&](auto e) {
+    e.b = b; e.out = r; return e; });
+}
+
+template <typename T>
+static int spmm_add(const glab_plan* p, const T* vals, const T* x, const T* b, int k, T* out,
+                    int64_t rb, int64_t re, void* stream) {
+  int rc = check_common(p, vals, x, rb, re);
+  if (rc) return rc;
+  if (!b || !out || (const void*)out == (const void*)x) return GLAB_E_ARG;
+  return dispatch_k<T, EpiAdd>(p, vals, x, k, rb, re, stream, [&](auto e) {
+    e.b = b; e.out = out; return e; });
+}
+
+template <typename T>
+static int jacobi(const glab_plan* p, const T* vals, const T* diag, const T* b, const T* x_in,
+                  T* x_out, const T* omega, int k, int64_t rb, int64_t re, void* stream) {
+  int rc = check_common(p, vals, x_in, rb, re);
+  if (rc) return rc;
+  if (!diag || !b || !x_out || !omega || x_out == x_in) return GLAB_E_ARG;
+  return dispatch_k<T, EpiJacobi>(p, vals, x_in, k, rb, re, stream, [&](auto e) {
+    e.diag = diag; e.b = b; e.x = x_in; e.xo = x_out; e.omega = omega; return e; });
+}
+
+template <typename T>
+static int cheby_first(const glab_plan* p, const T* vals, const T* b, const T* x_in, T* x_out, T* r,
+                       T* pv, const T* alpha, int k, int64_t rb, int64_t re, void* stream) {
+  int rc = check_common(p, vals, x_in, rb, re);
+  if (rc) return rc;
+  if (!b || !x_out || !r || !pv || !alpha || x_out == x_in) return GLAB_E_ARG;
+  return dispatch_k<T, EpiChebyFirst>(p, vals, x_in, k, rb, re, stream, [&](auto e) {
+    e.b = b; e.x = x_in; e.xo = x_out; e.r_ = r; e.p_ = pv; e.alpha = alpha; return e; });
+}
+
+template <typename T>
+static int cheby_next(const glab_plan* p, const T* vals, const T* p_in, T* p_out, T* r, T* x,
+                      const T* alpha_old, const T* alpha, const T* beta, int k, int64_t rb,
+                      int64_t re, void* stream) {
+  int rc = check_common(p, vals, p_in, rb, re);
+  if (rc) return rc;
+  if (!p_out || !r || !x || !alpha_old || !alpha || !beta || p_out == p_in) return GLAB_E_ARG;
+  return dispatch_k<T, EpiChebyNext>(p, vals, p_in, k, rb, re, stream, [&](auto e) {
+    e.p_in = p_in; e.p_out = p_out; e.r_ = r; e.x_ = x;
+    e.alpha_old = alpha_old; e.alpha = alpha; e.beta = beta; return e; });
+}
+
+template <typename T, class Epi>
+static int launch_reducing(const glab_plan* p, const T* vals, const T* x, const Epi& epi,
+                           int64_t rb, int64_t re, void* stream) {
+  // rb == re still launches one (empty) tile so the output sums are written (as zeros).
+  if (tuning().rpt == 2) return launch_tiles<T, 1, 2>(p, vals, x, epi, rb, re, true, stream);
+  return launch_tiles<T, 1, 1>(p, vals, x, epi, rb, re, true, stream);
+}
+
+template <typename T>
+static int power_step(const glab_plan* p, const T* vals, const T* b_in, T* y, const double* ss_in,
+                      double* ss_out, void* ws, int64_t rb, int64_t re, void* stream) {
+  int rc = check_common(p, vals, b_in, rb, re);
+  if (rc) return rc;
+  if (!y || !ss_out || !ws || y == b_in) return GLAB_E_ARG;
+  EpiPower<T> e{y, ss_in, ss_out, ws};
+  return launch_reducing<T>(p, vals, b_in, e, rb, re, stream);
+}
+
+template <typename T>
+static int rayleigh(const glab_plan* p, const T* vals, const T* b_in, T* b_out, T* y_out,
+                    const double* ss_in, double* sums_out, void* ws, int64_t rb, int64_t re,
+                    void* stream) {
+  int rc = check_common(p, vals, b_in, rb, re);
+  if (rc) return rc;
+  if (!b_out || !y_out || !sums_out || !ws || b_out == b_in) return GLAB_E_ARG;
+  EpiRayleigh<T> e{b_in, b_out, y_out, ss_in, sums_out, ws};
+  return launch_reducing<T>(p, vals, b_in, e, rb, re, stream);
+}
+
+template <typename T>
+static int xtax(const glab_plan* p, const T* vals, const T* x, double* sums_out, void* ws,
+                int64_t rb, int64_t re, void* stream) {
+  int rc = check_common(p, vals, x, rb, re);
+  if (rc) return rc;
+  if (!sums_out || !ws) return GLAB_E_ARG;
+  EpiXtAx<T> e{x, sums_out, ws};
+  return launch_reducing<T>(p, vals, x, e, rb, re, stream);
+}
+
+}  // namespace glab
+
+using namespace glab;
+
+extern "C" int64_t glab_reduce_workspace_bytes(void) { return 64 + (int64_t)kMaxReduceBlocks * 2 * 8; }
+
+#define GLAB_INST(SUF, T)                                                                          \
+  extern "C" int glab_spmm_##SUF(const glab_plan* p, const T* v, const T* x, int k, T* y,          \
+                                 int64_t rb, int64_t re, void* s) {                                \
+    return spmm<T>(p, v, x, k, y, rb, re, s);                                                      \
+  }                                                                                                \
+  extern "C" int glab_residual_##SUF(const glab_plan* p, const T* v, const T* x, const T* b, int k, \
+                                     T* r, int64_t rb, int64_t re, void* s) {                      \
+    return residual<T>(p, v, x, b, k, r, rb, re, s);                                               \
+  }                                                                                                \
+  extern "C" int glab_spmm_add_##SUF(const glab_plan* p, const T* v, const T* x, const T* b, int k, \
+                                     T* o, int64_t rb, int64_t re, void* s) {                      \
+    return spmm_add<T>(p, v, x, b, k, o, rb, re, s);                                               \
+  }                                                                                                \
+  extern "C" int glab_jacobi_##SUF(const glab_plan* p, const T* v, const T* d, const T* b,         \
+                                   const T* xi, T* xo, const T* w, int k, int64_t rb, int64_t re,  \
+                                   void* s) {                                                      \
+    return jacobi<T>(p, v, d, b, xi, xo, w, k, rb, re, s);                                         \
+  }                                                                                                \
+  extern "C" int glab_cheby_first_##SUF(const glab_plan* p, const T* v, const T* b, const T* xi,   \
+                                        T* xo, T* r, T* pv, const T* a, int k, int64_t rb,         \
+                                        int64_t re, void* s) {                                     \
+    return cheby_first<T>(p, v, b, xi, xo, r, pv, a, k, rb, re, s);                                \
+  }                                                                                                \
+  extern "C" int glab_cheby_next_##SUF(const glab_plan* p, const T* v, const T* pi, T* po, T* r,   \
+                                       T* x, const T* ao, const T* a, const T* b, int k,           \
+                                       int64_t rb, int64_t re, void* s) {                          \
+    return cheby_next<T>(p, v, pi, po, r, x, ao, a, b, k, rb, re, s);                              \
+  }                                                                                                \
+  extern "C" int glab_power_step_##SUF(const glab_plan* p, const T* v, const T* bi, T* y,          \
+                                       const double* si, double* so, void* ws, int64_t rb,         \
+                                       int64_t re, void* s) {                                      \
+    return power_step<T>(p, v, bi, y, si, so, ws, rb, re, s);                                      \
+  }                                                                                                \
+  extern "C" int glab_rayleigh_##SUF(const glab_plan* p, const T* v, const T* bi, T* bo, T* yo,    \
+                                     const double* si, double* so, void* ws, int64_t rb,           \
+                                     int64_t re, void* s) {                                        \
+    return rayleigh<T>(p, v, bi, bo, yo, si, so, ws, rb, re, s);                                   \
+  }                                                                                                \
+  extern "C" int glab_xtax_##SUF(const glab_plan* p, const T* v, const T* x, double* so, void* ws, \
+                                 int64_t rb, int64_t re, void* s) {                                \
+    return xtax<T>(p, v, x, so, ws, rb, re, s);                                                    \
+  }
+
+GLAB_INST(f32, float)
+GLAB_INST(f64, double)

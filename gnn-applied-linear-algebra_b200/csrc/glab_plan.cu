@@ -1,0 +1,333 @@
+// glab_plan.cu -- int64 COO -> int32 CSR plan (+ stable permutation) on the device.
+//
+// Replaces the grouping that torch_scatter.scatter(index=edgeij_pair[0]) performs implicitly on
+// every call (reference call sites listed in include/glab.h).  The plan is built once per
+// operator and reused by every layer step.
+//
+// Fast path (all reference generators emit row-sorted COO, UtilsGNN.py:53-67,74-78): one pass
+// that validates indices and detects sortedness, one pass that writes rowptr from the row
+// boundaries (no histogram, no scan), one pass that narrows col to int32.  perm stays NULL.
+// Slow path (arbitrary edge order): stable LSD radix sort of (row, edge id) with CUB -- setup
+// only, never on a layer step -- then the same boundary pass.
+#include <cub/device/device_radix_sort.cuh>
+#include <new>
+#include "glab_common.cuh"
+
+namespace glab {
+
+// flags[0] bit0 = rows not sorted, bit1 = index out of range
+__global__ void k_validate(const int64_t* __restrict__ row, const int64_t* __restrict__ col,
+                           int64_t nnz, int64_t n_rows, int64_t n_cols, int* flags) {
+  int f = 0;
+  for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < nnz;
+       e += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = row[e], c = col[e];
+    if (r < 0 || r >= n_rows || c < 0 || c >= n_cols) f |= 2;
+    if (e > 0 && row[e - 1] > r) f |= 1;
+  }
+  if (f) atomicOr(flags, f);
+}
+
+// rows sorted ascending: rowptr[r] = first slot whose row is >= r.
+template <typename RowT>
+__global__ void k_rowptr_from_sorted(const RowT* __restrict__ row, int64_t nnz, int64_t n_rows,
+                                     int32_t* __restrict__ rowptr) {
+  for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e <= nnz;
+       e += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t prev = (e == 0) ? -1 : (int64_t)row[e - 1];
+    const int64_t cur = (e == nnz) ? n_rows : (int64_t)row[e];
+    for (int64_t r = prev + 1; r <= cur; ++r) rowptr[r] = (int32_t)e;
+  }
+}
+
+__global__ void k_narrow(const int64_t* __restrict__ src, int64_t n, int32_t* __restrict__ dst) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n;
+       i += (int64_t)gridDim.x * blockDim.x)
+    dst[i] = (int32_t)src[i];
+}
+
+__global__ void k_iota_rows(const int64_t* __restrict__ row, int64_t n, int32_t* __restrict__ keys,
+                            int32_t* __restrict__ ids) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    keys[i] = (int32_t)row[i];
+    ids[i] = (int32_t)i;
+  }
+}
+
+__global__ void k_permute_cols(const int64_t* __restrict__ col, const int32_t* __restrict__ perm,
+                               int64_t n, int32_t* __restrict__ dst) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n;
+       i += (int64_t)gridDim.x * blockDim.x)
+    dst[i] = (int32_t)col[perm[i]];
+}
+
+__global__ void k_max_row(const int32_t* __restrict__ rowptr, int64_t n_rows, int* out) {
+  int m = 0;
+  for (int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; r < n_rows;
+       r += (int64_t)gridDim.x * blockDim.x)
+    m = max(m, rowptr[r + 1] - rowptr[r]);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0 && m > 0) atomicMax(out, m);
+}
+
+__global__ void k_validate_csr(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col,
+                               int64_t n_rows, int64_t n_cols, int64_t nnz, int* flags) {
+  int f = 0;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < nnz;
+       i += (int64_t)gridDim.x * blockDim.x)
+    if (col[i] < 0 || col[i] >= n_cols) f |= 2;
+  for (int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; r < n_rows;
+       r += (int64_t)gridDim.x * blockDim.x)
+    if (rowptr[r + 1] < rowptr[r]) f |= 1;
+  if (blockIdx.x == 0 && threadIdx.x == 0 && (rowptr[0] != 0 || rowptr[n_rows] != nnz)) f |= 1;
+  if (f) atomicOr(flags, f);
+}
+
+template <typename T>
+__global__ void k_gather_vals(const T* __restrict__ edge_attr, int64_t ld, int64_t column,
+                              const int32_t* __restrict__ perm, int64_t nnz, T* __restrict__ vals) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < nnz;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t e = perm ? (int64_t)perm[i] : i;
+    vals[i] = edge_attr[e * ld + column];
+  }
+}
+
+template <typename T>
+__global__ void k_scatter_edges(const T* __restrict__ in, const int32_t* __restrict__ perm,
+                                int64_t nnz, T* __restrict__ out, int64_t ld, int64_t column) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < nnz;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t e = perm ? (int64_t)perm[i] : i;
+    out[e * ld + column] = in[i];
+  }
+}
+
+static int grid_for(int64_t n, int sm_count) {
+  int64_t b = (n + 255) / 256;
+  int64_t cap = (int64_t)sm_count * 16;
+  if (b < 1) b = 1;
+  return (int)(b < cap ? b : cap);
+}
+
+static void plan_free(glab_plan* p) {
+  if (!p) return;
+  if (p->rowptr) cudaFree(p->rowptr);
+  if (p->colidx) cudaFree(p->colidx);
+  if (p->perm) cudaFree(p->perm);
+  delete p;
+}
+
+static int plan_alloc(int64_t n_rows, int64_t n_cols, int64_t nnz, glab_plan** out) {
+  if (!out || n_rows < 0 || n_cols < 0 || nnz < 0) return GLAB_E_ARG;
+  if (nnz >= (int64_t)INT32_MAX - 64 || n_rows >= (int64_t)INT32_MAX - 64 ||
+      n_cols >= (int64_t)INT32_MAX - 64)
+    return GLAB_E_RANGE;
+  glab_plan* p = new (std::nothrow) glab_plan();
+  if (!p) return GLAB_E_NOMEM;
+  p->n_rows = n_rows;
+  p->n_cols = n_cols;
+  p->nnz = nnz;
+  p->rowptr = nullptr;
+  p->colidx = nullptr;
+  p->perm = nullptr;
+  p->max_row_nnz = 0;
+  cudaError_t e = cudaGetDevice(&p->device);
+  if (e == cudaSuccess)
+    e = cudaDeviceGetAttribute(&p->sm_count, cudaDevAttrMultiProcessorCount, p->device);
+  if (e == cudaSuccess) e = cudaMalloc(&p->rowptr, (size_t)(n_rows + 1 + 8) * sizeof(int32_t));
+  if (e == cudaSuccess) e = cudaMalloc(&p->colidx, (size_t)(nnz + 8) * sizeof(int32_t));
+  if (e != cudaSuccess) {
+    plan_free(p);
+    cudaGetLastError();
+    return e == cudaErrorMemoryAllocation ? GLAB_E_NOMEM : (int)e;
+  }
+  *out = p;
+  return 0;
+}
+
+}  // namespace glab
+
+using namespace glab;
+
+extern "C" int glab_version(void) { return GLAB_VERSION; }
+
+extern "C" const char* glab_error_string(int code) {
+  switch (code) {
+    case 0: return "ok";
+    case GLAB_E_ARG: return "glab: invalid argument";
+    case GLAB_E_RANGE: return "glab: index out of range or nnz >= 2^31";
+    case GLAB_E_NOMEM: return "glab: out of device memory";
+    case GLAB_E_UNSORTED: return "glab: input not row sorted";
+    case GLAB_E_PEER: return "glab: peer memory mapping failed";
+    default: return code > 0 ? cudaGetErrorString((cudaError_t)code) : "glab: unknown error";
+  }
+}
+
+extern "C" int glab_plan_create(int64_t n_rows, int64_t n_cols, int64_t nnz, const int64_t* row,
+                                const int64_t* col, void* stream_, glab_plan** out) {
+  if (nnz > 0 && (!row || !col)) return GLAB_E_ARG;
+  glab_plan* p = nullptr;
+  int rc = plan_alloc(n_rows, n_cols, nnz, &p);
+  if (rc) return rc;
+  cudaStream_t st = as_stream(stream_);
+  int* d_flags = nullptr;  // [0] validation flags, [1] max row nnz
+  int h_flags[2] = {0, 0};
+  int32_t* keys_in = nullptr;
+  int32_t* keys_out = nullptr;
+  int32_t* ids_in = nullptr;
+  void* tmp = nullptr;
+  cudaError_t e = cudaMalloc(&d_flags, 2 * sizeof(int));
+  auto fail = [&](int code) {
+    if (d_flags) cudaFree(d_flags);
+    if (keys_in) cudaFree(keys_in);
+    if (keys_out) cudaFree(keys_out);
+    if (ids_in) cudaFree(ids_in);
+    if (tmp) cudaFree(tmp);
+    plan_free(p);
+    cudaGetLastError();
+    return code;
+  };
+  if (e != cudaSuccess) return fail((int)e);
+  if ((e = cudaMemsetAsync(d_flags, 0, 2 * sizeof(int), st)) != cudaSuccess) return fail((int)e);
+  const int g = grid_for(nnz, p->sm_count);
+  if (nnz > 0) k_validate<<<g, 256, 0, st>>>(row, col, nnz, n_rows, n_cols, d_flags);
+  if ((e = cudaMemcpyAsync(h_flags, d_flags, sizeof(int), cudaMemcpyDeviceToHost, st)) !=
+      cudaSuccess)
+    return fail((int)e);
+  if ((e = cudaStreamSynchronize(st)) != cudaSuccess) return fail((int)e);
+  if (h_flags[0] & 2) return fail(GLAB_E_RANGE);
+
+  if (!(h_flags[0] & 1)) {
+    k_rowptr_from_sorted<int64_t><<<grid_for(nnz + 1, p->sm_count), 256, 0, st>>>(row, nnz, n_rows,
+                                                                                 p->rowptr);
+    if (nnz > 0) k_narrow<<<g, 256, 0, st>>>(col, nnz, p->colidx);
+  } else {
+    // stable sort of edge ids by row (LSD radix sort is stable)
+    size_t tmp_bytes = 0;
+    int bits = 1;
+    while (((int64_t)1 << bits) < n_rows) ++bits;
+    if ((e = cudaMalloc(&keys_in, (size_t)nnz * 4)) != cudaSuccess) return fail(GLAB_E_NOMEM);
+    if ((e = cudaMalloc(&keys_out, (size_t)nnz * 4)) != cudaSuccess) return fail(GLAB_E_NOMEM);
+    if ((e = cudaMalloc(&ids_in, (size_t)nnz * 4)) != cudaSuccess) return fail(GLAB_E_NOMEM);
+    if ((e = cudaMalloc(&p->perm, (size_t)(nnz + 8) * 4)) != cudaSuccess) return fail(GLAB_E_NOMEM);
+    k_iota_rows<<<g, 256, 0, st>>>(row, nnz, keys_in, ids_in);
+    cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, keys_in, keys_out, ids_in, p->perm,
+                                    (int)nnz, 0, bits, st);
+    if ((e = cudaMalloc(&tmp, tmp_bytes ? tmp_bytes : 16)) != cudaSuccess) return fail(GLAB_E_NOMEM);
+    e = cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, keys_in, keys_out, ids_in, p->perm,
+                                        (int)nnz, 0, bits, st);
+    if (e != cudaSuccess) return fail((int)e);
+    k_rowptr_from_sorted<int32_t><<<grid_for(nnz + 1, p->sm_count), 256, 0, st>>>(keys_out, nnz,
+                                                                                 n_rows, p->rowptr);
+    k_permute_cols<<<g, 256, 0, st>>>(col, p->perm, nnz, p->colidx);
+  }
+  if (n_rows > 0) k_max_row<<<grid_for(n_rows, p->sm_count), 256, 0, st>>>(p->rowptr, n_rows, d_flags + 1);
+  if ((e = cudaMemcpyAsync(h_flags + 1, d_flags + 1, sizeof(int), cudaMemcpyDeviceToHost, st)) !=
+      cudaSuccess)
+    return fail((int)e);
+  if ((e = cudaStreamSynchronize(st)) != cudaSuccess) return fail((int)e);
+  if ((e = cudaGetLastError()) != cudaSuccess) return fail((int)e);
+  p->max_row_nnz = h_flags[1];
+  cudaFree(d_flags);
+  if (keys_in) cudaFree(keys_in);
+  if (keys_out) cudaFree(keys_out);
+  if (ids_in) cudaFree(ids_in);
+  if (tmp) cudaFree(tmp);
+  *out = p;
+  return 0;
+}
+
+extern "C" int glab_plan_create_csr(int64_t n_rows, int64_t n_cols, int64_t nnz,
+                                    const int32_t* rowptr, const int32_t* colidx, void* stream_,
+                                    glab_plan** out) {
+  if (!rowptr || (nnz > 0 && !colidx)) return GLAB_E_ARG;
+  glab_plan* p = nullptr;
+  int rc = plan_alloc(n_rows, n_cols, nnz, &p);
+  if (rc) return rc;
+  cudaStream_t st = as_stream(stream_);
+  int* d_flags = nullptr;
+  int h_flags[2] = {0, 0};
+  cudaError_t e = cudaMalloc(&d_flags, 2 * sizeof(int));
+  auto fail = [&](int code) {
+    if (d_flags) cudaFree(d_flags);
+    plan_free(p);
+    cudaGetLastError();
+    return code;
+  };
+  if (e != cudaSuccess) return fail((int)e);
+  cudaMemsetAsync(d_flags, 0, 2 * sizeof(int), st);
+  cudaMemcpyAsync(p->rowptr, rowptr, (size_t)(n_rows + 1) * 4, cudaMemcpyDeviceToDevice, st);
+  if (nnz > 0) cudaMemcpyAsync(p->colidx, colidx, (size_t)nnz * 4, cudaMemcpyDeviceToDevice, st);
+  k_validate_csr<<<grid_for(nnz > n_rows ? nnz : n_rows, p->sm_count), 256, 0, st>>>(
+      p->rowptr, p->colidx, n_rows, n_cols, nnz, d_flags);
+  if (n_rows > 0) k_max_row<<<grid_for(n_rows, p->sm_count), 256, 0, st>>>(p->rowptr, n_rows, d_flags + 1);
+  if ((e = cudaMemcpyAsync(h_flags, d_flags, 2 * sizeof(int), cudaMemcpyDeviceToHost, st)) !=
+      cudaSuccess)
+    return fail((int)e);
+  if ((e = cudaStreamSynchronize(st)) != cudaSuccess) return fail((int)e);
+  if ((e = cudaGetLastError()) != cudaSuccess) return fail((int)e);
+  if (h_flags[0]) return fail(GLAB_E_RANGE);
+  p->max_row_nnz = h_flags[1];
+  cudaFree(d_flags);
+  *out = p;
+  return 0;
+}
+
+extern "C" int glab_plan_destroy(glab_plan* plan) {
+  plan_free(plan);
+  return 0;
+}
+
+extern "C" int glab_plan_info(const glab_plan* p, int64_t* n_rows, int64_t* n_cols, int64_t* nnz,
+                              int32_t* max_row_nnz, int32_t* identity_perm) {
+  if (!p) return GLAB_E_ARG;
+  if (n_rows) *n_rows = p->n_rows;
+  if (n_cols) *n_cols = p->n_cols;
+  if (nnz) *nnz = p->nnz;
+  if (max_row_nnz) *max_row_nnz = p->max_row_nnz;
+  if (identity_perm) *identity_perm = p->perm ? 0 : 1;
+  return 0;
+}
+
+extern "C" int glab_plan_csr(const glab_plan* p, const int32_t** rowptr, const int32_t** colidx,
+                             const int32_t** perm) {
+  if (!p) return GLAB_E_ARG;
+  if (rowptr) *rowptr = p->rowptr;
+  if (colidx) *colidx = p->colidx;
+  if (perm) *perm = p->perm;
+  return 0;
+}
+
+template <typename T>
+static int gather_vals(const glab_plan* p, const T* edge_attr, int64_t ld, int64_t column, T* vals,
+                       void* stream) {
+  if (!p || !vals || (p->nnz > 0 && !edge_attr) || ld < 1 || column < 0 || column >= ld)
+    return GLAB_E_ARG;
+  if (p->nnz == 0) return 0;
+  k_gather_vals<T><<<grid_for(p->nnz, p->sm_count), 256, 0, as_stream(stream)>>>(
+      edge_attr, ld, column, p->perm, p->nnz, vals);
+  return (int)cudaGetLastError();
+}
+
+template <typename T>
+static int scatter_edges(const glab_plan* p, const T* in, T* out, int64_t ld, int64_t column,
+                         void* stream) {
+  if (!p || (p->nnz > 0 && (!in || !out)) || ld < 1 || column < 0 || column >= ld)
+    return GLAB_E_ARG;
+  if (p->nnz == 0) return 0;
+  k_scatter_edges<T><<<grid_for(p->nnz, p->sm_count), 256, 0, as_stream(stream)>>>(
+      in, p->perm, p->nnz, out, ld, column);
+  return (int)cudaGetLastError();
+}
+
+extern "C" int glab_gather_vals_f32(const glab_plan* p, const float* ea, int64_t ld, int64_t c,
+                                    float* v, void* s) { return gather_vals<float>(p, ea, ld, c, v, s); }
+extern "C" int glab_gather_vals_f64(const glab_plan* p, const double* ea, int64_t ld, int64_t c,
+                                    double* v, void* s) { return gather_vals<double>(p, ea, ld, c, v, s); }
+extern "C" int glab_scatter_edges_f32(const glab_plan* p, const float* in, float* out, int64_t ld,
+                                      int64_t c, void* s) { return scatter_edges<float>(p, in, out, ld, c, s); }
+extern "C" int glab_scatter_edges_f64(const glab_plan* p, const double* in, double* out, int64_t ld,
+                                      int64_t c, void* s) { return scatter_edges<double>(p, in, out, ld, c, s); }

@@ -1,0 +1,254 @@
+/*
+ * glab.h -- C ABI of libglab_b200.so: the B200 (sm_100a) edge-wise message-passing hot path
+ * behind the GNN-as-linear-algebra layers of sandialabs/gnn-applied-linear-algebra.
+ *
+ * The reference has no FFI of its own: its seam is the Python call
+ *     torch_scatter.scatter(src, edgeij_pair[0], dim=0, dim_size=n, reduce=...)
+ * inside each layer's edge->vertex aggregation, wrapped by torch_geometric.nn.MetaLayer
+ * (gather x[row], x[col] -> edge update -> aggregation -> vertex update -> global update).
+ * Every entry point below replaces one such (gather + edge update + scatter + vertex update)
+ * chain with ONE fused kernel launch; the citation on each function names the reference
+ * lines it replaces (paths relative to <reference>/pytorch/).
+ *
+ * Conventions
+ *   - extern "C", plain pointers and sizes, no C++/torch types.
+ *   - every function returns int: 0 = ok, >0 = cudaError_t, <0 = GLAB_E_* argument error.
+ *     Nothing throws, nothing aborts, nothing synchronises the device unless documented.
+ *   - all data pointers are BORROWED DEVICE pointers (owned by the caller, e.g. torch tensors);
+ *     the library allocates only inside opaque plans (glab_plan_*, glab_halo_*).
+ *   - `stream` is a cudaStream_t passed as void* (torch.cuda.current_stream().cuda_stream).
+ *   - dense vectors are row-major [n, k] with leading dimension k (k = number of RHS columns,
+ *     k in {1,2,4,8}); per-edge arrays are in CSR slot order unless the name says `edge order`.
+ *   - scalars that the reference keeps in the global attribute tensor `g` (omega, alpha, beta,
+ *     1/norm) are read through DEVICE pointers so no step ever needs a host sync.
+ *   - floating point: element-wise chains use IEEE mul/add/div in the reference's operation
+ *     order with FMA contraction disabled, and row sums accumulate sequentially in edge order
+ *     (the order of scatter_add_), so results match the reference's CPU path bit for bit
+ *     wherever the reference itself is order-deterministic.
+ */
+#ifndef GLAB_H_
+#define GLAB_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GLAB_VERSION 100
+
+#define GLAB_E_ARG      (-1)  /* null pointer / negative size / unsupported k                    */
+#define GLAB_E_RANGE    (-2)  /* nnz >= 2^31, row/col index outside [0, n)                       */
+#define GLAB_E_NOMEM    (-3)  /* plan allocation failed                                          */
+#define GLAB_E_UNSORTED (-4)  /* (internal) input not row-sorted and sorting was disabled        */
+#define GLAB_E_PEER     (-5)  /* peer (IPC) mapping failed                                       */
+
+typedef struct glab_plan glab_plan;   /* opaque: int32 CSR structure of one operator on one GPU */
+typedef struct glab_halo glab_halo;   /* opaque: peer-memory halo exchange of one row block     */
+
+int glab_version(void);
+const char* glab_error_string(int code);
+
+/* ------------------------------------------------------------------------------------------
+ * Plan: int64 COO (edgeij_pair[0] = aggregation target i, edgeij_pair[1] = source j) ->
+ * int32 CSR + stable permutation.  Replaces the implicit grouping done by
+ * scatter(index=edgeij_pair[0]) at every call site (MatVecGNN.py:60, GNNResidual.py:60,
+ * JacobiGNN.py:66, ChebyGNN.py:87, PowerMethodGNN.py:80, SOCClassicGNN.py:69,
+ * DirectInterpGNN.py:89,92) and the x[row]/x[col] gathers of MetaLayer.
+ * Arbitrary edge order and duplicate (i,j) pairs are accepted; within a row the CSR keeps the
+ * caller's edge order (stable), so duplicates are summed in the order scatter_add_ would.
+ * Synchronises `stream` once (it must read back nnz statistics).  ncols = length of the
+ * vectors that get gathered (n for a square operator; > n_rows for a row block with halo).
+ * ------------------------------------------------------------------------------------------ */
+int glab_plan_create(int64_t n_rows, int64_t n_cols, int64_t nnz,
+                     const int64_t* row, const int64_t* col, void* stream, glab_plan** out);
+/* Same, from an existing int32 CSR (device pointers are copied into the plan). */
+int glab_plan_create_csr(int64_t n_rows, int64_t n_cols, int64_t nnz,
+                         const int32_t* rowptr, const int32_t* colidx, void* stream,
+                         glab_plan** out);
+int glab_plan_destroy(glab_plan* plan);
+/* Introspection.  perm == NULL means "identity" (input was already row-sorted). */
+int glab_plan_info(const glab_plan* plan, int64_t* n_rows, int64_t* n_cols, int64_t* nnz,
+                   int32_t* max_row_nnz, int32_t* identity_perm);
+int glab_plan_csr(const glab_plan* plan, const int32_t** rowptr, const int32_t** colidx,
+                  const int32_t** perm);
+/* vals[slot] = edge_attr[perm[slot]*ld + column]  (CSR-ordered contiguous copy of A_ij). */
+int glab_gather_vals_f32(const glab_plan* plan, const float* edge_attr, int64_t ld, int64_t column,
+                         float* vals, void* stream);
+int glab_gather_vals_f64(const glab_plan* plan, const double* edge_attr, int64_t ld, int64_t column,
+                         double* vals, void* stream);
+/* out_edge_order[perm[slot]*ld + column] = in_slot_order[slot]  (inverse of the above). */
+int glab_scatter_edges_f32(const glab_plan* plan, const float* in_slots, float* out_edges,
+                           int64_t ld, int64_t column, void* stream);
+int glab_scatter_edges_f64(const glab_plan* plan, const double* in_slots, double* out_edges,
+                           int64_t ld, int64_t column, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Fused SpMV-bearing layer steps.  Common arguments: plan, vals[nnz] (CSR order), k columns,
+ * [row_begin,row_end) = rows to process (pass 0, n_rows for all; used for interior/boundary
+ * overlap with the halo exchange).  Gathered vectors have n_cols rows, the others n_rows.
+ * ------------------------------------------------------------------------------------------ */
+
+/* y = A x.  Replaces MatVecGNN.py:66-84 (c_ij = A_ij x_j), :43-62 (sum_j), :95-114. */
+int glab_spmm_f32(const glab_plan*, const float* vals, const float* x, int k, float* y,
+                  int64_t row_begin, int64_t row_end, void* stream);
+int glab_spmm_f64(const glab_plan*, const double* vals, const double* x, int k, double* y,
+                  int64_t row_begin, int64_t row_end, void* stream);
+
+/* r = b - A x.  Replaces GNNResidual.py:64-86, :43-62, :88-118. */
+int glab_residual_f32(const glab_plan*, const float* vals, const float* x, const float* b, int k,
+                      float* r, int64_t row_begin, int64_t row_end, void* stream);
+int glab_residual_f64(const glab_plan*, const double* vals, const double* x, const double* b, int k,
+                      double* r, int64_t row_begin, int64_t row_end, void* stream);
+
+/* out = b + A x  (may alias b).  The coarse-grid correction x + P xc of VCycle.py:226. */
+int glab_spmm_add_f32(const glab_plan*, const float* vals, const float* x, const float* b, int k,
+                      float* out, int64_t row_begin, int64_t row_end, void* stream);
+int glab_spmm_add_f64(const glab_plan*, const double* vals, const double* x, const double* b, int k,
+                      double* out, int64_t row_begin, int64_t row_end, void* stream);
+
+/* x_out = x_in + (omega*(b - A x_in))/diag  (one weighted-Jacobi sweep; x_out != x_in).
+ * Replaces JacobiGNN.py:71-89, :52-69, :91-123 (op order of :119).  diag is [n_rows] (shared by
+ * all k columns), omega_dev points to ONE device scalar (g[0], :112). */
+int glab_jacobi_f32(const glab_plan*, const float* vals, const float* diag, const float* b,
+                    const float* x_in, float* x_out, const float* omega_dev, int k,
+                    int64_t row_begin, int64_t row_end, void* stream);
+int glab_jacobi_f64(const glab_plan*, const double* vals, const double* diag, const double* b,
+                    const double* x_in, double* x_out, const double* omega_dev, int k,
+                    int64_t row_begin, int64_t row_end, void* stream);
+
+/* Chebyshev iteration 1:  r = b - A x_in;  p = r;  x_out = x_in + alpha*p.
+ * Replaces ChebyGNN.py:49-70, :73-89, :91-121, :141-163.  alpha_dev -> 1/d (:137). */
+int glab_cheby_first_f32(const glab_plan*, const float* vals, const float* b, const float* x_in,
+                         float* x_out, float* r, float* p, const float* alpha_dev, int k,
+                         int64_t row_begin, int64_t row_end, void* stream);
+int glab_cheby_first_f64(const glab_plan*, const double* vals, const double* b, const double* x_in,
+                         double* x_out, double* r, double* p, const double* alpha_dev, int k,
+                         int64_t row_begin, int64_t row_end, void* stream);
+
+/* Chebyshev iteration > 1:  r -= alpha_old*(A p_in);  p_out = r + beta*p_in;  x += alpha*p_out
+ * (r and x updated in place, p ping-pongs).  Replaces ChebyGNN.py:166-183, :186-216, :219-243;
+ * alpha_old is the previous iteration's alpha because MetaLayer runs the vertex update before
+ * the global update (:214 vs :262-263). */
+int glab_cheby_next_f32(const glab_plan*, const float* vals, const float* p_in, float* p_out,
+                        float* r, float* x, const float* alpha_old_dev, const float* alpha_dev,
+                        const float* beta_dev, int k, int64_t row_begin, int64_t row_end,
+                        void* stream);
+int glab_cheby_next_f64(const glab_plan*, const double* vals, const double* p_in, double* p_out,
+                        double* r, double* x, const double* alpha_old_dev, const double* alpha_dev,
+                        const double* beta_dev, int k, int64_t row_begin, int64_t row_end,
+                        void* stream);
+
+/* Power-method step with deferred normalisation:
+ *     y = (A b_in) / n,   n = sqrt(sumsq_in[0]) if sumsq_in != NULL, else 1;
+ *     sumsq_out[0] = sum_i y_i^2   (fp64 accumulation, deterministic two-level reduction).
+ * b_in is the previous step's UN-normalised y and sumsq_in its squared norm, so
+ * (A b_in)/n == A (b_in/n): the reference's b <- b/n (PowerMethodGNN.py:187-207) is folded into
+ * the next step and never costs a pass over the vector.  Replaces PowerMethodGNN.py:86-106,
+ * :64-83, :129-158 (b <- A b), :109-126 (y = b^2), :160-185 (n = sqrt(sum y)).
+ * `workspace` = device scratch of glab_reduce_workspace_bytes() bytes, zero-initialised once
+ * by the caller and then reusable by any number of stream-ordered calls. */
+int64_t glab_reduce_workspace_bytes(void);
+int glab_power_step_f32(const glab_plan*, const float* vals, const float* b_in, float* y,
+                        const double* sumsq_in, double* sumsq_out, void* workspace,
+                        int64_t row_begin, int64_t row_end, void* stream);
+int glab_power_step_f64(const glab_plan*, const double* vals, const double* b_in, double* y,
+                        const double* sumsq_in, double* sumsq_out, void* workspace,
+                        int64_t row_begin, int64_t row_end, void* stream);
+
+/* Rayleigh step:  bn = b_in / n (n as above);  Ab = (A b_in) / n;  y_out = bn*bn;
+ *     sums_out[0] = sum bn_i*Ab_i   (n_A, PowerMethodGNN.py:235,:264)
+ *     sums_out[1] = sum bn_i^2      (:124,:292)
+ * b_out receives bn (the normalised iterate the reference returns in vertex_attr[:,0]).
+ * Replaces PowerMethodGNN.py:209-237, :239-266, :268-294. */
+int glab_rayleigh_f32(const glab_plan*, const float* vals, const float* b_in, float* b_out,
+                      float* y_out, const double* sumsq_in, double* sums_out, void* workspace,
+                      int64_t row_begin, int64_t row_end, void* stream);
+int glab_rayleigh_f64(const glab_plan*, const double* vals, const double* b_in, double* b_out,
+                      double* y_out, const double* sumsq_in, double* sums_out, void* workspace,
+                      int64_t row_begin, int64_t row_end, void* stream);
+
+/* Matrix-weighted norm pieces: sums_out[0] = sum_i x_i*(W x)_i.  MatrixWeightedNorm.py:49-161. */
+int glab_xtax_f32(const glab_plan*, const float* vals, const float* x, double* sums_out,
+                  void* workspace, int64_t row_begin, int64_t row_end, void* stream);
+int glab_xtax_f64(const glab_plan*, const double* vals, const double* x, double* sums_out,
+                  void* workspace, int64_t row_begin, int64_t row_end, void* stream);
+
+/* c_slot = A_slot * x[col(slot)] for every edge (the `c_ij` / `z_ij` column the reference
+ * layers return in edge_attr, e.g. MatVecGNN.py:80-84).  Written straight to the caller's
+ * [nnz, ld] edge-order array at column `column` (k consecutive columns for k-column x). */
+int glab_edge_messages_f32(const glab_plan*, const float* vals, const float* x, int k,
+                           float* out_edges, int64_t ld, int64_t column, void* stream);
+int glab_edge_messages_f64(const glab_plan*, const double* vals, const double* x, int k,
+                           double* out_edges, int64_t ld, int64_t column, void* stream);
+
+/* The reference's seam itself, for callers that compose their own graph-network blocks:
+ *   segment_sum: out[i, :] = sum over the edges e with edgeij_pair[0][e] == i of src[e, :]
+ *                == torch_scatter.scatter(src, edgeij_pair[0], dim=0, dim_size=n, reduce="sum")
+ *                (MatVecGNN.py:60 and the other call sites), sequential in edge order;
+ *   segment_max: reduce="max" with 0 for rows without edges (SOCClassicGNN.py:69).
+ * src is [nnz, k] (k in {1,2,4,8}) contiguous in CSR slot order (use glab_gather_vals_* first
+ * when the plan's permutation is not the identity). */
+int glab_segment_sum_f32(const glab_plan*, const float* src_slots, int k, float* out, void* stream);
+int glab_segment_sum_f64(const glab_plan*, const double* src_slots, int k, double* out, void* stream);
+int glab_segment_max_f32(const glab_plan*, const float* src_slots, float* out, void* stream);
+int glab_segment_max_f64(const glab_plan*, const double* src_slots, double* out, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * AMG setup kernels (row-local, one pass).  Per-edge outputs are written in the caller's
+ * ORIGINAL edge order (out[perm[slot]]).
+ * ------------------------------------------------------------------------------------------ */
+
+/* Classical strength of connection on off-diagonal edges:
+ *     v_i = max_k(-A_ik) (0 for empty rows);  S = relu(((-1*A_ij)/v_i) - theta).
+ * Replaces SOCClassicGNN.py:50-72, :74-102, :104-129.  rowmax_out may be NULL. */
+int glab_soc_classic_f32(const glab_plan*, const float* vals, float theta, float* S_edges,
+                         float* rowmax_out, void* stream);
+int glab_soc_classic_f64(const glab_plan*, const double* vals, double theta, double* S_edges,
+                         double* rowmax_out, void* stream);
+
+/* Smoothed-aggregation strength measure S_ij = (A_ij*A_ij)/(A_ii*A_jj); no threshold.
+ * Replaces SOCSAGNN.py:49-71.  diag has n_cols entries. */
+int glab_soc_sa_f32(const glab_plan*, const float* vals, const float* diag, float* S_edges,
+                    void* stream);
+int glab_soc_sa_f64(const glab_plan*, const double* vals, const double* diag, double* S_edges,
+                    void* stream);
+
+/* Direct interpolation weights:
+ *     num_i = sum_k A_ik;  den_i = sum_k (A_ik*S_ik)*C_k;  alpha_i = (1/A_ii)*(num_i/den_i);
+ *     w_ij = (1 - C_i)*((-A_ij)*alpha_i)        for EVERY edge (NaN = 0*inf kept, see header).
+ * Replaces DirectInterpGNN.py:50-69, :71-97, :99-131, :133-152.  S[nnz] in CSR slot order,
+ * Cflag has n_cols entries (1 = coarse), diag n_rows entries. */
+int glab_direct_interp_f32(const glab_plan*, const float* vals, const float* S, const float* diag,
+                           const float* Cflag, float* w_edges, void* stream);
+int glab_direct_interp_f64(const glab_plan*, const double* vals, const double* S,
+                           const double* diag, const double* Cflag, double* w_edges, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Multi-GPU halo exchange over NVLink peer memory (one process per GPU).  Each rank owns a
+ * contiguous row block; gathered vectors are [n_local + n_halo, k] with the halo tail filled
+ * from the owners.  The exchange is a PUSH: a pack kernel stores this rank's boundary values
+ * straight into the peers' halo tails through mapped peer pointers, followed by a release flag;
+ * consumers wait on the flag in-stream (no NCCL call on the data path).
+ * ------------------------------------------------------------------------------------------ */
+int glab_ipc_handle_bytes(void);
+/* Allocate a device buffer that peers can map; writes an opaque handle (glab_ipc_handle_bytes()). */
+int glab_ipc_alloc(int64_t bytes, void** dev_ptr, void* handle_out);
+int glab_ipc_open(const void* handle, void** peer_ptr);
+int glab_ipc_close(void* peer_ptr);
+int glab_ipc_free(void* dev_ptr);
+/* dst_peer[dst_offset + i, :] = src[send_idx[i], :] for i < count (k columns, T = f32/f64),
+ * then (if flag_peer != NULL) a system-scope release store of `flag_value` to *flag_peer. */
+int glab_halo_push_f32(const float* src, const int32_t* send_idx, int64_t count, int k,
+                       float* dst_peer, int64_t dst_offset, uint32_t* flag_peer,
+                       uint32_t flag_value, void* stream);
+int glab_halo_push_f64(const double* src, const int32_t* send_idx, int64_t count, int k,
+                       double* dst_peer, int64_t dst_offset, uint32_t* flag_peer,
+                       uint32_t flag_value, void* stream);
+/* In-stream wait until *flag_local >= flag_value (written by a peer's push). */
+int glab_halo_wait(uint32_t* flag_local, uint32_t flag_value, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GLAB_H_ */

@@ -1,0 +1,44 @@
+import os
+import sys
+import warnings
+
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+warnings.filterwarnings("ignore", message=".*Sparse.*")
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
+
+
+@pytest.fixture(scope="session")
+def golden():
+    path = os.path.join(ROOT, "tests", "golden", "reference_layers.pt")
+    return torch.load(path, weights_only=False)
+
+
+@pytest.fixture(scope="session")
+def G():
+    import glab_b200
+    return glab_b200
+
+
+@pytest.fixture(scope="session")
+def dev():
+    assert torch.cuda.is_available(), "gpu-marked test without a GPU"
+    return torch.device("cuda:0")
+
+
+def same(a, b):
+    """Bit-for-bit equality including NaN positions, shape and dtype."""
+    return (a.shape == b.shape and a.dtype == b.dtype and torch.equal(torch.isnan(a), torch.isnan(b))
+            and torch.equal(torch.nan_to_num(a, nan=0.0), torch.nan_to_num(b, nan=0.0)))
+
+
+def relerr(a, b):
+    a, b = a.double(), b.double()
+    return ((a - b).norm() / b.norm().clamp_min(1e-300)).item()

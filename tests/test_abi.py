@@ -1,0 +1,52 @@
+"""CPU: the C-ABI shared library loads and exports every symbol include/glab.h declares; the
+host package binds them all; argument errors come back as codes (no compute without a GPU)."""
+import ctypes
+import os
+import re
+
+from conftest import ROOT
+
+
+def _declared():
+    src = open(os.path.join(ROOT, "include", "glab.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(glab_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_header_symbols_exported(G):
+    names = _declared()
+    assert len(names) >= 45
+    lib = ctypes.CDLL(G.LIB_PATH)
+    for n in names:
+        assert hasattr(lib, n), "libglab_b200.so does not export %s" % n
+
+
+def test_python_binds_every_symbol(G):
+    bound = set(G._lib.exported_symbols())
+    assert set(_declared()) <= bound, sorted(set(_declared()) - bound)
+
+
+def test_version_and_error_strings(G):
+    assert G.lib.glab_version() == 100
+    assert b"invalid argument" in G.lib.glab_error_string(-1)
+    assert G.lib.glab_error_string(0) == b"ok"
+    # argument validation happens before any CUDA call
+    assert G.lib.glab_plan_info(None, None, None, None, None, None) == -1
+    assert G.lib.glab_spmm_f32(None, None, None, 1, None, 0, 0, None) == -1
+    assert G.lib.glab_halo_wait(None, 0, None) == -1
+
+
+def test_sass_is_sm100a(G):
+    import subprocess
+    out = subprocess.run(["cuobjdump", "-lelf", G.LIB_PATH], capture_output=True, text=True).stdout
+    assert "sm_100a" in out
+
+
+def test_no_cpu_fallback(G):
+    import pytest
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with pytest.raises(G.GlabError):
+        G.JacobiGNN.JacobiGNN()(1, torch.zeros(4, 3), torch.zeros(2, 4, dtype=torch.long), torch.zeros(4, 2),
+                                torch.tensor([0.7]))
