@@ -1,0 +1,331 @@
+#!/usr/bin/env python
+"""bench.py -- fused SpMV-layer throughput (nnz/s) and HBM-roofline fraction on B200.
+
+Workload (BASELINE.json configs[1]): JacobiGNN (10 sweeps, w = 0.7) + ChebyRelaxGNN (degree 4,
+c = -3.4, d = -4) smoothing on the 4096 x 4096 5-point Laplacian (16.7 M rows, 83.9 M nnz), fp32.
+One "step" = one smoothing pass = 14 fused SpMV-bearing layer launches (10 glab_jacobi +
+1 glab_cheby_first + 3 glab_cheby_next).  metric value = 14 * nnz / step time.
+
+  value     kernels only, operator + vectors resident in HBM (C-ABI calls on torch's stream)
+  e2e       through the drop-in layer API: per step the vectors are copied from PINNED HOST
+            memory to the GPU, JacobiGNN.forward + ChebyRelaxGNN.forward run (including the
+            returned edge_attr message column), and the result x is read back to the host.
+            The operator (edge list + CSR plan) is step-invariant and stays resident, like
+            model weights.
+  roofline  dominant kernel = glab_jacobi: algorithmic bytes z(4+s)+4(n+1)+4ns per launch over
+            its CUDA-event time, against MEASURED_PEAKS.json hbm_gbs.
+  cpu_baseline / --impl reference
+            the reference's own layer code (oracle/ref_loader.py when /root/reference exists,
+            else the bit-exact restatement oracle/port.py) on the host cores, on a bounded sample.
+
+N > 1 (torchrun): the same operator row-block partitioned across ranks (strong scaling), halo
+rows pushed over NVLink peer memory each sweep.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+GRID = {"L4096": 4096, "L8192": 8192, "L2048": 2048, "L1024": 1024, "L256": 256}
+N_JACOBI, CHEB_DEG, OMEGA, CHEB_C, CHEB_D = 10, 4, 0.7, -3.4, -4.0
+LAUNCHES_PER_STEP = N_JACOBI + CHEB_DEG
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.isfile(path):
+        return float(json.load(open(path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def committed_traffic():
+    """dram bytes per glab_jacobi launch from the committed ncu --set full capture, or None."""
+    path = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.isfile(path):
+        return json.load(open(path))
+    return None
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.idx = gpu_index
+        self.proc = None
+        self.path = None
+
+    def start(self):
+        try:
+            fd, self.path = tempfile.mkstemp(suffix=".csv")
+            os.close(fd)
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                 "-lms", "100"], stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.proc is None:
+            return out
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        try:
+            for line in open(self.path):
+                f = [t.strip() for t in line.split(",")]
+                if len(f) < 9:
+                    continue
+                try:
+                    sm.append(float(f[1]))
+                    mx.append(float(f[2]))
+                except ValueError:
+                    continue
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            os.unlink(self.path)
+        except Exception:
+            pass
+        if sm:
+            sm.sort()
+            out.update(sm_mhz=sm[len(sm) // 2], sm_max_mhz=max(mx), samples=len(sm), reasons=sorted(reasons))
+        return out
+
+
+def jacobi_bytes(n, z, s=4, k=1):
+    return z * (4 + s) + 4 * (n + 1) + (3 * k + 1) * n * s
+
+
+def cheby_first_bytes(n, z, s=4, k=1):
+    return z * (4 + s) + 4 * (n + 1) + 5 * n * k * s
+
+
+def cheby_next_bytes(n, z, s=4, k=1):
+    return z * (4 + s) + 4 * (n + 1) + 6 * n * k * s
+
+
+# ------------------------------------------------------------------------------- reference arm
+def run_cpu_reference(workload, steps, warmup, sample_jacobi=2, sample_cheb=2):
+    """Times the reference's own CPU implementation of the path on a bounded sample of the
+    workload: `sample_jacobi` Jacobi sweeps + Chebyshev degree `sample_cheb` on the full operator."""
+    from oracle import port, ref_loader
+    N = GRID[workload]
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    torch.manual_seed(24601)
+    n = N * N
+    ei, ev = port.laplacian_2d(N)
+    ev = ev.float()
+    z = ei.shape[1]
+    b, x = torch.rand(n, 1), torch.rand(n, 1)
+    va = torch.cat([-4 * torch.ones(n, 1), b, x], 1)
+    ea = torch.cat([ev, torch.zeros_like(ev)], 1)
+    gw = torch.tensor(OMEGA).reshape(-1)
+    gc = torch.tensor([CHEB_C, CHEB_D])
+    if ref_loader.available():
+        R = ref_loader.load()
+        kind = "reference"
+        jac = R.JacobiGNN.JacobiGNN()
+        cheb = R.ChebyGNN.ChebyRelaxGNN(sample_cheb)
+
+        def one():
+            x1 = jac(sample_jacobi, va, ei, ea, gw)
+            return cheb(torch.cat([b, x1], 1), ei, ev, gc)[0]
+    else:
+        kind = "port"
+
+        def one():
+            x1 = port.jacobi(sample_jacobi, va, ei, ea, gw)
+            return port.chebyshev(sample_cheb, torch.cat([b, x1], 1), ei, ev, gc)[0]
+
+    for _ in range(warmup):
+        one()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        one()
+    dt = (time.perf_counter() - t0) / max(steps, 1)
+    layers = sample_jacobi + sample_cheb
+    return {"value": layers * z / dt, "ms_per_step": dt * 1e3, "cores": cores, "kind": kind, "n": n, "nnz": z,
+            "sample": "%d of %d Jacobi sweeps + Chebyshev degree %d of %d on the full %s operator "
+                      "(%d SpMV-bearing GN blocks per step)" % (sample_jacobi, N_JACOBI, sample_cheb, CHEB_DEG,
+                                                               workload, layers)}
+
+
+def main_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    steps = max(1, min(args.steps, 3))
+    warm = max(0, min(args.warmup, 1))
+    r = run_cpu_reference(args.workload, steps, warm)
+    line = {"impl": "reference", "metric": "fused SpMV-layer nnz/s", "value": r["value"], "unit": "nnz/s",
+            "n_gpus": args.gpus, "steps": steps, "warmup": warm, "ms_per_step": r["ms_per_step"],
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic", "config": workload_config(args.workload, r["n"], r["nnz"], args.gpus),
+            "cpu_baseline": {"value": r["value"], "unit": "nnz/s", "cores": r["cores"], "kind": r["kind"],
+                             "sample": r["sample"]},
+            "e2e": {"value": r["value"], "unit": "nnz/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+    return 0
+
+
+def workload_config(workload, n, z, gpus):
+    N = GRID[workload]
+    return {"workload": "%s: JacobiGNN(10 sweeps, w=0.7) + ChebyRelaxGNN(deg 4, c=-3.4, d=-4) on the %dx%d "
+                        "5-point Laplacian" % (workload, N, N),
+            "rows": n, "nnz": z, "rhs_columns": 1,
+            "fused_layer_launches_per_step": LAUNCHES_PER_STEP,
+            "partition": "single GPU" if gpus == 1 else "1-D row blocks over %d GPUs, halo push over NVLink peer memory" % gpus,
+            "l2": "inputs larger than L2 (CSR %.0f MB + vectors; 126 MB L2), no flush needed" % (z * 8 / 1e6),
+            "e2e_operator": "edge list + CSR plan resident (step-invariant); vectors H2D from pinned host and x D2H every step"}
+
+
+# ------------------------------------------------------------------------------- GPU arm
+def main_gpu(args):
+    import glab_b200 as G
+    rt = G.runtime
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit("--gpus %d needs torchrun with %d ranks" % (args.gpus, args.gpus))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+    N = GRID[args.workload]
+    n_global = N * N
+    torch.manual_seed(24601)
+
+    if world == 1:
+        from bench_support import SingleGpuSmoother
+        prob = SingleGpuSmoother(G, N, dev)
+    else:
+        from bench_support import PartitionedSmoother
+        prob = PartitionedSmoother(G, N, dev, rank, world)
+    z_global = prob.nnz_global
+
+    def barrier():
+        if world > 1:
+            import torch.distributed as dist
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---------------- kernels only (value) + roofline of the dominant kernel
+    for _ in range(args.warmup):
+        prob.step_kernels()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    jac_events = []
+    launches0 = rt.launch_count
+    barrier()
+    ev0.record()
+    for _ in range(args.steps):
+        jac_events.append(prob.step_kernels(time_jacobi=True))
+    ev1.record()
+    barrier()
+    launches = rt.launch_count - launches0
+    ms_total = ev0.elapsed_time(ev1)
+    jac_ms = sum(a.elapsed_time(b) for a, b in jac_events) / (len(jac_events) * N_JACOBI)
+
+    # ---------------- end to end through the layer API with pinned host buffers
+    for _ in range(min(args.warmup, 3)):
+        prob.step_e2e()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    t_wall0 = time.perf_counter()
+    e0.record()
+    for _ in range(args.steps):
+        prob.step_e2e()
+    e1.record()
+    barrier()
+    e2e_wall = time.perf_counter() - t_wall0
+    e2e_ms = max(e0.elapsed_time(e1), e2e_wall * 1e3)  # D2H is synchronous: host clock bounds it too
+    clocks = sampler.stop() if rank == 0 else None
+
+    if world > 1:
+        import torch.distributed as dist
+        t = torch.tensor([ms_total, jac_ms, e2e_ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_total, jac_ms, e2e_ms = t.tolist()
+
+    ms_step = ms_total / args.steps
+    value = LAUNCHES_PER_STEP * z_global / (ms_step * 1e-3)
+    e2e_value = LAUNCHES_PER_STEP * z_global / (e2e_ms / args.steps * 1e-3)
+    peak, peak_src = peaks()
+    # per-GPU roofline of the dominant kernel (its own rows / nnz)
+    bytes_jac = jacobi_bytes(prob.n_local, prob.nnz_local)
+    achieved = bytes_jac / (jac_ms * 1e-3) / 1e9
+    traffic = committed_traffic()
+    line = {
+        "metric": "fused SpMV-layer nnz/s", "value": value, "unit": "nnz/s", "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(args.workload, n_global, z_global, world),
+        "roofline": {"bound": "hbm", "kernel": "glab_jacobi_f32 (k_row_tiles<float,1,EpiJacobi>)",
+                     "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                     "peak_source": peak_src, "bytes_per_launch": bytes_jac, "ms_per_launch": jac_ms,
+                     "gnnz_per_s": prob.nnz_local / (jac_ms * 1e-3) / 1e9,
+                     "traffic": None if not traffic else traffic.get("jacobi_dram_bytes_per_launch"),
+                     "traffic_source": None if not traffic else traffic.get("source")},
+        "e2e": {"value": e2e_value, "unit": "nnz/s", "ms_per_step": e2e_ms / args.steps,
+                "h2d_bytes_per_step": prob.h2d_bytes * world, "d2h_bytes_per_step": prob.d2h_bytes * world,
+                "api": "JacobiGNN.forward(10, ...) + ChebyRelaxGNN(4).forward(...) on device copies of pinned host vectors"},
+        "gpu_launches": launches,
+        "clocks": clocks,
+        "setup": prob.setup_info,
+    }
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        r = run_cpu_reference(args.workload, 1, 0)
+        line["cpu_baseline"] = {"value": r["value"], "unit": "nnz/s", "cores": r["cores"], "kind": r["kind"],
+                                "sample": r["sample"], "ms_per_step": r["ms_per_step"]}
+    if rank == 0:
+        print(json.dumps(line))
+    if world > 1:
+        import torch.distributed as dist
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="glab", choices=["glab", "reference"])
+    ap.add_argument("--workload", default=os.environ.get("GLAB_BENCH_WORKLOAD", "L4096"), choices=sorted(GRID))
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "glab":
+        args.warmup = 3
+    if args.impl == "reference":
+        return main_reference(args)
+    return main_gpu(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

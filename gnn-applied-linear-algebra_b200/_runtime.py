@@ -269,7 +269,12 @@ def _rows(plan, rows):
     return (0, plan.n_rows) if rows is None else (int(rows[0]), int(rows[1]))
 
 
+launch_count = 0  # number of libglab kernels launched through the wrappers below (bench.py reads it)
+
+
 def _call(name, dtype, device, *args):
+    global launch_count
+    launch_count += 1
     with torch.cuda.device(device):
         check(getattr(lib, "glab_%s_%s" % (name, suffix(dtype)))(*args), "glab_" + name)
 

@@ -68,8 +68,9 @@ template <typename T> struct OpDirectInterp {
 template <typename T, class Op>
 static int launch_edge_tiles(const glab_plan* p, const T* vals, const T* aux, const Op& op, T* out,
                              void* stream) {
-  if (!p || !out || (p->nnz > 0 && !vals)) return GLAB_E_ARG;
-  if (p->n_rows == 0) return 0;
+  if (!p) return GLAB_E_ARG;
+  if (p->nnz == 0 || p->n_rows == 0) return 0;  // no edges -> no per-edge outputs
+  if (!out || !vals) return GLAB_E_ARG;
   const int ntiles = (int)((p->n_rows + kThreads - 1) / kThreads);
   int64_t want = (int64_t)kThreads * (p->max_row_nnz > 0 ? p->max_row_nnz : 1);
   int cap = (int)(want < 4096 ? want : 4096);
@@ -106,9 +107,9 @@ __global__ void k_edge_messages(const int32_t* __restrict__ colidx, const T* __r
 template <typename T>
 static int edge_messages(const glab_plan* p, const T* vals, const T* x, int k, T* out, int64_t ld,
                          int64_t column, void* stream) {
-  if (!p || !x || !out || (p->nnz > 0 && !vals) || ld < 1 || column < 0 || column + k > ld)
-    return GLAB_E_ARG;
+  if (!p || ld < 1 || column < 0 || column + k > ld) return GLAB_E_ARG;
   if (p->nnz == 0) return 0;
+  if (!x || !out || !vals) return GLAB_E_ARG;
   int64_t b = (p->nnz + 255) / 256;
   const int64_t capb = (int64_t)p->sm_count * 32;
   const int grid = (int)(b < capb ? b : capb);
@@ -175,13 +176,13 @@ using namespace glab;
     return launch_edge_tiles<T>(p, v, (const T*)nullptr, op, S, s);                                \
   }                                                                                                \
   extern "C" int glab_soc_sa_##SUF(const glab_plan* p, const T* v, const T* diag, T* S, void* s) { \
-    if (!diag) return GLAB_E_ARG;                                                                  \
+    if (p && p->nnz > 0 && !diag) return GLAB_E_ARG;                                               \
     OpSocSA<T> op{diag};                                                                           \
     return launch_edge_tiles<T>(p, v, (const T*)nullptr, op, S, s);                                \
   }                                                                                                \
   extern "C" int glab_direct_interp_##SUF(const glab_plan* p, const T* v, const T* S,              \
                                           const T* diag, const T* cflag, T* w, void* s) {          \
-    if (!diag || !cflag || (p && p->nnz > 0 && !S)) return GLAB_E_ARG;                             \
+    if (p && p->nnz > 0 && (!diag || !cflag || !S)) return GLAB_E_ARG;                            \
     OpDirectInterp<T> op{diag, cflag};                                                             \
     return launch_edge_tiles<T>(p, v, S, op, w, s);                                                \
   }                                                                                                \

@@ -1,0 +1,391 @@
+"""GPU parity tests: every drop-in layer (CUDA kernels behind the C ABI) against the CPU oracle
+(oracle/port.py, pinned to the reference) on the same seeded inputs, and against the committed
+golden vectors produced by the unmodified reference.
+
+Bars (BASELINE.json north_star): bit-exact strength masks / interpolation patterns; <= 1e-5
+relative error in fp32 and <= 1e-12 in fp64 for matvec, smoother, eigenvalue and V-cycle
+outputs.  Because the kernels accumulate in edge order without FMA contraction, most outputs
+are in fact compared BIT FOR BIT; only reductions over all vertices (norms, Rayleigh quotient)
+and the torch.sparse glue of the V-cycle use the tolerances.
+"""
+import ctypes
+
+import pytest
+import torch
+
+from conftest import relerr, same
+from oracle import port
+
+pytestmark = pytest.mark.gpu
+
+TOL = {torch.float32: 1e-5, torch.float64: 1e-12}
+
+
+def lap(N, dt):
+    ei, ev = port.laplacian_2d(N)
+    return ei, ev.to(dt)
+
+
+def rand_problem(n, z, dt, seed, with_diag=True):
+    """Random sparse operator in ARBITRARY edge order with duplicate (i,j) pairs, empty rows and
+    one long row (exercises the stable sort, the permutation and the chunked staging path)."""
+    g = torch.Generator().manual_seed(seed)
+    rows = torch.randint(0, n, (z,), generator=g)
+    cols = torch.randint(0, n, (z,), generator=g)
+    rows[rows == 3] = 4                                    # row 3 is empty
+    long_cols = torch.randint(0, n, (min(6000, 4 * n),), generator=g)
+    rows = torch.cat([rows, torch.full_like(long_cols, 7), rows[:50]])   # long row 7 + duplicates
+    cols = torch.cat([cols, long_cols, cols[:50]])
+    if with_diag:
+        d = torch.arange(n)
+        d = d[d != 3]
+        rows, cols = torch.cat([rows, d]), torch.cat([cols, d])
+    perm = torch.randperm(rows.numel(), generator=g)
+    ei = torch.stack([rows[perm], cols[perm]])
+    ev = (torch.rand(ei.shape[1], 1, generator=g, dtype=torch.float64) - 0.5).to(dt)
+    return ei, ev
+
+
+@pytest.mark.parametrize("dt", [torch.float32, torch.float64])
+@pytest.mark.parametrize("N", [5, 17, 64])
+@pytest.mark.parametrize("k", [1, 2, 4, 8])
+def test_matvec_bit_exact(G, dev, dt, N, k):
+    torch.manual_seed(24601)
+    ei, ev = lap(N, dt)
+    x = torch.rand(N * N, k, dtype=dt)
+    ref_v, ref_e = port.matvec(x, ei, ev)
+    layer = G.MetaLayer(G.MatVecGNN.EdgeUpdate(), G.MatVecGNN.VertexUpdate(G.MatVecGNN.edge_to_vertex_aggregation))
+    v, e, _ = layer(x.to(dev), ei.to(dev), ev.to(dev), None, batch=torch.zeros(N * N))
+    assert v.is_cuda and same(v.cpu(), ref_v) and same(e.cpu(), ref_e)
+
+
+def test_matvec_config1(G, dev):
+    """BASELINE config 1: laplacianfun_torch(64), fp64, seed 24601, k = 1 and 2 (tolerance 1e-12)."""
+    torch.manual_seed(24601)
+    ei, ev = G.UtilsGNN.laplacianfun_torch(64)
+    assert ei.shape[1] == 20224
+    for k in (1, 2):
+        x = torch.rand(4096, k, dtype=torch.float64)
+        ref_v, _ = port.matvec(x, ei, ev)
+        v, _, _ = G.MatVecGNN.MatVecGNN()(x.to(dev), ei.to(dev), ev.to(dev), None, None)
+        assert relerr(v.cpu()[:, k:], ref_v[:, k:]) <= 1e-12
+        A = torch.sparse_coo_tensor(ei, ev.flatten(), (4096, 4096)).to_sparse_csr()
+        assert relerr(v.cpu()[:, k:], A @ x) <= 1e-12
+
+
+@pytest.mark.parametrize("dt", [torch.float32, torch.float64])
+def test_host_tensors_in_host_tensors_out(G, dt):
+    """The reference's users hold CPU tensors: the drop-in uploads, computes on the GPU and
+    returns CPU tensors."""
+    torch.manual_seed(3)
+    ei, ev = lap(9, dt)
+    b, x = torch.rand(81, 1, dtype=dt), torch.rand(81, 1, dtype=dt)
+    r = G.GNNResidual.GNNResidual()(torch.cat([b, x], 1), ei, ev)
+    assert not r.is_cuda and same(r, port.residual(torch.cat([b, x], 1), ei, ev))
+
+
+@pytest.mark.parametrize("dt", [torch.float32, torch.float64])
+@pytest.mark.parametrize("N", [5, 33])
+def test_jacobi_bit_exact(G, dev, dt, N):
+    torch.manual_seed(24601)
+    n = N * N
+    ei, ev = lap(N, dt)
+    ev = ev * (1 + 0.05 * torch.rand_like(ev))
+    va = torch.cat([torch.rand(n, 1, dtype=dt) + 3.5, torch.rand(n, 1, dtype=dt), torch.rand(n, 1, dtype=dt)], 1)
+    ea = torch.cat([ev, torch.zeros_like(ev)], 1)
+    g = torch.tensor(0.7).reshape(-1)
+    J = G.JacobiGNN.JacobiGNN()
+    for iters in (0, 1, 2, 10):
+        out = J(iters, va.to(dev), ei.to(dev), ea.to(dev), g)
+        assert same(out.cpu(), port.jacobi(iters, va, ei, ea, g)), iters
+    out = J.iterate(va.to(dev), ei.to(dev), ea.to(dev), g.to(dev))
+    ref = port.jacobi_iterate(va, ei, ea, g)
+    assert same(out[0].cpu(), ref[0]) and same(out[1].cpu(), ref[1])
+
+
+@pytest.mark.parametrize("dt", [torch.float32, torch.float64])
+@pytest.mark.parametrize("k", [2, 8])
+def test_jacobi_cheby_multi_rhs_extension(G, dev, dt, k):
+    """k right-hand sides at once (config 5 extension): oracle = the reference run per column."""
+    torch.manual_seed(9)
+    N = 12
+    n = N * N
+    ei, ev = lap(N, dt)
+    diag = -4 * torch.ones(n, 1, dtype=dt)
+    b, x = torch.rand(n, k, dtype=dt), torch.rand(n, k, dtype=dt)
+    ea = torch.cat([ev, torch.zeros_like(ev)], 1)
+    g = torch.tensor(0.7).reshape(-1)
+    out = G.JacobiGNN.JacobiGNN()(3, torch.cat([diag, b, x], 1).to(dev), ei.to(dev), ea.to(dev), g).cpu()
+    gc = torch.tensor([-3.4, -4.0])
+    cv, _, _ = G.ChebyGNN.ChebyRelaxGNN(4)(torch.cat([b, x], 1).to(dev), ei.to(dev), ev.to(dev), gc)
+    rr = G.GNNResidual.GNNResidual()(torch.cat([b, x], 1).to(dev), ei.to(dev), ev.to(dev)).cpu()
+    for c in range(k):
+        ref = port.jacobi(3, torch.cat([diag, b[:, c:c + 1], x[:, c:c + 1]], 1), ei, ea, g)
+        assert same(out[:, c:c + 1], ref)
+        rv, _, _ = port.chebyshev(4, torch.cat([b[:, c:c + 1], x[:, c:c + 1]], 1), ei, ev, gc)
+        for j in range(4):   # [b | x | r | p] blocks of k columns
+            assert same(cv.cpu()[:, j * k + c], rv[:, j])
+        assert same(rr[:, c:c + 1], port.residual(torch.cat([b[:, c:c + 1], x[:, c:c + 1]], 1), ei, ev))
+
+
+@pytest.mark.parametrize("dt", [torch.float32, torch.float64])
+@pytest.mark.parametrize("deg", [1, 2, 3, 4, 8])
+def test_chebyshev_bit_exact(G, dev, dt, deg):
+    torch.manual_seed(24601)
+    N = 21
+    ei, ev = lap(N, dt)
+    b, x = torch.rand(N * N, 1, dtype=dt), torch.rand(N * N, 1, dtype=dt)
+    g = torch.tensor([-3.46, -4.0])
+    ref = port.chebyshev(deg, torch.cat([b, x], 1), ei, ev, g)
+    out = G.ChebyGNN.ChebyRelaxGNN(deg)(torch.cat([b, x], 1).to(dev), ei.to(dev), ev.to(dev), g)
+    for a, r in zip(out, ref):
+        assert same(a.cpu(), r)
+
+
+@pytest.mark.parametrize("dt", [torch.float32, torch.float64])
+def test_power_method(G, dev, dt):
+    torch.manual_seed(24601)
+    for N, iters in ((5, 10), (24, 100)):
+        ei, ev = lap(N, dt)
+        x = torch.rand(N * N, 1, dtype=dt)
+        ea = torch.cat([ev, torch.zeros_like(ev)], 1)
+        va = torch.cat([x, torch.zeros_like(x)], 1)
+        rv, re_, rg = port.power_method(iters, va, ei, ea, torch.zeros(3, dtype=dt))
+        ov, oe, og = G.PowerMethodGNN.PowerMethodGNN(iters)(va.to(dev), ei.to(dev), ea.to(dev),
+                                                           torch.zeros(3, dtype=dt), torch.zeros(N * N))
+        assert og.dtype == rg.dtype and ov.shape == rv.shape and oe.shape == re_.shape
+        assert relerr(og.cpu(), rg) <= TOL[dt]
+        assert relerr(ov.cpu(), rv) <= 10 * TOL[dt] and relerr(oe.cpu(), re_) <= 10 * TOL[dt]
+    # the reference's own 3x3 example: lambda -> 3 (PowerMethodGNN.py:338-383)
+    A = torch.tensor([[1., 2., 0], [-2., 1., 2.], [1., 3., 1.]], dtype=dt)
+    eij = torch.tensor([[i, j] for i in range(3) for j in range(3)]).T
+    ea = torch.stack([A.flatten(), torch.zeros(9, dtype=dt)], 1)
+    va = torch.cat([torch.rand(3, 1, dtype=dt), torch.zeros(3, 1, dtype=dt)], 1)
+    _, _, g = G.PowerMethodGNN.PowerMethodGNN(10)(va.to(dev), eij.to(dev), ea.to(dev), torch.zeros(3, dtype=dt), None)
+    assert abs(g[2].item() - 3.0) < 1e-3
+
+
+@pytest.mark.parametrize("dt", [torch.float32, torch.float64])
+def test_amg_setup_bit_exact(G, dev, dt):
+    """Classical SOC, SA SOC and direct interpolation on an ANISOTROPIC periodic FEM operator
+    (config 4 family: positive N/S couplings, corner/E-W ratio 0.2538 next to theta = 0.25)."""
+    N = 24
+    n = N * N
+    ei, ev = G.generators.constant_diffusion_fem(1.0, 0.01, N, dtype=torch.float64)
+    ev = ev.to(dt)
+    eo, ao = port.remove_diag_entries(ei, ev)
+    diag = G.generators.diagonal_of(ei, ev, n)
+    for theta in (0.25, 0.3, 0.0):
+        S_ref = port.soc_classic(theta, torch.zeros(n, 1, dtype=dt), eo, ao)
+        S = G.SOCClassicGNN.SOCClassicGNN(theta)(torch.zeros(n, 1, dtype=dt, device=dev), eo.to(dev), ao.to(dev))
+        assert same(S.cpu(), S_ref)
+        assert torch.equal(S.cpu() > 0, S_ref > 0)
+    S_ref = port.soc_classic(0.25, torch.zeros(n, 1, dtype=dt), eo, ao)
+    assert 0 < (S_ref > 0).sum() < S_ref.numel()          # the mask is non-trivial
+    _, e_sa, _ = G.SOCSAGNN.SOCSAGNN()(diag.to(dev), eo.to(dev), ao.to(dev), batch=None)
+    assert same(e_sa.cpu(), port.soc_sa(diag, eo, ao))
+    split = torch.zeros(n, 1, dtype=dt)
+    split[0::2] = 1
+    ed = torch.hstack([ao, S_ref.reshape(-1, 1) > 0])
+    w_ref = port.direct_interp(torch.hstack([diag, split]), eo, ed)
+    w = G.DirectInterpGNN.DirectInterpGNN()(torch.hstack([diag, split]).to(dev), eo.to(dev), ed.to(dev), None)
+    assert same(w.cpu(), w_ref)
+    for pat in (torch.isnan, lambda t: t == 0, lambda t: t != 0):
+        assert torch.equal(pat(w.cpu()), pat(w_ref))
+
+
+@pytest.mark.parametrize("dt", [torch.float32, torch.float64])
+def test_arbitrary_edge_order_duplicates_empty_and_long_rows(G, dev, dt):
+    n = 300
+    ei, ev = rand_problem(n, 2500, dt, 77)
+    x = torch.rand(n, 2, dtype=dt)
+    ref_v, ref_e = port.matvec(x, ei, ev)
+    v, e, _ = G.MatVecGNN.MatVecGNN()(x.to(dev), ei.to(dev), ev.to(dev), None, None)
+    assert same(v.cpu(), ref_v) and same(e.cpu(), ref_e)
+    plan = G.get_plan(ei.to(dev), n)
+    assert not plan.identity and plan.max_row_nnz >= 1200
+    # aggregation seam alone (scatter sum), 1-D and 2-D sources
+    c = torch.rand(ei.shape[1], 4, dtype=dt)
+    agg = G.MatVecGNN.edge_to_vertex_aggregation(ei.to(dev), c.to(dev), n)
+    assert same(agg.cpu(), port.scatter_sum(c, ei[0], n))
+    agg1 = G.MatVecGNN.edge_to_vertex_aggregation(ei.to(dev), c[:, 0].contiguous().to(dev), n)
+    assert same(agg1.cpu(), port.scatter_sum(c[:, 0].contiguous(), ei[0], n))
+    # Jacobi + residual + Chebyshev on the same messy operator
+    diag = torch.rand(n, 1, dtype=dt) + 1
+    b, x1 = torch.rand(n, 1, dtype=dt), torch.rand(n, 1, dtype=dt)
+    ea = torch.cat([ev, torch.zeros_like(ev)], 1)
+    g = torch.tensor(0.5).reshape(-1)
+    out = G.JacobiGNN.JacobiGNN().iterate(torch.cat([diag, b, x1], 1).to(dev), ei.to(dev), ea.to(dev), g)
+    ref = port.jacobi_iterate(torch.cat([diag, b, x1], 1), ei, ea, g)
+    assert same(out[0].cpu(), ref[0]) and same(out[1].cpu(), ref[1])
+    gc = torch.tensor([0.3, 2.0])
+    outc = G.ChebyGNN.ChebyRelaxGNN(3)(torch.cat([b, x1], 1).to(dev), ei.to(dev), ev.to(dev), gc)
+    refc = port.chebyshev(3, torch.cat([b, x1], 1), ei, ev, gc)
+    for a, r in zip(outc, refc):
+        assert same(a.cpu(), r)
+    # AMG setup kernels with a permutation: outputs must come back in the CALLER's edge order
+    eo, ao = rand_problem(n, 2500, dt, 78, with_diag=False)
+    keep = eo[0] != eo[1]
+    eo, ao = eo[:, keep], ao[keep]
+    S_ref = port.soc_classic(0.25, torch.zeros(n, 1, dtype=dt), eo, ao)
+    S = G.SOCClassicGNN.SOCClassicGNN(0.25)(torch.zeros(n, 1, dtype=dt), eo.to(dev), ao.to(dev))
+    assert same(S.cpu(), S_ref)
+    split = (torch.rand(n, 1) > 0.5).to(dt)
+    ed = torch.hstack([ao, (S_ref.reshape(-1, 1) > 0).to(dt)])
+    w = G.DirectInterpGNN.DirectInterpGNN()(torch.hstack([diag, split]).to(dev), eo.to(dev), ed.to(dev))
+    assert same(w.cpu(), port.direct_interp(torch.hstack([diag, split]), eo, ed))
+    _, e_sa, _ = G.SOCSAGNN.SOCSAGNN()(diag.to(dev), eo.to(dev), ao.to(dev))
+    assert same(e_sa.cpu(), port.soc_sa(diag, eo, ao))
+
+
+def test_empty_and_tiny_inputs(G, dev):
+    ei = torch.zeros(2, 0, dtype=torch.long)
+    ev = torch.zeros(0, 1)
+    x = torch.rand(5, 1)
+    v, e, _ = G.MatVecGNN.MatVecGNN()(x.to(dev), ei.to(dev), ev.to(dev), None, None)
+    assert same(v.cpu(), torch.cat([x, torch.zeros(5, 1)], 1)) and e.shape == (0, 2)
+    S = G.SOCClassicGNN.SOCClassicGNN(0.25)(torch.zeros(5, 1), ei.to(dev), ev.to(dev))
+    assert S.shape == (0,)
+    ei1 = torch.tensor([[0], [0]])
+    v, _, _ = G.MatVecGNN.MatVecGNN()(torch.tensor([[3.0]]).to(dev), ei1.to(dev), torch.tensor([[2.0]]).to(dev), None, None)
+    assert v.cpu().tolist() == [[3.0, 6.0]]
+    with pytest.raises(G.GlabError):
+        G.Plan.from_coo(torch.tensor([[0], [9]]).to(dev), 5)           # column out of range
+    with pytest.raises(G.GlabError):
+        G.MatVecGNN.MatVecGNN()(torch.rand(5, 3).to(dev), ei1.to(dev), torch.rand(1, 1).to(dev), None, None)
+
+
+def test_golden_vectors(G, dev, golden):
+    """The committed outputs of the unmodified reference, without any oracle code in between."""
+    for c in golden["layers"]:
+        dt, n = c["dtype"], c["N"] ** 2
+        ei = c["edge_index"].to(dev)
+        ev = c["edge_val64"].to(dt).to(dev)
+        v, e, _ = G.MatVecGNN.MatVecGNN()(c["x2"].to(dev), ei, ev, None, None)
+        assert same(v.cpu(), c["matvec2"][0]) and same(e.cpu(), c["matvec2"][1])
+        assert same(G.GNNResidual.GNNResidual()(torch.cat([c["b"], c["x"]], 1).to(dev), ei, ev).cpu(), c["residual"])
+        va = torch.cat([-4 * torch.ones(n, 1, dtype=dt), c["b"], c["x"]], 1).to(dev)
+        ea = torch.cat([ev, torch.zeros_like(ev)], 1)
+        assert same(G.JacobiGNN.JacobiGNN()(10, va, ei, ea, torch.tensor(0.7).reshape(-1)).cpu(), c["jacobi10"])
+        for deg, ref in c["cheby"].items():
+            out = G.ChebyGNN.ChebyRelaxGNN(deg)(torch.cat([c["b"], c["x"]], 1).to(dev), ei, ev, torch.tensor([-3.46, -4.0]))
+            assert all(same(a.cpu(), r) for a, r in zip(out, ref))
+        vp = torch.cat([c["x"], torch.zeros_like(c["x"])], 1).to(dev)
+        _, _, g = G.PowerMethodGNN.PowerMethodGNN(10)(vp, ei, ea, torch.zeros(3, dtype=dt), None)
+        assert relerr(g.cpu(), c["power10"][2]) <= TOL[dt]
+        eo, ao = c["off_index"].to(dev), c["off_val"].to(dev)
+        S = G.SOCClassicGNN.SOCClassicGNN(c["theta"])(torch.zeros(n, 1, dtype=dt, device=dev), eo, ao)
+        assert same(S.cpu(), c["soc_classic"])
+        dv = -4 * torch.ones(n, 1, dtype=dt, device=dev)
+        assert same(G.SOCSAGNN.SOCSAGNN()(dv, eo, ao)[1].cpu(), c["soc_sa"])
+        ed = torch.hstack([ao, (S.reshape(-1, 1) > 0)])
+        w = G.DirectInterpGNN.DirectInterpGNN()(torch.hstack([dv, c["splitting"].to(dev)]), eo, ed, None)
+        assert same(w.cpu(), c["direct_interp"])
+        nrm = G.MatrixWeightedNorm.MatrixWeightedNorm()(c["x"].to(dev), ei, -ev)
+        assert relerr(nrm.cpu(), c["mwnorm"]) <= TOL[dt]
+    k = golden["known"]["mv3"]
+    v, _, _ = G.MatVecGNN.MatVecGNN()(k["x"].to(dev), k["edge_index"].to(dev), k["A_ij"].to(dev), None, None)
+    assert v.cpu()[:, 1].tolist() == [20.0, 301.0, 1030.0]
+
+
+def test_vcycle_golden(G, dev, golden):
+    """Two-grid cycle against the reference's own runVCycle outputs (VCycle.py:262-277).  The
+    layer calls are bit-exact; P^T A P / P^T r go through different sparse kernels than
+    torch's CPU ones, hence the fp32 tolerance on x and on the residual norms."""
+    V = G.VCycle
+    for c in golden["vcycle"]:
+        N = c["N"]
+        ei, ev = G.UtilsGNN.laplacianfun_torch(N, device=dev)
+        A = torch.sparse_coo_tensor(ei, ev.flatten(), dtype=torch.float)
+        x, b = c["x0"].to(dev), c["b"].to(dev)
+        for ref_x, ref_norm in zip(c["xs"], c["residual_norms"]):
+            x = V.runVCycle(A, b, x, 3, 3, 5, True)
+            assert relerr(x.cpu(), ref_x) <= 1e-5
+            rn = torch.norm(V.runResidual(A, b, x)).item()
+            assert abs(rn - ref_norm) <= 1e-5 * max(ref_norm, 1e-2)
+    # host-tensor entry, like the reference script
+    c = golden["vcycle"][0]
+    ei, ev = G.UtilsGNN.laplacianfun_torch(c["N"])
+    A = torch.sparse_coo_tensor(ei, ev.flatten(), dtype=torch.float)
+    x = V.runVCycle(A, c["b"], c["x0"], 3, 3, 5, True)
+    assert not x.is_cuda and relerr(x, c["xs"][0]) <= 1e-5
+
+
+def test_c_abi_direct(G, dev):
+    """Straight through the C ABI with raw pointers (what a non-Python host would do)."""
+    lib = G.lib
+    torch.manual_seed(1)
+    N = 40
+    n = N * N
+    ei, ev = lap(N, torch.float32)
+    eid, vals = ei.to(dev).contiguous(), ev.to(dev).flatten().contiguous()
+    x = torch.rand(n, device=dev)
+    y = torch.empty(n, device=dev)
+    plan = ctypes.c_void_p()
+    st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+    P = ctypes.c_void_p
+    assert lib.glab_plan_create(n, n, eid.shape[1], P(eid[0].data_ptr()), P(eid[1].data_ptr()), st,
+                                ctypes.byref(plan)) == 0
+    mx, ident = ctypes.c_int32(), ctypes.c_int32()
+    assert lib.glab_plan_info(plan, None, None, None, ctypes.byref(mx), ctypes.byref(ident)) == 0
+    assert mx.value == 5 and ident.value == 1
+    assert lib.glab_spmm_f32(plan, P(vals.data_ptr()), P(x.data_ptr()), 1, P(y.data_ptr()), 0, n, st) == 0
+    ref, _ = port.matvec(x.cpu().view(-1, 1), ei, ev)
+    assert same(y.cpu().view(-1, 1), ref[:, 1:])
+    # row ranges (used for interior/boundary overlap): two halves == whole
+    y2 = torch.full((n,), float("nan"), device=dev)
+    assert lib.glab_spmm_f32(plan, P(vals.data_ptr()), P(x.data_ptr()), 1, P(y2.data_ptr()), 0, 777, st) == 0
+    assert lib.glab_spmm_f32(plan, P(vals.data_ptr()), P(x.data_ptr()), 1, P(y2.data_ptr()), 777, n, st) == 0
+    assert same(y2.cpu(), y.cpu())
+    # argument errors
+    assert lib.glab_spmm_f32(plan, P(vals.data_ptr()), P(x.data_ptr()), 3, P(y.data_ptr()), 0, n, st) == -1
+    assert lib.glab_spmm_f32(plan, P(vals.data_ptr()), P(x.data_ptr()), 1, P(y.data_ptr()), 0, n + 1, st) == -1
+    assert lib.glab_jacobi_f32(plan, P(vals.data_ptr()), P(x.data_ptr()), P(x.data_ptr()), P(x.data_ptr()),
+                               P(x.data_ptr()), P(x.data_ptr()), 1, 0, n, st) == -1   # in-place sweep refused
+    assert lib.glab_plan_destroy(plan) == 0
+
+
+@pytest.mark.parametrize("dt", [torch.float32, torch.float64])
+def test_large_operator_properties(G, dev, dt):
+    """Size-independent checks at a size the CPU oracle cannot reach in seconds (2048^2 rows):
+    A*1 equals the analytic row sums exactly, the fused Jacobi sweep equals its definition built
+    from the fused residual (bit-exact), linearity, and an independent fp64 torch.sparse CSR
+    product agrees within the tolerance."""
+    N = 2048
+    n = N * N
+    ei, ev = G.UtilsGNN.laplacianfun_torch(N, device=dev)
+    ev = ev.to(dt)
+    plan = G.get_plan(ei, n)
+    assert plan.identity and plan.nnz == 5 * n - 4 * N
+    vals = G.runtime.get_vals(plan, ev)
+    ones = torch.ones(n, 1, dtype=dt, device=dev)
+    y = G.runtime.spmm(plan, vals, ones)
+    idx = torch.arange(n, device=dev)
+    gy, gx = idx // N, idx % N
+    expected = -(((gy == 0) | (gy == N - 1)).to(dt) + ((gx == 0) | (gx == N - 1)).to(dt))
+    assert torch.equal(y.view(-1), expected)
+    torch.manual_seed(24601)
+    x = torch.rand(n, 1, dtype=dt, device=dev)
+    b = torch.rand(n, 1, dtype=dt, device=dev)
+    diag = torch.full((n,), -4.0, dtype=dt, device=dev)
+    w = torch.tensor([0.7], dtype=dt, device=dev)
+    xo = G.runtime.jacobi(plan, vals, diag, b, x, torch.empty_like(x), w)
+    r = G.runtime.residual(plan, vals, x, b)
+    assert torch.equal(xo, x + (w * r) / diag.view(-1, 1))
+    A = torch.sparse_coo_tensor(ei, ev.flatten().double(), (n, n)).to_sparse_csr()
+    yx = G.runtime.spmm(plan, vals, x)
+    assert relerr(yx, A @ x.double()) <= TOL[dt]
+    y2 = G.runtime.spmm(plan, vals, 2 * x)
+    assert torch.equal(y2, 2 * yx)                                   # scaling by 2 is exact
+    # power-method norms: deterministic (bitwise reproducible) reduction
+    va = torch.cat([x, torch.zeros_like(x)], 1)
+    ea = torch.cat([ev, torch.zeros_like(ev)], 1)
+    g1 = G.PowerMethodGNN.PowerMethodGNN(5)(va, ei, ea, torch.zeros(3, dtype=dt), None)[2]
+    g2 = G.PowerMethodGNN.PowerMethodGNN(5)(va, ei, ea, torch.zeros(3, dtype=dt), None)[2]
+    assert torch.equal(g1, g2)
+    bk = x.double()
+    for _ in range(5):
+        bk = A @ bk
+        bk = bk / bk.norm()
+    lam = ((bk * (A @ bk)).sum() / (bk * bk).sum()).item()
+    assert abs(g1[2].item() - lam) <= TOL[dt] * abs(lam)
