@@ -3,7 +3,7 @@
 // Each extern "C" entry is ONE kernel launch that replaces one or more reference GN blocks
 // (gathers + edge update + scatter + vertex update); citations are in include/glab.h.
 #include <cstdlib>
-#include "glab_tiles.cuh"
+#include "glab_pipe.cuh"
 
 namespace glab {
 
@@ -15,6 +15,10 @@ template <typename T, int K> struct EpiSpmm {  // y = A x            (MatVecGNN.
   using State = NoState;
   __device__ void init(State&) const {}
   __device__ void row(State&, int r, const T (&acc)[K]) const { store_vec<T, K>(y + (size_t)r * K, acc); }
+  static constexpr int kStreams = 0;
+  __host__ __device__ const T* stream_ptr(int) const { return nullptr; }
+  __host__ __device__ int stream_width(int) const { return 0; }
+  __device__ void row_staged(State& s, int r, const T (&acc)[K], const T*, const T*, const T*) const { row(s, r, acc); }
   __device__ void finish(State&) const {}
 };
 
@@ -30,6 +34,15 @@ template <typename T, int K> struct EpiResidual {  // r = b - A x  (GNNResidual.
     for (int c = 0; c < K; ++c) o[c] = bb[c] - acc[c];
     store_vec<T, K>(out + (size_t)r * K, o);
   }
+  static constexpr int kStreams = 1;
+  __host__ __device__ const T* stream_ptr(int) const { return b; }
+  __host__ __device__ int stream_width(int) const { return K; }
+  __device__ void row_staged(State&, int r, const T (&acc)[K], const T* sb, const T*, const T*) const {
+    T o[K];
+#pragma unroll
+    for (int c = 0; c < K; ++c) o[c] = sb[c] - acc[c];
+    store_vec<T, K>(out + (size_t)r * K, o);
+  }
   __device__ void finish(State&) const {}
 };
 
@@ -43,6 +56,15 @@ template <typename T, int K> struct EpiAdd {  // out = b + A x  (coarse-grid cor
     load_vec<T, K>(bb, b + (size_t)r * K);
 #pragma unroll
     for (int c = 0; c < K; ++c) o[c] = bb[c] + acc[c];
+    store_vec<T, K>(out + (size_t)r * K, o);
+  }
+  static constexpr int kStreams = 1;
+  __host__ __device__ const T* stream_ptr(int) const { return b; }
+  __host__ __device__ int stream_width(int) const { return K; }
+  __device__ void row_staged(State&, int r, const T (&acc)[K], const T* sb, const T*, const T*) const {
+    T o[K];
+#pragma unroll
+    for (int c = 0; c < K; ++c) o[c] = sb[c] + acc[c];
     store_vec<T, K>(out + (size_t)r * K, o);
   }
   __device__ void finish(State&) const {}
@@ -65,6 +87,16 @@ template <typename T, int K> struct EpiJacobi {  // x + w*(b - Ax)/d  (JacobiGNN
     for (int c = 0; c < K; ++c) o[c] = xx[c] + (s.w * (bb[c] - acc[c])) / d;
     store_vec<T, K>(xo + (size_t)r * K, o);
   }
+  static constexpr int kStreams = 3;
+  __host__ __device__ const T* stream_ptr(int i) const { return i == 0 ? diag : (i == 1 ? b : x); }
+  __host__ __device__ int stream_width(int i) const { return i == 0 ? 1 : K; }
+  __device__ void row_staged(State& s, int r, const T (&acc)[K], const T* sd, const T* sb, const T* sx) const {
+    T o[K];
+    const T d = sd[0];
+#pragma unroll
+    for (int c = 0; c < K; ++c) o[c] = sx[c] + (s.w * (sb[c] - acc[c])) / d;
+    store_vec<T, K>(xo + (size_t)r * K, o);
+  }
   __device__ void finish(State&) const {}
 };
 
@@ -85,6 +117,20 @@ template <typename T, int K> struct EpiChebyFirst {  // ChebyGNN.py:117, :160-16
     for (int c = 0; c < K; ++c) {
       rr[c] = bb[c] - acc[c];
       o[c] = xx[c] + s.a * rr[c];
+    }
+    store_vec<T, K>(r_ + (size_t)r * K, rr);
+    store_vec<T, K>(p_ + (size_t)r * K, rr);
+    store_vec<T, K>(xo + (size_t)r * K, o);
+  }
+  static constexpr int kStreams = 2;
+  __host__ __device__ const T* stream_ptr(int i) const { return i == 0 ? b : x; }
+  __host__ __device__ int stream_width(int) const { return K; }
+  __device__ void row_staged(State& s, int r, const T (&acc)[K], const T* sb, const T* sx, const T*) const {
+    T rr[K], o[K];
+#pragma unroll
+    for (int c = 0; c < K; ++c) {
+      rr[c] = sb[c] - acc[c];
+      o[c] = sx[c] + s.a * rr[c];
     }
     store_vec<T, K>(r_ + (size_t)r * K, rr);
     store_vec<T, K>(p_ + (size_t)r * K, rr);
@@ -122,6 +168,21 @@ template <typename T, int K> struct EpiChebyNext {  // ChebyGNN.py:214, :240-241
     store_vec<T, K>(p_out + (size_t)r * K, pp);
     store_vec<T, K>(x_ + (size_t)r * K, xx);
   }
+  static constexpr int kStreams = 3;
+  __host__ __device__ const T* stream_ptr(int i) const { return i == 0 ? p_in : (i == 1 ? r_ : x_); }
+  __host__ __device__ int stream_width(int) const { return K; }
+  __device__ void row_staged(State& s, int r, const T (&acc)[K], const T* sp, const T* sr, const T* sx) const {
+    T pp[K], rr[K], xx[K];
+#pragma unroll
+    for (int c = 0; c < K; ++c) {
+      rr[c] = sr[c] - s.ao * acc[c];
+      pp[c] = rr[c] + s.b * sp[c];
+      xx[c] = sx[c] + s.a * pp[c];
+    }
+    store_vec<T, K>(r_ + (size_t)r * K, rr);
+    store_vec<T, K>(p_out + (size_t)r * K, pp);
+    store_vec<T, K>(x_ + (size_t)r * K, xx);
+  }
   __device__ void finish(State&) const {}
 };
 
@@ -142,6 +203,10 @@ template <typename T> struct EpiPower {  // PowerMethodGNN.py:156, :124, :183, :
     const T sq = v * v;
     s.s += (double)sq;
   }
+  static constexpr int kStreams = 0;
+  __host__ __device__ const T* stream_ptr(int) const { return nullptr; }
+  __host__ __device__ int stream_width(int) const { return 0; }
+  __device__ void row_staged(State& s, int r, const T (&acc)[1], const T*, const T*, const T*) const { row(s, r, acc); }
   __device__ void finish(State& s) const { grid_reduce2(s.s, 0.0, ws, sumsq_out); }
 };
 
@@ -169,6 +234,20 @@ template <typename T> struct EpiRayleigh {  // PowerMethodGNN.py:205, :235, :264
     s.s0 += (double)yA;
     s.s1 += (double)sq;
   }
+  static constexpr int kStreams = 1;
+  __host__ __device__ const T* stream_ptr(int) const { return b_in; }
+  __host__ __device__ int stream_width(int) const { return 1; }
+  __device__ void row_staged(State& s, int r, const T (&acc)[1], const T* sbi, const T*, const T*) const {
+    const T bi = sbi[0];
+    const T bn = s.scale ? bi / s.n : bi;
+    const T ab = s.scale ? acc[0] / s.n : acc[0];
+    const T yA = bn * ab;
+    const T sq = bn * bn;
+    b_out[r] = bn;
+    y_out[r] = sq;
+    s.s0 += (double)yA;
+    s.s1 += (double)sq;
+  }
   __device__ void finish(State& s) const { grid_reduce2(s.s0, s.s1, ws, sums_out); }
 };
 
@@ -182,6 +261,13 @@ template <typename T> struct EpiXtAx {  // MatrixWeightedNorm.py:107-109
     const T v = __ldg(x + r) * acc[0];
     s.s += (double)v;
   }
+  static constexpr int kStreams = 1;
+  __host__ __device__ const T* stream_ptr(int) const { return x; }
+  __host__ __device__ int stream_width(int) const { return 1; }
+  __device__ void row_staged(State& s, int r, const T (&acc)[1], const T* sx, const T*, const T*) const {
+    const T v = sx[0] * acc[0];
+    s.s += (double)v;
+  }
   __device__ void finish(State& s) const { grid_reduce2(s.s, 0.0, ws, sums_out); }
 };
 
@@ -190,13 +276,19 @@ struct Tuning {
   int rpt;        // rows per thread for K == 1 kernels (1 or 2)
   int cap_max;    // staging capacity upper bound in slots
   int persist;    // CTAs per SM for persistent (reducing) kernels
+  int pipe;       // 1 = use the TMA pipeline kernel when the tile fits (default), 0 = never
+  int stages;     // 0 = auto, else forced ring depth
+  int ctas;       // 0 = auto (occupancy API), else forced CTAs per SM for the pipeline
 };
 
 static const Tuning& tuning() {
   static Tuning t = [] {
-    Tuning v{1, 4096, 8};
+    Tuning v{1, 4096, 8, 1, 0, 0};
     if (const char* e = getenv("GLAB_RPT")) v.rpt = atoi(e) == 2 ? 2 : 1;
     if (const char* e = getenv("GLAB_CAP")) { int c = atoi(e); if (c >= 256 && c <= 8192) v.cap_max = c & ~31; }
+    if (const char* e = getenv("GLAB_PIPE")) v.pipe = atoi(e) != 0;
+    if (const char* e = getenv("GLAB_STAGES")) { int c = atoi(e); if (c >= 2 && c <= 8) v.stages = c; }
+    if (const char* e = getenv("GLAB_CTAS")) { int c = atoi(e); if (c >= 1 && c <= 8) v.ctas = c; }
     if (const char* e = getenv("GLAB_PERSIST")) { int c = atoi(e); if (c >= 1 && c <= 16) v.persist = c; }
     return v;
   }();
@@ -231,6 +323,88 @@ static int launch_tiles(const glab_plan* p, const T* vals, const T* x, const Epi
   return (int)cudaGetLastError();
 }
 
+
+static inline int round_up(int x, int m) { return (x + m - 1) / m * m; }
+
+constexpr int kNoPipe = -1000;
+template <typename T, int K, int U, class Epi>
+static int launch_pipe_u(const glab_plan*, const T*, const T*, const Epi&, int64_t, int64_t, void*);
+
+// U (gathers in flight per pass) follows the operator: 5- and 9-point stencils get an exact
+// unrolled row; anything else 8 (k = 1), 4 (k = 2) or 2 (k >= 4).
+template <typename T, int K, class Epi>
+static int launch_pipe(const glab_plan* p, const T* vals, const T* x, const Epi& epi, int64_t row_begin,
+                       int64_t row_end, void* stream) {
+  if constexpr (K == 1) {
+    if (p->max_row_nnz == 5) return launch_pipe_u<T, 1, 5>(p, vals, x, epi, row_begin, row_end, stream);
+    if (p->max_row_nnz == 9) return launch_pipe_u<T, 1, 9>(p, vals, x, epi, row_begin, row_end, stream);
+    return launch_pipe_u<T, 1, 8>(p, vals, x, epi, row_begin, row_end, stream);
+  } else {
+    return launch_pipe_u<T, K, (K == 2 ? 4 : 2)>(p, vals, x, epi, row_begin, row_end, stream);
+  }
+}
+constexpr int kNoPipeUnused = 0;  // sentinel: operator does not fit the pipeline, use the generic kernel
+
+// TMA pipeline launch.  Returns kNoPipe if the operator does not fit the pipeline (caller falls
+// back to the generic chunked kernel), 0 on success, or an error code.
+template <typename T, int K, int U, class Epi>
+static int launch_pipe_u(const glab_plan* p, const T* vals, const T* x, const Epi& epi, int64_t row_begin,
+                         int64_t row_end, void* stream) {
+  if (!tuning().pipe) return kNoPipe;
+  // 16-byte granule preconditions of the bulk copies (see k_row_pipe)
+  if ((reinterpret_cast<uintptr_t>(p->rowptr) & 15) || ((row_begin * 4) & 15)) return kNoPipe;
+  for (int i = 0; i < Epi::kStreams; ++i) {
+    if (reinterpret_cast<uintptr_t>(epi.stream_ptr(i)) & 15) return kNoPipe;
+    if ((row_begin * epi.stream_width(i) * (int64_t)sizeof(T)) & 15) return kNoPipe;
+  }
+  const int64_t slots = (int64_t)kThreads * (p->max_row_nnz > 0 ? p->max_row_nnz : 1);
+  if (slots > 24576) return kNoPipe;
+  PipeLayout L;
+  int off = 0;
+  L.off_row = off; off += round_up((kThreads + 1) * 4 + 32, 128);
+  L.off_col = off; off += round_up((int)slots * 4 + 32, 128);
+  L.off_val = off; off += round_up((int)slots * (int)sizeof(T) + 32, 128);
+  for (int i = 0; i < kMaxStreams; ++i) {
+    L.off_stream[i] = off;
+    if (i < Epi::kStreams) off += round_up(kThreads * epi.stream_width(i) * (int)sizeof(T) + 32, 128);
+  }
+  L.stage_bytes = off;
+  auto kern = k_row_pipe<T, K, U, Epi>;
+  static int max_smem = 0;  // per instantiation: 227 KB minus the kernel's static shared memory
+  if (!max_smem) {
+    cudaFuncAttributes fa;
+    GLAB_CUDA(cudaFuncGetAttributes(&fa, kern));
+    const int m = 227 * 1024 - (int)fa.sharedSizeBytes;
+    GLAB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, m));
+    max_smem = m;
+  }
+  if (2 * L.stage_bytes + 128 > max_smem) return kNoPipe;
+  // ring depth: enough stages that (CTAs/SM x stages) keeps >= ~128 KB in flight per SM, within smem
+  int want_ctas = tuning().ctas ? tuning().ctas : ((K * (int)sizeof(T) <= 8) ? 4 : 2);
+  int stages = tuning().stages;
+  if (!stages) {
+    stages = (max_smem / want_ctas - 128) / L.stage_bytes;
+    if (stages > 4) stages = 4;
+  }
+  while (stages > 2 && (size_t)stages * L.stage_bytes + 128 > (size_t)max_smem) --stages;
+  if (stages < 2) stages = 2;
+  L.stages = stages;
+  const size_t smem = (size_t)stages * L.stage_bytes + 128;
+  int occ = 0;
+  GLAB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kPipeThreads, smem));
+  if (occ < 1) return kNoPipe;
+  if (tuning().ctas && occ > tuning().ctas) occ = tuning().ctas;
+  const int64_t nrows = row_end - row_begin;
+  const int ntiles = (int)((nrows + kThreads - 1) / kThreads);
+  int grid = p->sm_count * occ;
+  if (grid > kMaxReduceBlocks) grid = kMaxReduceBlocks;
+  if (grid > ntiles) grid = ntiles;
+  if (grid < 1) grid = 1;
+  TileArgs<T> a{p->rowptr, p->colidx, vals, (int)row_begin, (int)row_end, (int)slots};
+  kern<<<grid, kPipeThreads, smem, as_stream(stream)>>>(a, x, epi, ntiles, L);
+  return (int)cudaGetLastError();
+}
+
 static int check_common(const glab_plan* p, const void* vals, const void* x, int64_t rb, int64_t re) {
   if (!p || !x) return GLAB_E_ARG;
   if (p->nnz > 0 && !vals) return GLAB_E_ARG;
@@ -243,6 +417,17 @@ template <typename T, template <typename, int> class EpiK, class Make>
 static int dispatch_k(const glab_plan* p, const T* vals, const T* x, int k, int64_t rb, int64_t re,
                       void* stream, Make make) {
   if (rb == re) return 0;
+  {
+    int rc = kNoPipe;
+    switch (k) {
+      case 1: rc = launch_pipe<T, 1>(p, vals, x, make(EpiK<T, 1>{}), rb, re, stream); break;
+      case 2: rc = launch_pipe<T, 2>(p, vals, x, make(EpiK<T, 2>{}), rb, re, stream); break;
+      case 4: rc = launch_pipe<T, 4>(p, vals, x, make(EpiK<T, 4>{}), rb, re, stream); break;
+      case 8: rc = launch_pipe<T, 8>(p, vals, x, make(EpiK<T, 8>{}), rb, re, stream); break;
+      default: return GLAB_E_ARG;
+    }
+    if (rc != kNoPipe) return rc;
+  }
   switch (k) {
     case 1:
       if (tuning().rpt == 2) return launch_tiles<T, 1, 2>(p, vals, x, make(EpiK<T, 1>{}), rb, re, false, stream);
@@ -319,6 +504,10 @@ template <typename T, class Epi>
 static int launch_reducing(const glab_plan* p, const T* vals, const T* x, const Epi& epi,
                            int64_t rb, int64_t re, void* stream) {
   // rb == re still launches one (empty) tile so the output sums are written (as zeros).
+  {
+    const int rc = launch_pipe<T, 1>(p, vals, x, epi, rb, re, stream);
+    if (rc != kNoPipe) return rc;
+  }
   if (tuning().rpt == 2) return launch_tiles<T, 1, 2>(p, vals, x, epi, rb, re, true, stream);
   return launch_tiles<T, 1, 1>(p, vals, x, epi, rb, re, true, stream);
 }

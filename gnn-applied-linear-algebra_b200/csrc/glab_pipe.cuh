@@ -1,0 +1,237 @@
+// glab_pipe.cuh -- persistent, warp-specialised, TMA-fed row-tile pipeline (the fast path of
+// every fused SpMV-bearing layer on sm_100a).
+//
+// Why: the plain one-tile-per-CTA kernel (glab_tiles.cuh) is latency bound -- every CTA walks
+// the dependent chain rowptr -> CSR stream -> barrier -> gather -> store, and ncu shows ~18
+// warps per issue slot parked on the long scoreboard at 49 % of the HBM roofline.  Here the
+// streaming part of the traffic (colidx, vals, the tile's rowptr slice and the row-aligned
+// slices of the epilogue's input vectors: diag / b / x_i / r / p) never touches a register on
+// its way in: ONE producer lane per CTA issues 1-D bulk asynchronous copies
+// (cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes, i.e. the TMA engine) into a
+// ring of `S` shared-memory stages, running S-1 tiles ahead of the 8 consumer warps, with
+// full/empty mbarriers per stage.  The consumers only do shared-memory reads, the L1/L2-served
+// gathers of x[col], the fused epilogue and coalesced stores.  Grid = (#SMs x CTAs/SM), tiles
+// are dealt round-robin so that concurrently running CTAs work on neighbouring row blocks and
+// share their gather windows in L2.
+#pragma once
+#include "glab_tiles.cuh"
+
+namespace glab {
+
+constexpr int kPipeThreads = kThreads + 32;  // 8 consumer warps + 1 producer warp
+constexpr int kMaxStreams = 3;               // row-aligned epilogue input vectors staged by TMA
+
+struct PipeLayout {
+  int stages;
+  int stage_bytes;             // multiple of 128
+  int off_col, off_val, off_row;
+  int off_stream[kMaxStreams];
+};
+
+// ---- mbarrier / bulk-copy PTX wrappers ------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_fence_init() {
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "WAIT_%=:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra DONE_%=;\n\t"
+      "bra WAIT_%=;\n\t"
+      "DONE_%=:\n\t"
+      "}" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+// global -> shared bulk copy through the TMA engine; src/dst 16-byte aligned, bytes % 16 == 0.
+__device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+          smem_u32(dst_smem)),
+      "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+      : "memory");
+}
+
+// [p, p + n*esz) widened to 16-byte granules: returns aligned start, bytes (multiple of 16).
+__device__ __forceinline__ void align16(const void* p, int nbytes, const void*& start, uint32_t& bytes) {
+  const uintptr_t p0 = reinterpret_cast<uintptr_t>(p);
+  const uintptr_t a0 = p0 & ~static_cast<uintptr_t>(15);
+  start = reinterpret_cast<const void*>(a0);
+  bytes = static_cast<uint32_t>(((p0 - a0) + (uintptr_t)nbytes + 15) & ~static_cast<uintptr_t>(15));
+}
+__device__ __forceinline__ int lead_elems(const void* p, int esz) {
+  return static_cast<int>(reinterpret_cast<uintptr_t>(p) & 15) / esz;
+}
+
+// Epilogue protocol for the pipeline (all in glab_layers.cu):
+//   static constexpr int kStreams;  const T* stream_ptr(i);  int stream_width(i)  (elements/row)
+//   State, init(State&), finish(State&)
+//   row_staged(State&, int r, const T (&acc)[K], const T* s0, const T* s1, const T* s2)
+//       s_i -> this row's elements of stream i in shared memory.
+// Host-checked preconditions: rowptr and every stream pointer are 16-byte aligned and
+// row_begin * width * sizeof(T) is a multiple of 16, so those slices start on a 16-byte granule
+// (only the colidx / vals slices, which start at an arbitrary CSR slot, carry a lead offset).
+// U = gathers kept in flight per thread per pass; rows of exactly U entries (every interior row
+// of a U-point stencil) take an unpredicated straight-line path.
+template <typename T, int K, int U, class Epi>
+__global__ void __launch_bounds__(kPipeThreads, (K * sizeof(T) <= 8) ? 4 : 2)
+k_row_pipe(TileArgs<T> a, const T* __restrict__ x, Epi epi, int ntiles, PipeLayout L) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw);
+  uint64_t* empty = full + L.stages;
+  unsigned char* stage0 = smem_raw + 128;  // barriers live in the first 128 bytes (<= 8 stages)
+  const int tid = threadIdx.x;
+  const int S = L.stages;
+
+  if (tid == 0) {
+    for (int s = 0; s < S; ++s) {
+      mbar_init(full + s, 1);
+      mbar_init(empty + s, kThreads / 32);
+    }
+    mbar_fence_init();
+  }
+  __syncthreads();
+
+  typename Epi::State st;
+  epi.init(st);
+
+  if (tid >= kThreads) {
+    // ------------------------------------------------------------------ producer warp
+    if (tid == kThreads) {
+      int tile = blockIdx.x;
+      int e0n = 0, e1n = 0;
+      if (tile < ntiles) {
+        const int r0 = a.row_begin + tile * kThreads;
+        e0n = __ldg(a.rowptr + r0);
+        e1n = __ldg(a.rowptr + min(r0 + kThreads, a.row_end));
+      }
+      int s = 0;
+      uint32_t phase = 0;
+      for (; tile < ntiles; tile += gridDim.x) {
+        const int r0 = a.row_begin + tile * kThreads;
+        const int r1 = min(r0 + kThreads, a.row_end);
+        const int e0 = e0n, e1 = e1n;
+        const int nt = tile + gridDim.x;
+        if (nt < ntiles) {  // prefetch the next tile's extents while this stage drains
+          const int q0 = a.row_begin + nt * kThreads;
+          e0n = __ldg(a.rowptr + q0);
+          e1n = __ldg(a.rowptr + min(q0 + kThreads, a.row_end));
+        }
+        mbar_wait(empty + s, phase ^ 1u);
+        unsigned char* sb = stage0 + (size_t)s * L.stage_bytes;
+        const void *src_c = nullptr, *src_v = nullptr;
+        uint32_t nb_c = 0, nb_v = 0, nb_s[kMaxStreams];
+        const uint32_t nb_r = (uint32_t)(((r1 - r0 + 1) * 4 + 15) & ~15);
+        uint32_t total = nb_r;
+        if (e1 > e0) {
+          align16(a.colidx + e0, (e1 - e0) * 4, src_c, nb_c);
+          align16(a.vals + e0, (e1 - e0) * (int)sizeof(T), src_v, nb_v);
+          total += nb_c + nb_v;
+        }
+#pragma unroll
+        for (int i = 0; i < kMaxStreams; ++i) {
+          nb_s[i] = 0;
+          if (i < Epi::kStreams) {
+            nb_s[i] = (uint32_t)(((r1 - r0) * epi.stream_width(i) * (int)sizeof(T) + 15) & ~15);
+            total += nb_s[i];
+          }
+        }
+        mbar_expect_tx(full + s, total);
+        bulk_g2s(sb + L.off_row, a.rowptr + r0, nb_r, full + s);
+        if (nb_c) {
+          bulk_g2s(sb + L.off_col, src_c, nb_c, full + s);
+          bulk_g2s(sb + L.off_val, src_v, nb_v, full + s);
+        }
+#pragma unroll
+        for (int i = 0; i < kMaxStreams; ++i)
+          if (i < Epi::kStreams)
+            bulk_g2s(sb + L.off_stream[i], epi.stream_ptr(i) + (size_t)r0 * epi.stream_width(i), nb_s[i],
+                     full + s);
+        if (++s == S) { s = 0; phase ^= 1u; }
+      }
+    }
+  } else {
+    // ------------------------------------------------------------------ consumer warps
+    int s = 0;
+    uint32_t phase = 0;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+      const int r0 = a.row_begin + tile * kThreads;
+      const int r1 = min(r0 + kThreads, a.row_end);
+      const int r = r0 + tid;
+      unsigned char* sb = stage0 + (size_t)s * L.stage_bytes;
+      const int32_t* srow = reinterpret_cast<const int32_t*>(sb + L.off_row);
+      mbar_wait(full + s, phase);
+      if (r < r1) {
+        const int e0 = srow[0];
+        const int rs = srow[tid], re = srow[tid + 1];
+        const int32_t* scol = reinterpret_cast<const int32_t*>(sb + L.off_col) + lead_elems(a.colidx + e0, 4) - e0;
+        const T* sval = reinterpret_cast<const T*>(sb + L.off_val) + lead_elems(a.vals + e0, sizeof(T)) - e0;
+        T acc[K];
+#pragma unroll
+        for (int c = 0; c < K; ++c) acc[c] = T(0);
+        if (re - rs == U) {
+          T vv[U];
+          T xv[U][K];
+#pragma unroll
+          for (int u = 0; u < U; ++u) {
+            const int col = scol[rs + u];
+            vv[u] = sval[rs + u];
+            load_vec<T, K>(xv[u], x + (size_t)col * K);
+          }
+#pragma unroll
+          for (int u = 0; u < U; ++u) {
+#pragma unroll
+            for (int c = 0; c < K; ++c) acc[c] = acc[c] + vv[u] * xv[u][c];
+          }
+        } else {
+          for (int base = rs; base < re; base += U) {
+            T vv[U];
+            T xv[U][K];
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+              if (base + u < re) {
+                const int col = scol[base + u];
+                vv[u] = sval[base + u];
+                load_vec<T, K>(xv[u], x + (size_t)col * K);
+              }
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+              if (base + u < re) {
+#pragma unroll
+                for (int c = 0; c < K; ++c) acc[c] = acc[c] + vv[u] * xv[u][c];
+              }
+            }
+          }
+        }
+        const T* sp[kMaxStreams] = {nullptr, nullptr, nullptr};
+#pragma unroll
+        for (int i = 0; i < kMaxStreams; ++i)
+          if (i < Epi::kStreams)
+            sp[i] = reinterpret_cast<const T*>(sb + L.off_stream[i]) + (size_t)tid * epi.stream_width(i);
+        epi.row_staged(st, r, acc, sp[0], sp[1], sp[2]);
+      }
+      __syncwarp();
+      if ((tid & 31) == 0) mbar_arrive(empty + s);
+      if (++s == S) { s = 0; phase ^= 1u; }
+    }
+  }
+  epi.finish(st);
+}
+
+}  // namespace glab

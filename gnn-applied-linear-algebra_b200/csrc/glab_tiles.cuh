@@ -98,7 +98,7 @@ k_row_tiles(TileArgs<T> a, const T* __restrict__ x, Epi epi, int ntiles) {
 // byte 64: partial[2*cta + {0,1}].
 // ------------------------------------------------------------------------------------------
 __device__ __forceinline__ void grid_reduce2(double s0, double s1, void* ws, double* out) {
-  __shared__ double red[2][kThreads / 32];
+  __shared__ double red[2][16];  // up to 16 warps per CTA
   __shared__ bool is_last;
   unsigned int* ticket = reinterpret_cast<unsigned int*>(ws);
   double* partial = reinterpret_cast<double*>(reinterpret_cast<unsigned char*>(ws) + 64);
@@ -109,8 +109,7 @@ __device__ __forceinline__ void grid_reduce2(double s0, double s1, void* ws, dou
   __syncthreads();
   if (tid == 0) {
     double t0 = 0, t1 = 0;
-#pragma unroll
-    for (int i = 0; i < kThreads / 32; ++i) { t0 += red[0][i]; t1 += red[1][i]; }
+    for (int i = 0; i < (int)(blockDim.x >> 5); ++i) { t0 += red[0][i]; t1 += red[1][i]; }
     partial[2 * blockIdx.x] = t0;
     partial[2 * blockIdx.x + 1] = t1;
     __threadfence();
@@ -121,7 +120,7 @@ __device__ __forceinline__ void grid_reduce2(double s0, double s1, void* ws, dou
   if (is_last) {
     __threadfence();
     double t0 = 0, t1 = 0;
-    for (int i = tid; i < (int)gridDim.x; i += kThreads) {
+    for (int i = tid; i < (int)gridDim.x; i += (int)blockDim.x) {
       t0 += __ldcg(partial + 2 * i);
       t1 += __ldcg(partial + 2 * i + 1);
     }
@@ -132,8 +131,7 @@ __device__ __forceinline__ void grid_reduce2(double s0, double s1, void* ws, dou
     __syncthreads();
     if (tid == 0) {
       double u0 = 0, u1 = 0;
-#pragma unroll
-      for (int i = 0; i < kThreads / 32; ++i) { u0 += red[0][i]; u1 += red[1][i]; }
+      for (int i = 0; i < (int)(blockDim.x >> 5); ++i) { u0 += red[0][i]; u1 += red[1][i]; }
       out[0] = u0;
       out[1] = u1;
       *ticket = 0u;  // re-arm for the next stream-ordered call
