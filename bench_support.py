@@ -78,3 +78,120 @@ class SingleGpuSmoother:
         v, e, g = self.cheb(torch.cat([va[:, 1:2], x1], 1), self.ei, self.ev, self.gc)
         self.out_host.copy_(v[:, 1:2])          # D2H of the step's result (synchronous)
         return self.out_host
+
+
+class PartitionedSmoother:
+    """The same smoothing pass on an operator row-block partitioned over `world` GPUs (strong
+    scaling): each rank builds only its slab of the stencil, halo rows travel over NVLink peer
+    memory (glab_halo_push / glab_halo_wait), and the whole pass is replayed as one CUDA graph."""
+
+    N_JACOBI, CHEB_DEG, OMEGA, CHEB_C, CHEB_D = 10, 4, 0.7, -3.4, -4.0
+
+    def __init__(self, G, N, dev, rank, world, engine="peer", use_graph=True):
+        import torch.distributed as dist
+        from glab_b200 import dist as gd
+        self.G, self.rt, self.dev, self.rank, self.world = G, G.runtime, dev, rank, world
+        n = N * N
+        t0 = time.perf_counter()
+        self.part = gd.RowPartition(n, world, align=256)
+        r0, r1 = self.part.bounds(rank)
+        ei, ev = G.generators.laplacian_2d(N, torch.float64, dev, rows=(r0, r1))
+        ev = ev.float().contiguous()
+        self.halo = gd.HaloPlan.build(self.part, rank, ei[1])
+        lei = torch.stack([ei[0] - r0, self.halo.local_columns(ei[1])]).contiguous()
+        del ei
+        torch.cuda.synchronize()
+        t1 = time.perf_counter()
+        self.op = gd.DistOperator(lei, ev, self.halo, k=1, engine=engine)
+        torch.cuda.synchronize()
+        t2 = time.perf_counter()
+        nl = self.halo.n_local
+        self.n_local, self.nnz_local = nl, self.op.plan.nnz
+        z = torch.tensor([self.nnz_local], dtype=torch.int64, device=dev)
+        dist.all_reduce(z)
+        self.nnz_global = int(z.item())
+        self.setup_info = {"generate_ms": (t1 - t0) * 1e3, "plan_build_ms": (t2 - t1) * 1e3, "engine": engine,
+                           "rows_local": nl, "halo_rows": self.halo.n_halo, "interior": [self.op.lo, self.op.hi],
+                           "cuda_graph": bool(use_graph)}
+        g = torch.Generator().manual_seed(24601 + rank)
+        self.b_host = torch.rand(nl, 1, generator=g).pin_memory()
+        self.x_host = torch.rand(nl, 1, generator=g).pin_memory()
+        self.out_host = torch.empty(nl, 1).pin_memory()
+        self.diag = torch.full((nl,), -4.0, device=dev)
+        self.b = self.b_host.to(dev).contiguous()
+        self.x_stage = torch.empty(nl, 1, device=dev)
+        self.w = torch.tensor([self.OMEGA], device=dev)
+        rows, _ = G.ChebyGNN._recurrence(self.CHEB_DEG, torch.tensor([self.CHEB_C, self.CHEB_D]))
+        self.table = torch.stack([torch.stack(r) for r in rows]).to(dev).contiguous()
+        self.x = torch.empty(nl, 1, device=dev)
+        self.r = torch.empty(nl, 1, device=dev)
+        self.op.load("v0", self.x_host.to(dev))
+        torch.cuda.synchronize()
+        dist.barrier()
+        self.h2d_bytes = 2 * nl * 4
+        self.d2h_bytes = nl * 4
+        self.graph = None
+        self.jac_graph = None
+        self.use_graph = use_graph and engine == "peer"
+        if self.use_graph:
+            self._capture()
+
+    def _sweeps(self):
+        op = self.op
+        op.publish("v0")
+        return op.jacobi(self.N_JACOBI, self.diag, self.b, self.w, "v0")
+
+    def _pass(self):
+        cur = self._sweeps()
+        self.op.chebyshev(self.CHEB_DEG, self.b, self.table, cur, self.x, self.r)
+
+    def _capture(self):
+        import torch.distributed as dist
+        s = torch.cuda.Stream()
+        s.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(s):
+            self._pass()          # warm every kernel (attribute setup, lazy init) before capture
+        torch.cuda.current_stream().wait_stream(s)
+        torch.cuda.synchronize()
+        dist.barrier()
+        c0 = self.rt.launch_count
+        self.jac_graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.jac_graph):
+            self._jac_result = self._sweeps()
+        c1 = self.rt.launch_count
+        self.cheb_graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.cheb_graph):
+            self.op.chebyshev(self.CHEB_DEG, self.b, self.table, self._jac_result, self.x, self.r)
+        self.graph_launches = (c1 - c0, self.rt.launch_count - c1)   # kernels inside each graph
+        torch.cuda.synchronize()
+        dist.barrier()
+
+    def step_kernels(self, time_jacobi=False):
+        ev = None
+        if time_jacobi:
+            ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+            ev[0].record()
+        if self.use_graph:
+            self.jac_graph.replay()
+            self.rt.launch_count += sum(self.graph_launches)
+        else:
+            cur = self._sweeps()
+        if time_jacobi:
+            ev[1].record()
+        if self.use_graph:
+            self.cheb_graph.replay()
+        else:
+            self.op.chebyshev(self.CHEB_DEG, self.b, self.table, cur, self.x, self.r)
+        return ev
+
+    def step_e2e(self):
+        dev = self.dev
+        self.b.copy_(self.b_host, non_blocking=True)
+        self.x_stage.copy_(self.x_host, non_blocking=True)
+        self.op.vec["v0"][:self.n_local].copy_(self.x_stage)
+        self.step_kernels()
+        self.out_host.copy_(self.x)
+        return self.out_host
+
+    def close(self):
+        self.op.close()

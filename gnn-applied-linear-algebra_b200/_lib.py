@@ -51,7 +51,14 @@ _sig("glab_ipc_alloc", c_int, _I64, POINTER(P), P)
 _sig("glab_ipc_open", c_int, P, POINTER(P))
 _sig("glab_ipc_close", c_int, P)
 _sig("glab_ipc_free", c_int, P)
-_sig("glab_halo_wait", c_int, P, c_uint32, P)
+
+
+class PushDesc(ctypes.Structure):
+    _fields_ = [("send_idx", c_void_p), ("count", c_int64), ("dst", c_void_p), ("dst_offset", c_int64),
+                ("flag", c_void_p)]
+
+
+_sig("glab_halo_wait", c_int, c_int, POINTER(c_void_p), POINTER(c_void_p), P)
 
 for _suf, _ct in (("f32", c_float), ("f64", c_double)):
     _sig("glab_gather_vals_" + _suf, c_int, P, P, _I64, _I64, P, P)
@@ -71,7 +78,7 @@ for _suf, _ct in (("f32", c_float), ("f64", c_double)):
     _sig("glab_soc_classic_" + _suf, c_int, P, P, _ct, P, P, P)
     _sig("glab_soc_sa_" + _suf, c_int, P, P, P, P, P)
     _sig("glab_direct_interp_" + _suf, c_int, P, P, P, P, P, P, P)
-    _sig("glab_halo_push_" + _suf, c_int, P, P, _I64, _INT, P, _I64, P, c_uint32, P)
+    _sig("glab_halo_push_" + _suf, c_int, P, _INT, _INT, POINTER(PushDesc), P)
 
 
 def check(rc, what=""):

@@ -12,41 +12,55 @@
 
 namespace glab {
 
+struct PushArgs {
+  glab_push_desc d[GLAB_MAX_PEERS];
+};
+
 template <typename T, int K>
-__global__ void k_halo_push(const T* __restrict__ src, const int32_t* __restrict__ send_idx,
-                            int64_t count, T* __restrict__ dst, int64_t dst_offset,
-                            uint32_t* flag, uint32_t flag_value, unsigned int* done_counter) {
-  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < count;
+__global__ void k_halo_push(const T* __restrict__ src, PushArgs a, unsigned int* done_counter) {
+  const glab_push_desc d = a.d[blockIdx.y];
+  T* __restrict__ dst = reinterpret_cast<T*>(d.dst);
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < d.count;
        i += (int64_t)gridDim.x * blockDim.x) {
     T v[K];
-    load_vec_rw<T, K>(v, src + (size_t)send_idx[i] * K);
-    store_vec<T, K>(dst + (size_t)(dst_offset + i) * K, v);
+    load_vec_rw<T, K>(v, src + (size_t)d.send_idx[i] * K);
+    store_vec<T, K>(dst + (size_t)(d.dst_offset + i) * K, v);
   }
-  if (flag == nullptr) return;
-  // last CTA to finish publishes the flag after all peer stores are visible system-wide
+  if (d.flag == nullptr) return;
+  // the last CTA of this peer's slice publishes the arrival after all stores are visible
   __threadfence_system();
   __syncthreads();
   if (threadIdx.x == 0) {
-    const unsigned int t = atomicAdd(done_counter, 1u);
+    const unsigned int t = atomicAdd(done_counter + blockIdx.y, 1u);
     if (t == gridDim.x - 1) {
-      *done_counter = 0u;
+      done_counter[blockIdx.y] = 0u;
       __threadfence_system();
-      asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(flag), "r"(flag_value) : "memory");
+      asm volatile("red.release.sys.global.add.u32 [%0], 1;" ::"l"(d.flag) : "memory");
     }
   }
 }
 
-__global__ void k_halo_wait(uint32_t* flag, uint32_t flag_value) {
+struct WaitArgs {
+  uint32_t* flag[GLAB_MAX_PEERS];
+  uint32_t* expect[GLAB_MAX_PEERS];
+};
+
+__global__ void k_halo_wait(WaitArgs a, int n) {
+  const int i = threadIdx.x;
+  if (i >= n) return;
+  const uint32_t want = *a.expect[i] + 1u;
+  *a.expect[i] = want;
   uint32_t v;
   do {
-    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(flag) : "memory");
-    if ((int32_t)(v - flag_value) >= 0) break;
-    __nanosleep(64);
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(a.flag[i]) : "memory");
+    if ((int32_t)(v - want) >= 0) break;
+    __nanosleep(32);
   } while (true);
 }
 
-static unsigned int* done_counter_for_device() {
-  // one 4-byte counter per process/device, zero-initialised; pushes on one stream are ordered.
+static unsigned int* done_counters() {
+  // GLAB_MAX_PEERS 4-byte counters per process/device, zero-initialised; pushes on one stream
+  // are ordered, and every launch leaves them at zero.
   static unsigned int* ctr = nullptr;
   if (!ctr) {
     if (cudaMalloc(&ctr, 256) != cudaSuccess) return nullptr;
@@ -56,20 +70,27 @@ static unsigned int* done_counter_for_device() {
 }
 
 template <typename T>
-static int halo_push(const T* src, const int32_t* send_idx, int64_t count, int k, T* dst,
-                     int64_t dst_offset, uint32_t* flag, uint32_t flag_value, void* stream) {
-  if (count < 0 || (count > 0 && (!src || !send_idx || !dst))) return GLAB_E_ARG;
-  unsigned int* ctr = done_counter_for_device();
+static int halo_push(const T* src, int k, int n_peers, const glab_push_desc* descs, void* stream) {
+  if (n_peers < 0 || n_peers > GLAB_MAX_PEERS || (n_peers > 0 && (!src || !descs))) return GLAB_E_ARG;
+  if (n_peers == 0) return 0;
+  PushArgs a;
+  int64_t mx = 1;
+  for (int q = 0; q < n_peers; ++q) {
+    a.d[q] = descs[q];
+    if (descs[q].count < 0 || (descs[q].count > 0 && (!descs[q].send_idx || !descs[q].dst))) return GLAB_E_ARG;
+    if (descs[q].count > mx) mx = descs[q].count;
+  }
+  unsigned int* ctr = done_counters();
   if (!ctr) return GLAB_E_NOMEM;
-  int64_t b = (count + 255) / 256;
-  if (b < 1) b = 1;
-  if (b > 64) b = 64;
+  int64_t b = (mx + 255) / 256;
+  if (b > 32) b = 32;
+  dim3 grid((unsigned)b, (unsigned)n_peers);
   cudaStream_t st = as_stream(stream);
   switch (k) {
-    case 1: k_halo_push<T, 1><<<(int)b, 256, 0, st>>>(src, send_idx, count, dst, dst_offset, flag, flag_value, ctr); break;
-    case 2: k_halo_push<T, 2><<<(int)b, 256, 0, st>>>(src, send_idx, count, dst, dst_offset, flag, flag_value, ctr); break;
-    case 4: k_halo_push<T, 4><<<(int)b, 256, 0, st>>>(src, send_idx, count, dst, dst_offset, flag, flag_value, ctr); break;
-    case 8: k_halo_push<T, 8><<<(int)b, 256, 0, st>>>(src, send_idx, count, dst, dst_offset, flag, flag_value, ctr); break;
+    case 1: k_halo_push<T, 1><<<grid, 256, 0, st>>>(src, a, ctr); break;
+    case 2: k_halo_push<T, 2><<<grid, 256, 0, st>>>(src, a, ctr); break;
+    case 4: k_halo_push<T, 4><<<grid, 256, 0, st>>>(src, a, ctr); break;
+    case 8: k_halo_push<T, 8><<<grid, 256, 0, st>>>(src, a, ctr); break;
     default: return GLAB_E_ARG;
   }
   return (int)cudaGetLastError();
@@ -121,16 +142,21 @@ extern "C" int glab_ipc_free(void* dev_ptr) {
   return 0;
 }
 
-extern "C" int glab_halo_push_f32(const float* src, const int32_t* idx, int64_t count, int k,
-                                  float* dst, int64_t off, uint32_t* flag, uint32_t val, void* s) {
-  return halo_push<float>(src, idx, count, k, dst, off, flag, val, s);
+extern "C" int glab_halo_push_f32(const float* src, int k, int n, const glab_push_desc* d, void* s) {
+  return halo_push<float>(src, k, n, d, s);
 }
-extern "C" int glab_halo_push_f64(const double* src, const int32_t* idx, int64_t count, int k,
-                                  double* dst, int64_t off, uint32_t* flag, uint32_t val, void* s) {
-  return halo_push<double>(src, idx, count, k, dst, off, flag, val, s);
+extern "C" int glab_halo_push_f64(const double* src, int k, int n, const glab_push_desc* d, void* s) {
+  return halo_push<double>(src, k, n, d, s);
 }
-extern "C" int glab_halo_wait(uint32_t* flag, uint32_t val, void* s) {
-  if (!flag) return GLAB_E_ARG;
-  k_halo_wait<<<1, 1, 0, as_stream(s)>>>(flag, val);
+extern "C" int glab_halo_wait(int n, uint32_t* const* flags, uint32_t* const* expect, void* s) {
+  if (n < 0 || n > GLAB_MAX_PEERS || (n > 0 && (!flags || !expect))) return GLAB_E_ARG;
+  if (n == 0) return 0;
+  WaitArgs a;
+  for (int i = 0; i < n; ++i) {
+    if (!flags[i] || !expect[i]) return GLAB_E_ARG;
+    a.flag[i] = flags[i];
+    a.expect[i] = expect[i];
+  }
+  k_halo_wait<<<1, 32, 0, as_stream(s)>>>(a, n);
   return (int)cudaGetLastError();
 }

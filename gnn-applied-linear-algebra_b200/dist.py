@@ -1,0 +1,440 @@
+"""Row-block partitioning + halo exchange for the multi-GPU path (one process per GPU).
+
+The reference is single-process CPU code; this module is the new piece that BASELINE.json's
+north_star asks for: "large structured operators are row-block partitioned across the GPUs of
+one box; each smoother/matvec step exchanges halo rows; the power method's norms use an
+allreduce".
+
+Layout per rank r (P ranks):
+  * rows [off[r], off[r+1]) of the operator, as a local CSR plan with n_rows = n_local and
+    n_cols = n_local + n_halo: local columns keep their order (col - off[r]); columns owned by
+    other ranks are renumbered n_local + (position in the sorted list of needed halo columns),
+    so the halo tail is grouped by owner and ordered by global index;
+  * every gathered vector is [n_local + n_halo, k]; the halo tail is refreshed before each
+    SpMV-bearing step.
+Two exchange engines share the same plan:
+  * `exchange()`  -- torch.distributed isend/irecv of packed rows (gloo on CPU for the tests,
+    NCCL on GPUs): the portable baseline;
+  * `PeerHalo`    -- CUDA-IPC peer memory over NVLink: a pack kernel STORES this rank's boundary
+    rows directly into the neighbour's halo tail and publishes an epoch flag; the consumer waits
+    on its flag in-stream (glab_halo_push_* / glab_halo_wait).  No NCCL call on the data path.
+The partition logic (this file's torch index arithmetic) is covered on CPU by
+tests/test_dist_cpu.py with world_size-2 gloo.
+"""
+import ctypes
+
+import torch
+import torch.distributed as dist
+
+from . import _runtime as rt
+from ._lib import check, lib
+
+
+class RowPartition:
+    """Contiguous row blocks: rank r owns rows [offsets[r], offsets[r+1])."""
+
+    def __init__(self, n, world, align=1):
+        base = (n // world) // align * align
+        offs = [min(r * base, n) for r in range(world)] + [n]
+        self.n, self.world = n, world
+        self.offsets = torch.tensor(offs, dtype=torch.int64)
+
+    def bounds(self, rank):
+        return int(self.offsets[rank]), int(self.offsets[rank + 1])
+
+    def owner(self, cols):
+        """Owning rank of each global column index."""
+        offs = self.offsets.to(cols.device)
+        return torch.bucketize(cols, offs[1:-1], right=True)
+
+
+class HaloPlan:
+    """What this rank needs from / must send to every peer, derived from the global column
+    indices of its row block (works for any matrix, not only stencils)."""
+
+    def __init__(self, part, rank, halo_cols, recv_counts, send_rows):
+        self.part, self.rank = part, rank
+        self.r0, self.r1 = part.bounds(rank)
+        self.n_local = self.r1 - self.r0
+        self.halo_cols = halo_cols                      # sorted global ids, int64
+        self.n_halo = int(halo_cols.numel())
+        self.recv_counts = recv_counts                  # python list per peer
+        self.recv_offsets = [0] * part.world
+        acc = 0
+        for q in range(part.world):
+            self.recv_offsets[q] = acc
+            acc += recv_counts[q]
+        self.send_rows = send_rows                      # per peer: LOCAL row ids (int32 tensors)
+        self.peers_recv = [q for q in range(part.world) if recv_counts[q] > 0]
+        self.peers_send = [q for q in range(part.world) if send_rows[q].numel() > 0]
+
+    @classmethod
+    def build(cls, part, rank, global_cols, group=None):
+        """global_cols: int64 tensor of the GLOBAL column index of every local edge."""
+        r0, r1 = part.bounds(rank)
+        dev = global_cols.device
+        outside = (global_cols < r0) | (global_cols >= r1)
+        halo_cols = torch.unique(global_cols[outside])             # sorted
+        owners = part.owner(halo_cols)
+        recv_counts = torch.bincount(owners, minlength=part.world).tolist()
+        # tell every owner which of its rows we need
+        need = [halo_cols[owners == q].cpu() for q in range(part.world)]
+        if part.world == 1:
+            gathered = [need]
+        else:
+            gathered = [None] * part.world
+            dist.all_gather_object(gathered, need, group=group)
+        send_rows = []
+        for q in range(part.world):
+            wanted = gathered[q][rank] if q != rank else torch.empty(0, dtype=torch.int64)
+            send_rows.append((wanted - r0).to(torch.int32).to(dev))
+        return cls(part, rank, halo_cols, recv_counts, send_rows)
+
+    def local_columns(self, global_cols):
+        """Global -> local column numbering (local block first, halo tail after)."""
+        r0, r1 = self.r0, self.r1
+        inside = (global_cols >= r0) & (global_cols < r1)
+        pos = torch.searchsorted(self.halo_cols, global_cols.clamp(min=0))
+        return torch.where(inside, global_cols - r0, pos + self.n_local)
+
+    def interior_rows(self, local_rows, local_cols, align=256):
+        """[lo, hi): a contiguous range of rows none of which reads the halo tail (aligned to the
+        kernel's 256-row tiles).  Rows outside it must wait for the exchange."""
+        touches = torch.zeros(self.n_local, dtype=torch.bool, device=local_rows.device)
+        touches[local_rows[local_cols >= self.n_local]] = True
+        idx = torch.nonzero(touches).reshape(-1)
+        if idx.numel() == 0:
+            return 0, self.n_local
+        mid = self.n_local // 2
+        lead = idx[idx < mid]
+        trail = idx[idx >= mid]
+        lo = int(lead.max()) + 1 if lead.numel() else 0
+        hi = int(trail.min()) if trail.numel() else self.n_local
+        lo = min((lo + align - 1) // align * align, self.n_local)
+        hi = max(hi // align * align, lo)
+        return lo, hi
+
+    # ------------------------------------------------------------------ portable exchange
+    def exchange(self, x_ext, group=None):
+        """Refresh the halo tail of x_ext ([n_local + n_halo, k]) with isend/irecv."""
+        if self.part.world == 1:
+            return
+        ops, keep = [], []
+        for q in self.peers_recv:
+            a = self.n_local + self.recv_offsets[q]
+            buf = x_ext[a:a + self.recv_counts[q]]
+            ops.append(dist.P2POp(dist.irecv, buf, q, group=group))
+        for q in self.peers_send:
+            buf = x_ext.index_select(0, self.send_rows[q].long())
+            keep.append(buf)
+            ops.append(dist.P2POp(dist.isend, buf, q, group=group))
+        for w in dist.batch_isend_irecv(ops):
+            w.wait()
+
+
+def partition_coo(edge_index, edge_val, part, rank, group=None):
+    """Rows of a GLOBAL COO that belong to `rank`, renumbered for the local plan.
+    Returns (local_edge_index [2, z_loc], local_vals [z_loc, F], HaloPlan)."""
+    r0, r1 = part.bounds(rank)
+    mine = (edge_index[0] >= r0) & (edge_index[0] < r1)
+    rows = edge_index[0][mine] - r0
+    gcols = edge_index[1][mine]
+    halo = HaloPlan.build(part, rank, gcols, group)
+    cols = halo.local_columns(gcols)
+    return torch.stack([rows, cols]), edge_val[mine], halo
+
+
+def extend(x_local, n_halo):
+    """[n_local, k] -> [n_local + n_halo, k] with a zero halo tail."""
+    tail = torch.zeros((n_halo,) + tuple(x_local.shape[1:]), dtype=x_local.dtype, device=x_local.device)
+    return torch.cat([x_local, tail], 0).contiguous()
+
+
+# ---------------------------------------------------------------------------- NVLink peer path
+class PeerBuffer:
+    """A device buffer other ranks can map (CUDA IPC).  `local` is a torch view of our copy,
+    `peer_ptr[q]` the address of rank q's copy in OUR address space."""
+
+    def __init__(self, numel, dtype, device, group=None):
+        self.dtype, self.device, self.numel = dtype, device, numel
+        esz = torch.empty(0, dtype=dtype).element_size()
+        nbytes = max(numel * esz, 16)
+        hb = lib.glab_ipc_handle_bytes()
+        handle = (ctypes.c_ubyte * hb)()
+        p = ctypes.c_void_p()
+        with torch.cuda.device(device):
+            check(lib.glab_ipc_alloc(nbytes, ctypes.byref(p), handle), "glab_ipc_alloc")
+        self._ptr = p.value
+        typestr = {torch.float32: "<f4", torch.float64: "<f8", torch.int32: "<i4", torch.uint8: "|u1"}[dtype]
+        self.local = torch.as_tensor(rt._DevArray(self._ptr, max(numel, 1), typestr, self), device=device)[:numel]
+        world = dist.get_world_size(group) if dist.is_initialized() else 1
+        rank = dist.get_rank(group) if dist.is_initialized() else 0
+        handles = [None] * world
+        if world > 1:
+            dist.all_gather_object(handles, bytes(handle), group=group)
+        self.peer_ptr = {}
+        self._opened = []
+        for q in range(world):
+            if q == rank:
+                self.peer_ptr[q] = self._ptr
+                continue
+            hq = (ctypes.c_ubyte * hb).from_buffer_copy(handles[q])
+            pq = ctypes.c_void_p()
+            with torch.cuda.device(device):
+                check(lib.glab_ipc_open(hq, ctypes.byref(pq)), "glab_ipc_open")
+            self.peer_ptr[q] = pq.value
+            self._opened.append(pq.value)
+
+    def close(self):
+        for p in self._opened:
+            lib.glab_ipc_close(ctypes.c_void_p(p))
+        self._opened = []
+        if self._ptr:
+            lib.glab_ipc_free(ctypes.c_void_p(self._ptr))
+            self._ptr = None
+
+
+class PeerHalo:
+    """Push-style halo exchange over peer memory for a set of named vectors.
+
+    Every exchanged vector lives in a PeerBuffer of (n_local + n_halo) * k elements.  push(name)
+    is ONE kernel launch that packs this rank's boundary rows of vector `name` straight into
+    each neighbour's halo tail of the SAME-named vector and increments that neighbour's arrival
+    counter; wait(name) is ONE single-CTA kernel that orders the consumer behind the arrival of
+    all its neighbours' pushes.  Counters only count up (no host-side epoch), so a captured CUDA
+    graph of sweeps can be replayed."""
+
+    def __init__(self, halo, k, dtype, device, names, group=None):
+        from ._lib import PushDesc
+        self.halo, self.k, self.dtype, self.device, self.group = halo, k, dtype, device, group
+        self.rank = halo.rank
+        ext = halo.n_local + halo.n_halo
+        self.bufs = {nm: PeerBuffer(ext * k, dtype, device, group) for nm in names}
+        self.views = {nm: b.local.view(ext, k) for nm, b in self.bufs.items()}
+        world = halo.part.world
+        # words (16-byte spaced): arrival counter [name][peer] (bumped remotely by that peer) and
+        # expect counter [name][peer] (local bookkeeping of the wait kernel)
+        self.flag_index = {nm: i for i, nm in enumerate(names)}
+        self.flags = PeerBuffer(2 * len(names) * world * 4, torch.int32, device, group)
+        offs = [None] * world
+        if world > 1:
+            dist.all_gather_object(offs, halo.recv_offsets, group=group)
+        else:
+            offs = [halo.recv_offsets]
+        peer_n_local = [halo.part.bounds(q)[1] - halo.part.bounds(q)[0] for q in range(world)]
+        self._suf = rt.suffix(dtype)
+        self._push_desc, self._wait_args = {}, {}
+        nw = len(names) * world
+        for nm in names:
+            descs = (PushDesc * max(len(halo.peers_send), 1))()
+            for i, q in enumerate(halo.peers_send):
+                idx = halo.send_rows[q]
+                descs[i].send_idx = idx.data_ptr()
+                descs[i].count = idx.numel()
+                descs[i].dst = self.bufs[nm].peer_ptr[q]
+                descs[i].dst_offset = peer_n_local[q] + offs[q][self.rank]
+                descs[i].flag = self.flags.peer_ptr[q] + (self.flag_index[nm] * world + self.rank) * 16
+            self._push_desc[nm] = descs
+            nf = len(halo.peers_recv)
+            fl = (ctypes.c_void_p * max(nf, 1))()
+            ex = (ctypes.c_void_p * max(nf, 1))()
+            base = self.flags.peer_ptr[self.rank]
+            for i, q in enumerate(halo.peers_recv):
+                fl[i] = base + (self.flag_index[nm] * world + q) * 16
+                ex[i] = base + (nw + self.flag_index[nm] * world + q) * 16
+            self._wait_args[nm] = (nf, fl, ex)
+        if world > 1:
+            dist.barrier(group=group)
+
+    def push(self, name):
+        """After the kernel that produced vector `name`: send boundary rows to every neighbour."""
+        n = len(self.halo.peers_send)
+        if n == 0:
+            return
+        fn = getattr(lib, "glab_halo_push_" + self._suf)
+        rt.launch_count += 1
+        with torch.cuda.device(self.device):
+            check(fn(rt.ptr(self.views[name]), self.k, n, self._push_desc[name], rt.stream_ptr()),
+                  "glab_halo_push")
+
+    def wait(self, name):
+        """Before the kernel that gathers vector `name`'s halo tail."""
+        nf, fl, ex = self._wait_args[name]
+        if nf == 0:
+            return
+        rt.launch_count += 1
+        with torch.cuda.device(self.device):
+            check(lib.glab_halo_wait(nf, fl, ex, rt.stream_ptr()), "glab_halo_wait")
+
+    def close(self):
+        torch.cuda.synchronize(self.device)
+        if dist.is_initialized() and self.halo.part.world > 1:
+            dist.barrier(group=self.group)
+        for b in self.bufs.values():
+            b.close()
+        self.flags.close()
+
+
+class DistOperator:
+    """One rank's row block of an operator + the halo machinery, with the fused layer steps of
+    the single-GPU path applied block-wise:
+
+        interior rows (no halo column)   -> kernel launched immediately
+        wait for the neighbours' pushes  -> glab_halo_wait
+        boundary rows                    -> kernel(s) on the two edge ranges
+        push the new boundary values     -> glab_halo_push
+
+    engine = "peer" (NVLink peer memory, default on GPUs) or "torch" (isend/irecv through
+    torch.distributed: NCCL on GPUs, gloo in the CPU tests -- there the kernels are replaced by
+    the caller's own local step, see tests/test_dist_cpu.py)."""
+
+    def __init__(self, local_edge_index, local_vals, halo, k=1, engine="peer", group=None):
+        self.halo, self.k, self.group, self.engine = halo, k, group, engine
+        self.device = local_vals.device
+        self.dtype = local_vals.dtype
+        n_loc, n_ext = halo.n_local, halo.n_local + halo.n_halo
+        self.plan = rt.Plan.from_coo(local_edge_index.contiguous(), n_loc, n_ext)
+        self.vals = rt.get_vals(self.plan, local_vals.view(-1, 1))
+        self._keep = (local_edge_index, local_vals)
+        self.lo, self.hi = halo.interior_rows(local_edge_index[0], local_edge_index[1])
+        self.names = ["v0", "va", "vb"]
+        if engine == "peer":
+            self.peer = PeerHalo(halo, k, self.dtype, self.device, self.names, group)
+            self.vec = self.peer.views
+        else:
+            self.peer = None
+            self.vec = {nm: torch.zeros(n_ext, k, dtype=self.dtype, device=self.device) for nm in self.names}
+        self.n_local, self.n_ext = n_loc, n_ext
+
+    # -- halo plumbing -----------------------------------------------------------------------
+    def publish(self, name):
+        """Make the local rows of vector `name` visible in the neighbours' halo tails."""
+        if self.halo.part.world == 1:
+            return
+        if self.peer is not None:
+            self.peer.push(name)
+        else:
+            self.halo.exchange(self.vec[name], self.group)
+
+    def acquire(self, name):
+        if self.peer is not None and self.halo.part.world > 1:
+            self.peer.wait(name)
+
+    def _ranges(self):
+        """(interior range, [boundary ranges])"""
+        out = []
+        if self.lo > 0:
+            out.append((0, self.lo))
+        if self.hi < self.n_local:
+            out.append((self.hi, self.n_local))
+        return (self.lo, self.hi), out
+
+    def run_step(self, name_in, launch):
+        """launch(rows) issues the fused kernel for a row range; the gathered vector is `name_in`
+        (already published by the producer of its values)."""
+        interior, boundary = self._ranges()
+        if self.halo.part.world == 1 or self.peer is None:
+            launch((0, self.n_local))
+            return
+        if interior[1] > interior[0]:
+            launch(interior)
+        self.acquire(name_in)
+        for rng in boundary:
+            launch(rng)
+
+    # -- fused layer steps -------------------------------------------------------------------
+    def load(self, name, x_local):
+        self.vec[name][:self.n_local].copy_(x_local.view(self.n_local, self.k))
+        self.publish(name)
+
+    def jacobi(self, n_iters, diag, b, omega_dev, start="v0"):
+        """n_iters sweeps starting from vector `start` (already load()-ed / published), ping-ponging
+        through "va"/"vb" (never overwriting `start` if it is "v0"); returns the name of the
+        vector holding the result."""
+        cur = start
+        for _ in range(n_iters):
+            nxt = "va" if cur != "va" else "vb"
+            xin, xout = self.vec[cur], self.vec[nxt]
+            self.run_step(cur, lambda rows: rt.jacobi(self.plan, self.vals, diag, b, xin, xout, omega_dev, rows))
+            self.publish(nxt)
+            cur = nxt
+        return cur
+
+    def spmv(self, name_in, out, b=None):
+        xin = self.vec[name_in]
+        if b is None:
+            self.run_step(name_in, lambda rows: rt.spmm(self.plan, self.vals, xin, out, rows))
+        else:
+            self.run_step(name_in, lambda rows: rt.residual(self.plan, self.vals, xin, b, out, rows))
+        return out
+
+    def chebyshev(self, deg, b, table, start="va", x=None, r=None):
+        """Chebyshev relaxation of degree `deg` from vector `start` ("va" or "vb").  x lives in its
+        own local buffer after iteration 1 (only p is gathered), so the named peer vectors
+        ping-pong p.  Returns (x, r, name of p)."""
+        n, k = self.n_local, self.k
+        other = "vb" if start == "va" else "va"
+        xin = self.vec[start]
+        x = torch.empty(n, k, dtype=self.dtype, device=self.device) if x is None else x
+        r = torch.empty_like(x) if r is None else r
+        pv = self.vec[other]
+        self.run_step(start, lambda rows: rt.cheby_first(self.plan, self.vals, b, xin, x, r, pv, table[0, 1:2], rows))
+        self.publish(other)
+        cur, nxt = other, start
+        for it in range(1, deg):
+            pin, pout = self.vec[cur], self.vec[nxt]
+            self.run_step(cur, lambda rows: rt.cheby_next(self.plan, self.vals, pin, pout, r, x,
+                                                          table[it, 0:1], table[it, 1:2], table[it, 2:3], rows))
+            self.publish(nxt)
+            cur, nxt = nxt, cur
+        return x, r, cur
+
+    def power_method(self, num_iter, start="v0"):
+        """Power iteration + Rayleigh quotient on the partitioned operator; the squared norms are
+        all-reduced (2 fp64 scalars) once per iteration.  Returns (lambda, n, n_A) as a device
+        fp64 tensor [3] and the name of the vector holding the normalised iterate."""
+        n = self.n_local
+        cur = start
+        sums = torch.zeros(2 * (num_iter + 2), dtype=torch.float64, device=self.device)
+        prev = None
+        multi = self.halo.part.world > 1
+        for it in range(num_iter):
+            nxt = "va" if cur != "va" else "vb"
+            ss = sums[2 * it:2 * it + 2]
+            bin_, yout = self.vec[cur], self.vec[nxt]
+            part = torch.zeros(2, dtype=torch.float64, device=self.device)
+            self._reduced_step(cur, lambda rows, acc: rt.power_step(self.plan, self.vals, bin_, yout, prev, acc, rows),
+                               part)
+            if multi:
+                dist.all_reduce(part, group=self.group)
+            ss.copy_(part)
+            self.publish(nxt)
+            cur = nxt
+            prev = ss
+        bout = torch.empty(n, self.k, dtype=self.dtype, device=self.device)
+        yout = torch.empty_like(bout)
+        part = torch.zeros(2, dtype=torch.float64, device=self.device)
+        bin_ = self.vec[cur]
+        self._reduced_step(cur, lambda rows, acc: rt.rayleigh(self.plan, self.vals, bin_, bout, yout, prev, acc, rows),
+                           part)
+        if multi:
+            dist.all_reduce(part, group=self.group)
+        norm = torch.sqrt(prev[0]) if prev is not None else torch.ones((), dtype=torch.float64, device=self.device)
+        return torch.stack([part[0] / part[1], norm, part[0]]), bout, yout
+
+    def _reduced_step(self, name_in, launch, total):
+        """Reducing kernels write their partial sums per launch; ranges are accumulated."""
+        interior, boundary = self._ranges()
+        if self.halo.part.world == 1 or self.peer is None:
+            launch((0, self.n_local), total)
+            return
+        tmp = torch.zeros(2 * (1 + len(boundary)), dtype=torch.float64, device=self.device)
+        launch(interior, tmp[0:2])
+        self.acquire(name_in)
+        for i, rng in enumerate(boundary):
+            launch(rng, tmp[2 * i + 2:2 * i + 4])
+        total.copy_(tmp.view(-1, 2).sum(0))
+
+    def close(self):
+        if self.peer is not None:
+            self.peer.close()

@@ -11,13 +11,15 @@ import torch
 _OFFS = [(-1, -1), (-1, 0), (-1, 1), (0, -1), (0, 0), (0, 1), (1, -1), (1, 0), (1, 1)]  # (dy, dx)
 
 
-def stencil_coo(ny, nx, weights, periodic=False, dtype=torch.float64, device="cpu"):
+def stencil_coo(ny, nx, weights, periodic=False, dtype=torch.float64, device="cpu", rows=None):
     """weights: {(dy, dx): value}; grid point (y, x) has index y*nx + x (x fastest).
     Dirichlet truncation drops out-of-grid neighbours; periodic wraps them.  Columns are
     emitted in ascending order within each row (== scipy/torch coalesced COO order)."""
     device = torch.device(device)
-    n = ny * nx
-    idx = torch.arange(n, dtype=torch.int64, device=device)
+    if rows is None:
+        rows = (0, ny * nx)
+    idx = torch.arange(rows[0], rows[1], dtype=torch.int64, device=device)   # GLOBAL row ids of this block
+    n = idx.numel()
     gy, gx = idx // nx, idx % nx
     offs = [o for o in _OFFS if o in weights and weights[o] != 0]
     cols, keep = [], []
@@ -36,16 +38,18 @@ def stencil_coo(ny, nx, weights, periodic=False, dtype=torch.float64, device="cp
         # wrap-around breaks the ascending column order inside a row: sort each row's entries
         cols, order = torch.sort(cols, dim=1, stable=True)
         vals = torch.gather(vals, 1, order)
-    rows = idx.view(-1, 1).expand(n, len(offs))
-    edge_index = torch.stack([rows[keep], cols[keep]])
+    ridx = idx.view(-1, 1).expand(n, len(offs))
+    edge_index = torch.stack([ridx[keep], cols[keep]])
     edge_val = vals[keep].reshape(-1, 1).contiguous()
     return edge_index, edge_val
 
 
-def laplacian_2d(N, dtype=torch.float64, device="cpu"):
-    """5-point (negative) Laplacian, diag -4, off-diag +1, Dirichlet truncation."""
+def laplacian_2d(N, dtype=torch.float64, device="cpu", rows=None):
+    """5-point (negative) Laplacian, diag -4, off-diag +1, Dirichlet truncation.
+    rows=(r0, r1) builds only that block of rows (global row / column ids), for the
+    row-partitioned multi-GPU path."""
     w = {(0, 0): -4.0, (0, -1): 1.0, (0, 1): 1.0, (-1, 0): 1.0, (1, 0): 1.0}
-    return stencil_coo(N, N, w, False, dtype, device)
+    return stencil_coo(N, N, w, False, dtype, device, rows)
 
 
 def heat_fem_stencil(hx=1.0, hy=1.0):
@@ -59,10 +63,10 @@ def heat_fem_stencil(hx=1.0, hy=1.0):
     return w
 
 
-def heat_fem_2d(num_cells, h=(1.0, 1.0), dtype=torch.float64, device="cpu"):
+def heat_fem_2d(num_cells, h=(1.0, 1.0), dtype=torch.float64, device="cpu", rows=None):
     """heateqnfem2dfun(num_cells, h, [2,2]): (num_cells-1) interior nodes per direction."""
     mx, my = num_cells[0] - 1, num_cells[1] - 1
-    return stencil_coo(my, mx, heat_fem_stencil(h[0], h[1]), False, dtype, device)
+    return stencil_coo(my, mx, heat_fem_stencil(h[0], h[1]), False, dtype, device, rows)
 
 
 def constant_diffusion_stencil(alpha, beta):

@@ -237,16 +237,26 @@ int glab_ipc_alloc(int64_t bytes, void** dev_ptr, void* handle_out);
 int glab_ipc_open(const void* handle, void** peer_ptr);
 int glab_ipc_close(void* peer_ptr);
 int glab_ipc_free(void* dev_ptr);
-/* dst_peer[dst_offset + i, :] = src[send_idx[i], :] for i < count (k columns, T = f32/f64),
- * then (if flag_peer != NULL) a system-scope release store of `flag_value` to *flag_peer. */
-int glab_halo_push_f32(const float* src, const int32_t* send_idx, int64_t count, int k,
-                       float* dst_peer, int64_t dst_offset, uint32_t* flag_peer,
-                       uint32_t flag_value, void* stream);
-int glab_halo_push_f64(const double* src, const int32_t* send_idx, int64_t count, int k,
-                       double* dst_peer, int64_t dst_offset, uint32_t* flag_peer,
-                       uint32_t flag_value, void* stream);
-/* In-stream wait until *flag_local >= flag_value (written by a peer's push). */
-int glab_halo_wait(uint32_t* flag_local, uint32_t flag_value, void* stream);
+/* One push = one kernel launch for ALL neighbours (gridDim.y = peer):
+ *   for every peer q < n_peers:  dst[q][dst_offset[q] + i, :] = src[send_idx[q][i], :], i < count[q]
+ * (k columns), followed by a system-scope release increment (+1) of *flag[q], a uint32 word
+ * in peer q's memory.  Flags only ever count up, so a CUDA graph that contains pushes and waits
+ * can be replayed any number of times.  `descs` is a HOST array, copied at launch. */
+#define GLAB_MAX_PEERS 8
+typedef struct glab_push_desc {
+  const int32_t* send_idx;   /* device: local row ids to send to this peer        */
+  int64_t count;
+  void* dst;                 /* peer-mapped base of the destination vector        */
+  int64_t dst_offset;        /* first destination row (the peer's halo tail slot) */
+  uint32_t* flag;            /* peer-mapped arrival counter, may be NULL          */
+} glab_push_desc;
+int glab_halo_push_f32(const float* src, int k, int n_peers, const glab_push_desc* descs, void* stream);
+int glab_halo_push_f64(const double* src, int k, int n_peers, const glab_push_desc* descs, void* stream);
+/* One wait = one single-CTA kernel: for every i < n_flags, ++expect[i] (a device-local uint32
+ * that mirrors how many pushes this rank has consumed from that peer) and spin, with
+ * system-scope acquire loads, until *flags[i] >= expect[i].  flags / expect are HOST arrays of
+ * device pointers. */
+int glab_halo_wait(int n_flags, uint32_t* const* flags, uint32_t* const* expect, void* stream);
 
 #ifdef __cplusplus
 }

@@ -33,7 +33,7 @@ def test_version_and_error_strings(G):
     # argument validation happens before any CUDA call
     assert G.lib.glab_plan_info(None, None, None, None, None, None) == -1
     assert G.lib.glab_spmm_f32(None, None, None, 1, None, 0, 0, None) == -1
-    assert G.lib.glab_halo_wait(None, 0, None) == -1
+    assert G.lib.glab_halo_wait(1, None, None, None) == -1
 
 
 def test_sass_is_sm100a(G):
