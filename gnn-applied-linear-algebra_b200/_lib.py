@@ -58,7 +58,7 @@ class PushDesc(ctypes.Structure):
                 ("flag", c_void_p)]
 
 
-_sig("glab_halo_wait", c_int, c_int, POINTER(c_void_p), POINTER(c_void_p), P)
+_sig("glab_halo_wait", c_int, c_int, POINTER(c_void_p), P, P)
 
 for _suf, _ct in (("f32", c_float), ("f64", c_double)):
     _sig("glab_gather_vals_" + _suf, c_int, P, P, _I64, _I64, P, P)
@@ -78,7 +78,7 @@ for _suf, _ct in (("f32", c_float), ("f64", c_double)):
     _sig("glab_soc_classic_" + _suf, c_int, P, P, _ct, P, P, P)
     _sig("glab_soc_sa_" + _suf, c_int, P, P, P, P, P)
     _sig("glab_direct_interp_" + _suf, c_int, P, P, P, P, P, P, P)
-    _sig("glab_halo_push_" + _suf, c_int, P, _INT, _INT, POINTER(PushDesc), P)
+    _sig("glab_halo_push_" + _suf, c_int, P, _INT, _INT, POINTER(PushDesc), P, P)
 
 
 def check(rc, what=""):

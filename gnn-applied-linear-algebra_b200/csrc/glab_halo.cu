@@ -17,7 +17,9 @@ struct PushArgs {
 };
 
 template <typename T, int K>
-__global__ void k_halo_push(const T* __restrict__ src, PushArgs a, unsigned int* done_counter) {
+__global__ void k_halo_push(const T* __restrict__ src, PushArgs a, unsigned int* done_counter,
+                            uint32_t* pushed_local) {
+  if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0 && pushed_local) *pushed_local += 1u;
   const glab_push_desc d = a.d[blockIdx.y];
   T* __restrict__ dst = reinterpret_cast<T*>(d.dst);
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < d.count;
@@ -42,14 +44,14 @@ __global__ void k_halo_push(const T* __restrict__ src, PushArgs a, unsigned int*
 
 struct WaitArgs {
   uint32_t* flag[GLAB_MAX_PEERS];
-  uint32_t* expect[GLAB_MAX_PEERS];
 };
 
-__global__ void k_halo_wait(WaitArgs a, int n) {
+__global__ void k_bump(uint32_t* p) { *p += 1u; }
+
+__global__ void k_halo_wait(WaitArgs a, int n, const uint32_t* pushed_local) {
   const int i = threadIdx.x;
   if (i >= n) return;
-  const uint32_t want = *a.expect[i] + 1u;
-  *a.expect[i] = want;
+  const uint32_t want = *pushed_local;
   uint32_t v;
   do {
     asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(a.flag[i]) : "memory");
@@ -70,9 +72,13 @@ static unsigned int* done_counters() {
 }
 
 template <typename T>
-static int halo_push(const T* src, int k, int n_peers, const glab_push_desc* descs, void* stream) {
+static int halo_push(const T* src, int k, int n_peers, const glab_push_desc* descs,
+                     uint32_t* pushed_local, void* stream) {
   if (n_peers < 0 || n_peers > GLAB_MAX_PEERS || (n_peers > 0 && (!src || !descs))) return GLAB_E_ARG;
-  if (n_peers == 0) return 0;
+  if (n_peers == 0) {
+    if (pushed_local) k_bump<<<1, 1, 0, as_stream(stream)>>>(pushed_local);
+    return (int)cudaGetLastError();
+  }
   PushArgs a;
   int64_t mx = 1;
   for (int q = 0; q < n_peers; ++q) {
@@ -87,10 +93,10 @@ static int halo_push(const T* src, int k, int n_peers, const glab_push_desc* des
   dim3 grid((unsigned)b, (unsigned)n_peers);
   cudaStream_t st = as_stream(stream);
   switch (k) {
-    case 1: k_halo_push<T, 1><<<grid, 256, 0, st>>>(src, a, ctr); break;
-    case 2: k_halo_push<T, 2><<<grid, 256, 0, st>>>(src, a, ctr); break;
-    case 4: k_halo_push<T, 4><<<grid, 256, 0, st>>>(src, a, ctr); break;
-    case 8: k_halo_push<T, 8><<<grid, 256, 0, st>>>(src, a, ctr); break;
+    case 1: k_halo_push<T, 1><<<grid, 256, 0, st>>>(src, a, ctr, pushed_local); break;
+    case 2: k_halo_push<T, 2><<<grid, 256, 0, st>>>(src, a, ctr, pushed_local); break;
+    case 4: k_halo_push<T, 4><<<grid, 256, 0, st>>>(src, a, ctr, pushed_local); break;
+    case 8: k_halo_push<T, 8><<<grid, 256, 0, st>>>(src, a, ctr, pushed_local); break;
     default: return GLAB_E_ARG;
   }
   return (int)cudaGetLastError();
@@ -142,21 +148,22 @@ extern "C" int glab_ipc_free(void* dev_ptr) {
   return 0;
 }
 
-extern "C" int glab_halo_push_f32(const float* src, int k, int n, const glab_push_desc* d, void* s) {
-  return halo_push<float>(src, k, n, d, s);
+extern "C" int glab_halo_push_f32(const float* src, int k, int n, const glab_push_desc* d,
+                                  uint32_t* pushed, void* s) {
+  return halo_push<float>(src, k, n, d, pushed, s);
 }
-extern "C" int glab_halo_push_f64(const double* src, int k, int n, const glab_push_desc* d, void* s) {
-  return halo_push<double>(src, k, n, d, s);
+extern "C" int glab_halo_push_f64(const double* src, int k, int n, const glab_push_desc* d,
+                                  uint32_t* pushed, void* s) {
+  return halo_push<double>(src, k, n, d, pushed, s);
 }
-extern "C" int glab_halo_wait(int n, uint32_t* const* flags, uint32_t* const* expect, void* s) {
-  if (n < 0 || n > GLAB_MAX_PEERS || (n > 0 && (!flags || !expect))) return GLAB_E_ARG;
+extern "C" int glab_halo_wait(int n, uint32_t* const* flags, const uint32_t* pushed, void* s) {
+  if (n < 0 || n > GLAB_MAX_PEERS || (n > 0 && (!flags || !pushed))) return GLAB_E_ARG;
   if (n == 0) return 0;
   WaitArgs a;
   for (int i = 0; i < n; ++i) {
-    if (!flags[i] || !expect[i]) return GLAB_E_ARG;
+    if (!flags[i]) return GLAB_E_ARG;
     a.flag[i] = flags[i];
-    a.expect[i] = expect[i];
   }
-  k_halo_wait<<<1, 32, 0, as_stream(s)>>>(a, n);
+  k_halo_wait<<<1, 32, 0, as_stream(s)>>>(a, n, pushed);
   return (int)cudaGetLastError();
 }

@@ -213,7 +213,7 @@ class PeerHalo:
         self.views = {nm: b.local.view(ext, k) for nm, b in self.bufs.items()}
         world = halo.part.world
         # words (16-byte spaced): arrival counter [name][peer] (bumped remotely by that peer) and
-        # expect counter [name][peer] (local bookkeeping of the wait kernel)
+        # pushed counter [name] (how often THIS rank has pushed the vector; the wait target)
         self.flag_index = {nm: i for i, nm in enumerate(names)}
         self.flags = PeerBuffer(2 * len(names) * world * 4, torch.int32, device, group)
         offs = [None] * world
@@ -237,34 +237,31 @@ class PeerHalo:
             self._push_desc[nm] = descs
             nf = len(halo.peers_recv)
             fl = (ctypes.c_void_p * max(nf, 1))()
-            ex = (ctypes.c_void_p * max(nf, 1))()
             base = self.flags.peer_ptr[self.rank]
             for i, q in enumerate(halo.peers_recv):
                 fl[i] = base + (self.flag_index[nm] * world + q) * 16
-                ex[i] = base + (nw + self.flag_index[nm] * world + q) * 16
-            self._wait_args[nm] = (nf, fl, ex)
+            pushed = base + (nw + self.flag_index[nm]) * 16
+            self._wait_args[nm] = (nf, fl, ctypes.c_void_p(pushed))
         if world > 1:
             dist.barrier(group=group)
 
     def push(self, name):
         """After the kernel that produced vector `name`: send boundary rows to every neighbour."""
         n = len(self.halo.peers_send)
-        if n == 0:
-            return
         fn = getattr(lib, "glab_halo_push_" + self._suf)
         rt.launch_count += 1
         with torch.cuda.device(self.device):
-            check(fn(rt.ptr(self.views[name]), self.k, n, self._push_desc[name], rt.stream_ptr()),
-                  "glab_halo_push")
+            check(fn(rt.ptr(self.views[name]), self.k, n, self._push_desc[name], self._wait_args[name][2],
+                     rt.stream_ptr()), "glab_halo_push")
 
     def wait(self, name):
         """Before the kernel that gathers vector `name`'s halo tail."""
-        nf, fl, ex = self._wait_args[name]
+        nf, fl, pushed = self._wait_args[name]
         if nf == 0:
             return
         rt.launch_count += 1
         with torch.cuda.device(self.device):
-            check(lib.glab_halo_wait(nf, fl, ex, rt.stream_ptr()), "glab_halo_wait")
+            check(lib.glab_halo_wait(nf, fl, pushed, rt.stream_ptr()), "glab_halo_wait")
 
     def close(self):
         torch.cuda.synchronize(self.device)
@@ -305,6 +302,7 @@ class DistOperator:
             self.peer = None
             self.vec = {nm: torch.zeros(n_ext, k, dtype=self.dtype, device=self.device) for nm in self.names}
         self.n_local, self.n_ext = n_loc, n_ext
+        self.side = torch.cuda.Stream(self.device) if (self.peer is not None and local_vals.is_cuda) else None
 
     # -- halo plumbing -----------------------------------------------------------------------
     def publish(self, name):
@@ -329,18 +327,37 @@ class DistOperator:
             out.append((self.hi, self.n_local))
         return (self.lo, self.hi), out
 
-    def run_step(self, name_in, launch):
+    def run_step(self, name_in, launch, name_out=None):
         """launch(rows) issues the fused kernel for a row range; the gathered vector is `name_in`
-        (already published by the producer of its values)."""
+        (already published by the producer of its values).  If `name_out` is given, the vector of
+        that name -- which the step writes -- is published to the neighbours as soon as the
+        boundary rows are done.
+
+        Peer engine: fork/join over two streams.  The interior rows run on the caller's stream
+        while a side stream waits for the neighbours' halo, processes the boundary rows and
+        pushes the new boundary values, so the exchange latency and the small launches hide
+        behind the interior kernel.  Captured in a CUDA graph the events become plain edges."""
         interior, boundary = self._ranges()
         if self.halo.part.world == 1 or self.peer is None:
             launch((0, self.n_local))
+            if name_out is not None:
+                self.publish(name_out)
             return
+        main = torch.cuda.current_stream(self.device)
+        fork = torch.cuda.Event()
+        join = torch.cuda.Event()
+        fork.record(main)
+        with torch.cuda.stream(self.side):
+            self.side.wait_event(fork)
+            self.acquire(name_in)
+            for rng in boundary:
+                launch(rng)
+            if name_out is not None:
+                self.publish(name_out)
+            join.record(self.side)
         if interior[1] > interior[0]:
             launch(interior)
-        self.acquire(name_in)
-        for rng in boundary:
-            launch(rng)
+        main.wait_event(join)
 
     # -- fused layer steps -------------------------------------------------------------------
     def load(self, name, x_local):
@@ -355,8 +372,8 @@ class DistOperator:
         for _ in range(n_iters):
             nxt = "va" if cur != "va" else "vb"
             xin, xout = self.vec[cur], self.vec[nxt]
-            self.run_step(cur, lambda rows: rt.jacobi(self.plan, self.vals, diag, b, xin, xout, omega_dev, rows))
-            self.publish(nxt)
+            self.run_step(cur, lambda rows: rt.jacobi(self.plan, self.vals, diag, b, xin, xout, omega_dev, rows),
+                          nxt)
             cur = nxt
         return cur
 
@@ -378,14 +395,13 @@ class DistOperator:
         x = torch.empty(n, k, dtype=self.dtype, device=self.device) if x is None else x
         r = torch.empty_like(x) if r is None else r
         pv = self.vec[other]
-        self.run_step(start, lambda rows: rt.cheby_first(self.plan, self.vals, b, xin, x, r, pv, table[0, 1:2], rows))
-        self.publish(other)
+        self.run_step(start, lambda rows: rt.cheby_first(self.plan, self.vals, b, xin, x, r, pv, table[0, 1:2], rows),
+                      other)
         cur, nxt = other, start
         for it in range(1, deg):
             pin, pout = self.vec[cur], self.vec[nxt]
             self.run_step(cur, lambda rows: rt.cheby_next(self.plan, self.vals, pin, pout, r, x,
-                                                          table[it, 0:1], table[it, 1:2], table[it, 2:3], rows))
-            self.publish(nxt)
+                                                          table[it, 0:1], table[it, 1:2], table[it, 2:3], rows), nxt)
             cur, nxt = nxt, cur
         return x, r, cur
 

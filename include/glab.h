@@ -239,9 +239,11 @@ int glab_ipc_close(void* peer_ptr);
 int glab_ipc_free(void* dev_ptr);
 /* One push = one kernel launch for ALL neighbours (gridDim.y = peer):
  *   for every peer q < n_peers:  dst[q][dst_offset[q] + i, :] = src[send_idx[q][i], :], i < count[q]
- * (k columns), followed by a system-scope release increment (+1) of *flag[q], a uint32 word
- * in peer q's memory.  Flags only ever count up, so a CUDA graph that contains pushes and waits
- * can be replayed any number of times.  `descs` is a HOST array, copied at launch. */
+ * (k columns), followed by a system-scope release increment (+1) of *flag[q], a uint32 arrival
+ * counter in peer q's memory, and by ++*pushed_local (this rank's own count of pushes of this
+ * vector, device resident).  Counters only ever count up and live on the device, so a CUDA
+ * graph that contains pushes and waits can be replayed any number of times.
+ * `descs` is a HOST array, copied at launch.  n_peers == 0 still bumps *pushed_local. */
 #define GLAB_MAX_PEERS 8
 typedef struct glab_push_desc {
   const int32_t* send_idx;   /* device: local row ids to send to this peer        */
@@ -250,13 +252,15 @@ typedef struct glab_push_desc {
   int64_t dst_offset;        /* first destination row (the peer's halo tail slot) */
   uint32_t* flag;            /* peer-mapped arrival counter, may be NULL          */
 } glab_push_desc;
-int glab_halo_push_f32(const float* src, int k, int n_peers, const glab_push_desc* descs, void* stream);
-int glab_halo_push_f64(const double* src, int k, int n_peers, const glab_push_desc* descs, void* stream);
-/* One wait = one single-CTA kernel: for every i < n_flags, ++expect[i] (a device-local uint32
- * that mirrors how many pushes this rank has consumed from that peer) and spin, with
- * system-scope acquire loads, until *flags[i] >= expect[i].  flags / expect are HOST arrays of
- * device pointers. */
-int glab_halo_wait(int n_flags, uint32_t* const* flags, uint32_t* const* expect, void* stream);
+int glab_halo_push_f32(const float* src, int k, int n_peers, const glab_push_desc* descs,
+                       uint32_t* pushed_local, void* stream);
+int glab_halo_push_f64(const double* src, int k, int n_peers, const glab_push_desc* descs,
+                       uint32_t* pushed_local, void* stream);
+/* One wait = one single-CTA kernel: spin, with system-scope acquire loads, until every arrival
+ * counter *flags[i] (i < n_flags) has reached *pushed_local -- i.e. until each neighbour has
+ * pushed this vector as often as this rank has (all ranks run the same sequence of pushes).
+ * flags is a HOST array of device pointers. */
+int glab_halo_wait(int n_flags, uint32_t* const* flags, const uint32_t* pushed_local, void* stream);
 
 #ifdef __cplusplus
 }
