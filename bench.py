@@ -193,7 +193,9 @@ def workload_config(workload, n, z, gpus):
             "rows": n, "nnz": z, "rhs_columns": 1,
             "fused_layer_launches_per_step": LAUNCHES_PER_STEP,
             "partition": "single GPU" if gpus == 1 else "1-D row blocks over %d GPUs, halo push over NVLink peer memory" % gpus,
-            "l2": "inputs larger than L2 (CSR %.0f MB + vectors; 126 MB L2), no flush needed" % (z * 8 / 1e6),
+            "l2": ("inputs larger than L2 (CSR %.0f MB + vectors per GPU; 126 MB L2), no flush needed"
+                   if z * 8 / gpus > 1.5 * 126e6 else
+                   "per-GPU working set (CSR %.0f MB + vectors) is comparable to the 126 MB L2: partly L2-resident across sweeps, as it would be in production at this size") % (z * 8 / 1e6 / gpus),
             "e2e_operator": "edge list + CSR plan resident (step-invariant); vectors H2D from pinned host and x D2H every step"}
 
 

@@ -60,6 +60,6 @@ class ChebyRelaxGNN(torch.nn.Module):
             rt.cheby_next(plan, vals, p, p_alt, r, x, table[it, 0:1], table[it, 1:2], table[it, 2:3])
             gathered = p
             p, p_alt = p_alt, p
-        e_out = rt.with_messages(plan, vals, gathered, io.up(edge_attr, dt)[:, 0])
+        e_out = rt.with_messages(plan, vals, gathered)
         v_out = torch.cat([b, x, r, p], 1)
         return io.down(v_out), io.down(e_out), g_out

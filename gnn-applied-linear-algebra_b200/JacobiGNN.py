@@ -28,7 +28,7 @@ class JacobiGNN(torch.nn.Module):
     def iterate(self, vertex_attr, edgeij_pair, edge_attr, g, batch=None):
         io, dt, plan, vals, va, diag, b, x, w = self._setup(vertex_attr, edgeij_pair, edge_attr, g)
         x_new = rt.jacobi(plan, vals, diag, b, x, torch.empty_like(x), w)
-        e_out = rt.with_messages(plan, vals, x, io.up(edge_attr, dt)[:, 0])
+        e_out = rt.with_messages(plan, vals, x)
         v_out = torch.cat([diag.view(-1, 1), b, x_new], 1)
         return io.down(v_out), io.down(e_out), g
 

@@ -48,7 +48,7 @@ class EdgeUpdate(torch.nn.Module):
         vals = rt.get_vals(plan, edge_attr, 0, dt)
         xd = rt.dense(io.up(x, dt))
         y = rt.spmm(plan, vals, xd)
-        e_out = rt.with_messages(plan, vals, xd, io.up(edge_attr, dt))
+        e_out = rt.with_messages(plan, vals, xd)
         return io.down(torch.cat([xd, y], 1)), io.down(e_out), u
 
 

@@ -39,6 +39,6 @@ class PowerMethodGNN(torch.nn.Module):
         g_dev = io.up(g).to(torch.float64)
         norm = torch.sqrt(ss_prev[0]) if ss_prev is not None else g_dev[0]
         g_out = torch.stack([norm, ray[0], ray[0] / ray[1]]).to(g.dtype if g.dtype.is_floating_point else dt)
-        e_out = rt.with_messages(plan, vals, b_out, io.up(edge_attr, dt)[:, 0])
+        e_out = rt.with_messages(plan, vals, b_out)
         v_out = torch.stack([b_out, y_out], 1)
         return io.down(v_out), io.down(e_out), io.down(g_out)

@@ -73,6 +73,7 @@ for _suf, _ct in (("f32", c_float), ("f64", c_double)):
     _sig("glab_rayleigh_" + _suf, c_int, P, P, P, P, P, P, P, P, _I64, _I64, P)
     _sig("glab_xtax_" + _suf, c_int, P, P, P, P, P, _I64, _I64, P)
     _sig("glab_edge_messages_" + _suf, c_int, P, P, P, _INT, P, _I64, _I64, P)
+    _sig("glab_edge_attr_" + _suf, c_int, P, P, P, _INT, P, _I64, P)
     _sig("glab_segment_sum_" + _suf, c_int, P, P, _INT, P, P)
     _sig("glab_segment_max_" + _suf, c_int, P, P, P, P)
     _sig("glab_soc_classic_" + _suf, c_int, P, P, _ct, P, P, P)

@@ -358,12 +358,13 @@ def edge_messages(plan, vals, x, out_edges, col):
           out_edges.stride(0), col, stream_ptr())
 
 
-def with_messages(plan, vals, x, A_col):
-    """The reference's returned edge_attr = cat([A_ij, c_ij], 1) (e.g. MatVecGNN.py:84)."""
+def with_messages(plan, vals, x, A_col=None):
+    """The reference's returned edge_attr = cat([A_ij, c_ij], 1) (e.g. MatVecGNN.py:84), in the
+    caller's edge order, produced by one kernel (vals already holds A_ij in slot order)."""
     k = _k_of(x)
     out = torch.empty((plan.nnz, 1 + k), dtype=x.dtype, device=plan.device)
-    out[:, 0] = A_col.reshape(-1)
-    edge_messages(plan, vals, x, out, 1)
+    _call("edge_attr", x.dtype, plan.device, plan.handle, ptr(vals), ptr(x), k, ptr(out), out.stride(0),
+          stream_ptr())
     return out
 
 

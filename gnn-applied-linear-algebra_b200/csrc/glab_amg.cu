@@ -87,11 +87,15 @@ static int launch_edge_tiles(const glab_plan* p, const T* vals, const T* aux, co
   return (int)cudaGetLastError();
 }
 
-// c[e, column + c] = A_slot * x[col(slot), c]
-template <typename T, int K>
+// c[e, column + c] = A_slot * x[col(slot), c]; with write_A also out[e, column - 1] = A_slot, so
+// that the reference's returned edge_attr = cat([A_ij, c_ij], 1) is produced by ONE pass with
+// one (1+K)-wide store per edge.
+template <typename T, int K, bool WriteA>
 __global__ void k_edge_messages(const int32_t* __restrict__ colidx, const T* __restrict__ vals,
                                 const int32_t* __restrict__ perm, const T* __restrict__ x,
                                 int64_t nnz, T* __restrict__ out, int64_t ld, int64_t column) {
+  const bool packed = WriteA && K == 1 && ld == 2 && column == 1 &&
+                      (reinterpret_cast<uintptr_t>(out) % (2 * sizeof(T)) == 0);
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < nnz;
        i += (int64_t)gridDim.x * blockDim.x) {
     const int col = __ldg(colidx + i);
@@ -99,15 +103,21 @@ __global__ void k_edge_messages(const int32_t* __restrict__ colidx, const T* __r
     T xv[K];
     load_vec<T, K>(xv, x + (size_t)col * K);
     const int64_t e = perm ? (int64_t)__ldg(perm + i) : i;
+    if (packed) {
+      T pair[2] = {v, v * xv[0]};
+      store_vec<T, 2>(out + e * 2, pair);
+    } else {
+      if (WriteA) out[e * ld + column - 1] = v;
 #pragma unroll
-    for (int c = 0; c < K; ++c) out[e * ld + column + c] = v * xv[c];
+      for (int c = 0; c < K; ++c) out[e * ld + column + c] = v * xv[c];
+    }
   }
 }
 
-template <typename T>
+template <typename T, bool WriteA>
 static int edge_messages(const glab_plan* p, const T* vals, const T* x, int k, T* out, int64_t ld,
                          int64_t column, void* stream) {
-  if (!p || ld < 1 || column < 0 || column + k > ld) return GLAB_E_ARG;
+  if (!p || ld < 1 || column < (WriteA ? 1 : 0) || column + k > ld) return GLAB_E_ARG;
   if (p->nnz == 0) return 0;
   if (!x || !out || !vals) return GLAB_E_ARG;
   int64_t b = (p->nnz + 255) / 256;
@@ -115,10 +125,10 @@ static int edge_messages(const glab_plan* p, const T* vals, const T* x, int k, T
   const int grid = (int)(b < capb ? b : capb);
   cudaStream_t st = as_stream(stream);
   switch (k) {
-    case 1: k_edge_messages<T, 1><<<grid, 256, 0, st>>>(p->colidx, vals, p->perm, x, p->nnz, out, ld, column); break;
-    case 2: k_edge_messages<T, 2><<<grid, 256, 0, st>>>(p->colidx, vals, p->perm, x, p->nnz, out, ld, column); break;
-    case 4: k_edge_messages<T, 4><<<grid, 256, 0, st>>>(p->colidx, vals, p->perm, x, p->nnz, out, ld, column); break;
-    case 8: k_edge_messages<T, 8><<<grid, 256, 0, st>>>(p->colidx, vals, p->perm, x, p->nnz, out, ld, column); break;
+    case 1: k_edge_messages<T, 1, WriteA><<<grid, 256, 0, st>>>(p->colidx, vals, p->perm, x, p->nnz, out, ld, column); break;
+    case 2: k_edge_messages<T, 2, WriteA><<<grid, 256, 0, st>>>(p->colidx, vals, p->perm, x, p->nnz, out, ld, column); break;
+    case 4: k_edge_messages<T, 4, WriteA><<<grid, 256, 0, st>>>(p->colidx, vals, p->perm, x, p->nnz, out, ld, column); break;
+    case 8: k_edge_messages<T, 8, WriteA><<<grid, 256, 0, st>>>(p->colidx, vals, p->perm, x, p->nnz, out, ld, column); break;
     default: return GLAB_E_ARG;
   }
   return (int)cudaGetLastError();
@@ -188,7 +198,11 @@ using namespace glab;
   }                                                                                                \
   extern "C" int glab_edge_messages_##SUF(const glab_plan* p, const T* v, const T* x, int k,       \
                                           T* out, int64_t ld, int64_t column, void* s) {           \
-    return edge_messages<T>(p, v, x, k, out, ld, column, s);                                       \
+    return edge_messages<T, false>(p, v, x, k, out, ld, column, s);                                \
+  }                                                                                                \
+  extern "C" int glab_edge_attr_##SUF(const glab_plan* p, const T* v, const T* x, int k, T* out,   \
+                                      int64_t ld, void* s) {                                       \
+    return edge_messages<T, true>(p, v, x, k, out, ld, 1, s);                                      \
   }
 
 #define GLAB_SEG_INST(SUF, T)                                                                      \

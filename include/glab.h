@@ -194,6 +194,14 @@ int glab_segment_sum_f64(const glab_plan*, const double* src_slots, int k, doubl
 int glab_segment_max_f32(const glab_plan*, const float* src_slots, float* out, void* stream);
 int glab_segment_max_f64(const glab_plan*, const double* src_slots, double* out, void* stream);
 
+/* out_edges[e, 0] = A_ij and out_edges[e, 1..k] = A_ij * x_j in ONE pass: the reference layers'
+ * returned edge_attr = torch.cat([A_ij, c_ij], 1) (MatVecGNN.py:84, JacobiGNN.py:88,
+ * ChebyGNN.py:70,183, PowerMethodGNN.py:106).  out_edges is [nnz, ld], ld >= 1 + k. */
+int glab_edge_attr_f32(const glab_plan*, const float* vals, const float* x, int k, float* out_edges,
+                       int64_t ld, void* stream);
+int glab_edge_attr_f64(const glab_plan*, const double* vals, const double* x, int k, double* out_edges,
+                       int64_t ld, void* stream);
+
 /* ------------------------------------------------------------------------------------------
  * AMG setup kernels (row-local, one pass).  Per-edge outputs are written in the caller's
  * ORIGINAL edge order (out[perm[slot]]).
