@@ -223,7 +223,8 @@ def main_gpu(args):
         prob = SingleGpuSmoother(G, N, dev)
     else:
         from bench_support import PartitionedSmoother
-        prob = PartitionedSmoother(G, N, dev, rank, world)
+        prob = PartitionedSmoother(G, N, dev, rank, world, engine=os.environ.get("GLAB_DIST_ENGINE", "peer"),
+                                   use_graph=os.environ.get("GLAB_DIST_GRAPH", "1") != "0")
     z_global = prob.nnz_global
 
     def barrier():

@@ -132,7 +132,7 @@ class PartitionedSmoother:
         self.d2h_bytes = nl * 4
         self.graph = None
         self.jac_graph = None
-        self.use_graph = use_graph and engine == "peer"
+        self.use_graph = use_graph and engine in ("peer", "peer-split")
         if self.use_graph:
             self._capture()
 

@@ -58,6 +58,14 @@ class PushDesc(ctypes.Structure):
                 ("flag", c_void_p)]
 
 
+class HaloStep(ctypes.Structure):
+    """glab_halo_step (include/glab.h)."""
+    _fields_ = [("interior_begin", c_int64), ("interior_end", c_int64), ("n_wait", c_int32),
+                ("wait_flags", POINTER(c_void_p)), ("wait_target", c_void_p), ("n_push", c_int32),
+                ("push", POINTER(PushDesc)), ("pushed_counter", c_void_p), ("push_src", c_void_p),
+                ("done_counter", c_void_p)]
+
+
 _sig("glab_halo_wait", c_int, c_int, POINTER(c_void_p), P, P)
 
 for _suf, _ct in (("f32", c_float), ("f64", c_double)):
@@ -74,6 +82,14 @@ for _suf, _ct in (("f32", c_float), ("f64", c_double)):
     _sig("glab_xtax_" + _suf, c_int, P, P, P, P, P, _I64, _I64, P)
     _sig("glab_edge_messages_" + _suf, c_int, P, P, P, _INT, P, _I64, _I64, P)
     _sig("glab_edge_attr_" + _suf, c_int, P, P, P, _INT, P, _I64, P)
+    _H = POINTER(HaloStep)
+    _sig("glab_spmm_halo_" + _suf, c_int, P, P, P, _INT, P, _H, P)
+    _sig("glab_residual_halo_" + _suf, c_int, P, P, P, P, _INT, P, _H, P)
+    _sig("glab_jacobi_halo_" + _suf, c_int, P, P, P, P, P, P, P, _INT, _H, P)
+    _sig("glab_cheby_first_halo_" + _suf, c_int, P, P, P, P, P, P, P, P, _INT, _H, P)
+    _sig("glab_cheby_next_halo_" + _suf, c_int, P, P, P, P, P, P, P, P, P, _INT, _H, P)
+    _sig("glab_power_step_halo_" + _suf, c_int, P, P, P, P, P, P, P, _H, P)
+    _sig("glab_rayleigh_halo_" + _suf, c_int, P, P, P, P, P, P, P, P, _H, P)
     _sig("glab_segment_sum_" + _suf, c_int, P, P, _INT, P, P)
     _sig("glab_segment_max_" + _suf, c_int, P, P, P, P)
     _sig("glab_soc_classic_" + _suf, c_int, P, P, _ct, P, P, P)

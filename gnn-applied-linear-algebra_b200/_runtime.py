@@ -279,19 +279,26 @@ def _call(name, dtype, device, *args):
         check(getattr(lib, "glab_%s_%s" % (name, suffix(dtype)))(*args), "glab_" + name)
 
 
-def spmm(plan, vals, x, out=None, rows=None):
+def spmm(plan, vals, x, out=None, rows=None, halo=None):
     k = _k_of(x)
     if out is None:
         out = torch.empty((plan.n_rows,) + tuple(x.shape[1:]), dtype=x.dtype, device=x.device)
+    if halo is not None:
+        _call("spmm_halo", x.dtype, plan.device, plan.handle, ptr(vals), ptr(x), k, ptr(out), halo, stream_ptr())
+        return out
     rb, re = _rows(plan, rows)
     _call("spmm", x.dtype, plan.device, plan.handle, ptr(vals), ptr(x), k, ptr(out), rb, re, stream_ptr())
     return out
 
 
-def residual(plan, vals, x, b, out=None, rows=None):
+def residual(plan, vals, x, b, out=None, rows=None, halo=None):
     k = _k_of(x)
     if out is None:
         out = torch.empty_like(b)
+    if halo is not None:
+        _call("residual_halo", x.dtype, plan.device, plan.handle, ptr(vals), ptr(x), ptr(b), k, ptr(out), halo,
+              stream_ptr())
+        return out
     rb, re = _rows(plan, rows)
     _call("residual", x.dtype, plan.device, plan.handle, ptr(vals), ptr(x), ptr(b), k, ptr(out), rb, re,
           stream_ptr())
@@ -308,38 +315,58 @@ def spmm_add(plan, vals, x, b, out=None, rows=None):
     return out
 
 
-def jacobi(plan, vals, diag, b, x_in, x_out, omega_dev, rows=None):
+def jacobi(plan, vals, diag, b, x_in, x_out, omega_dev, rows=None, halo=None):
     k = _k_of(x_in)
+    if halo is not None:
+        _call("jacobi_halo", x_in.dtype, plan.device, plan.handle, ptr(vals), ptr(diag), ptr(b), ptr(x_in),
+              ptr(x_out), ptr(omega_dev), k, halo, stream_ptr())
+        return x_out
     rb, re = _rows(plan, rows)
     _call("jacobi", x_in.dtype, plan.device, plan.handle, ptr(vals), ptr(diag), ptr(b), ptr(x_in),
           ptr(x_out), ptr(omega_dev), k, rb, re, stream_ptr())
     return x_out
 
 
-def cheby_first(plan, vals, b, x_in, x_out, r, p, alpha_dev, rows=None):
+def cheby_first(plan, vals, b, x_in, x_out, r, p, alpha_dev, rows=None, halo=None):
     k = _k_of(x_in)
+    if halo is not None:
+        _call("cheby_first_halo", x_in.dtype, plan.device, plan.handle, ptr(vals), ptr(b), ptr(x_in), ptr(x_out),
+              ptr(r), ptr(p), ptr(alpha_dev), k, halo, stream_ptr())
+        return
     rb, re = _rows(plan, rows)
     _call("cheby_first", x_in.dtype, plan.device, plan.handle, ptr(vals), ptr(b), ptr(x_in), ptr(x_out),
           ptr(r), ptr(p), ptr(alpha_dev), k, rb, re, stream_ptr())
 
 
-def cheby_next(plan, vals, p_in, p_out, r, x, alpha_old_dev, alpha_dev, beta_dev, rows=None):
+def cheby_next(plan, vals, p_in, p_out, r, x, alpha_old_dev, alpha_dev, beta_dev, rows=None, halo=None):
     k = _k_of(p_in)
+    if halo is not None:
+        _call("cheby_next_halo", p_in.dtype, plan.device, plan.handle, ptr(vals), ptr(p_in), ptr(p_out), ptr(r),
+              ptr(x), ptr(alpha_old_dev), ptr(alpha_dev), ptr(beta_dev), k, halo, stream_ptr())
+        return
     rb, re = _rows(plan, rows)
     _call("cheby_next", p_in.dtype, plan.device, plan.handle, ptr(vals), ptr(p_in), ptr(p_out), ptr(r),
           ptr(x), ptr(alpha_old_dev), ptr(alpha_dev), ptr(beta_dev), k, rb, re, stream_ptr())
 
 
-def power_step(plan, vals, b_in, y, sumsq_in, sumsq_out, rows=None):
-    rb, re = _rows(plan, rows)
+def power_step(plan, vals, b_in, y, sumsq_in, sumsq_out, rows=None, halo=None):
     ws = reduce_workspace(plan.device)
+    if halo is not None:
+        _call("power_step_halo", b_in.dtype, plan.device, plan.handle, ptr(vals), ptr(b_in), ptr(y),
+              ptr(sumsq_in), ptr(sumsq_out), ptr(ws), halo, stream_ptr())
+        return
+    rb, re = _rows(plan, rows)
     _call("power_step", b_in.dtype, plan.device, plan.handle, ptr(vals), ptr(b_in), ptr(y), ptr(sumsq_in),
           ptr(sumsq_out), ptr(ws), rb, re, stream_ptr())
 
 
-def rayleigh(plan, vals, b_in, b_out, y_out, sumsq_in, sums_out, rows=None):
-    rb, re = _rows(plan, rows)
+def rayleigh(plan, vals, b_in, b_out, y_out, sumsq_in, sums_out, rows=None, halo=None):
     ws = reduce_workspace(plan.device)
+    if halo is not None:
+        _call("rayleigh_halo", b_in.dtype, plan.device, plan.handle, ptr(vals), ptr(b_in), ptr(b_out), ptr(y_out),
+              ptr(sumsq_in), ptr(sums_out), ptr(ws), halo, stream_ptr())
+        return
+    rb, re = _rows(plan, rows)
     _call("rayleigh", b_in.dtype, plan.device, plan.handle, ptr(vals), ptr(b_in), ptr(b_out), ptr(y_out),
           ptr(sumsq_in), ptr(sums_out), ptr(ws), rb, re, stream_ptr())
 

@@ -323,33 +323,121 @@ static int launch_tiles(const glab_plan* p, const T* vals, const T* x, const Epi
   return (int)cudaGetLastError();
 }
 
-
-static inline int round_up(int x, int m) { return (x + m - 1) / m * m; }
-
 constexpr int kNoPipe = -1000;
+static inline int round_up(int x, int m) { return (x + m - 1) / m * m; }
 template <typename T, int K, int U, class Epi>
-static int launch_pipe_u(const glab_plan*, const T*, const T*, const Epi&, int64_t, int64_t, void*);
+static int launch_pipe_halo(const glab_plan*, const T*, const T*, const Epi&, void*, const glab_halo_step*);
+template <typename T, int K, int U, class Epi>
+static int launch_pipe_u(const glab_plan*, const T*, const T*, const Epi&, int64_t, int64_t, void*,
+                         const glab_halo_step*);
 
 // U (gathers in flight per pass) follows the operator: 5- and 9-point stencils get an exact
 // unrolled row; anything else 8 (k = 1), 4 (k = 2) or 2 (k >= 4).
 template <typename T, int K, class Epi>
 static int launch_pipe(const glab_plan* p, const T* vals, const T* x, const Epi& epi, int64_t row_begin,
-                       int64_t row_end, void* stream) {
+                       int64_t row_end, void* stream, const glab_halo_step* h = nullptr) {
   if constexpr (K == 1) {
-    if (p->max_row_nnz == 5) return launch_pipe_u<T, 1, 5>(p, vals, x, epi, row_begin, row_end, stream);
-    if (p->max_row_nnz == 9) return launch_pipe_u<T, 1, 9>(p, vals, x, epi, row_begin, row_end, stream);
-    return launch_pipe_u<T, 1, 8>(p, vals, x, epi, row_begin, row_end, stream);
+    if (p->max_row_nnz == 5) return launch_pipe_u<T, 1, 5>(p, vals, x, epi, row_begin, row_end, stream, h);
+    if (p->max_row_nnz == 9) return launch_pipe_u<T, 1, 9>(p, vals, x, epi, row_begin, row_end, stream, h);
+    return launch_pipe_u<T, 1, 8>(p, vals, x, epi, row_begin, row_end, stream, h);
   } else {
-    return launch_pipe_u<T, K, (K == 2 ? 4 : 2)>(p, vals, x, epi, row_begin, row_end, stream);
+    return launch_pipe_u<T, K, (K == 2 ? 4 : 2)>(p, vals, x, epi, row_begin, row_end, stream, h);
   }
 }
 constexpr int kNoPipeUnused = 0;  // sentinel: operator does not fit the pipeline, use the generic kernel
+
+
+template <typename T, class Epi>
+static bool make_pipe_layout(const glab_plan* p, const Epi& epi, PipeLayout& L, int64_t& slots) {
+  slots = (int64_t)kThreads * (p->max_row_nnz > 0 ? p->max_row_nnz : 1);
+  if (slots > 24576) return false;
+  int off = 0;
+  L.off_row = off; off += round_up((kThreads + 1) * 4 + 32, 128);
+  L.off_col = off; off += round_up((int)slots * 4 + 32, 128);
+  L.off_val = off; off += round_up((int)slots * (int)sizeof(T) + 32, 128);
+  for (int i = 0; i < kMaxStreams; ++i) {
+    L.off_stream[i] = off;
+    if (i < Epi::kStreams) off += round_up(kThreads * epi.stream_width(i) * (int)sizeof(T) + 32, 128);
+  }
+  L.stage_bytes = off;
+  return true;
+}
+
+// Fused step + halo exchange launch (whole row block, boundary tiles last).  No fallback: an
+// operator that does not fit the pipeline returns GLAB_E_ARG and the caller uses the
+// separate wait / boundary / push kernels instead.
+template <typename T, int K, int U, class Epi>
+static int launch_pipe_halo(const glab_plan* p, const T* vals, const T* x, const Epi& epi, void* stream,
+                            const glab_halo_step* hs) {
+  if (hs->n_wait < 0 || hs->n_wait > GLAB_MAX_PEERS || hs->n_push < 0 || hs->n_push > GLAB_MAX_PEERS)
+    return GLAB_E_ARG;
+  if ((hs->n_wait > 0 && (!hs->wait_flags || !hs->wait_target)) || (hs->n_push > 0 && (!hs->push || !hs->push_src)) ||
+      !hs->done_counter)
+    return GLAB_E_ARG;
+  const int64_t n = p->n_rows;
+  if (hs->interior_begin < 0 || hs->interior_end < hs->interior_begin || hs->interior_end > n ||
+      (hs->interior_begin % kThreads) || (hs->interior_end % kThreads && hs->interior_end != n))
+    return GLAB_E_ARG;
+  if (reinterpret_cast<uintptr_t>(p->rowptr) & 15) return GLAB_E_ARG;
+  for (int i = 0; i < Epi::kStreams; ++i)
+    if (reinterpret_cast<uintptr_t>(epi.stream_ptr(i)) & 15) return GLAB_E_ARG;
+  PipeLayout L;
+  int64_t slots;
+  if (!make_pipe_layout<T>(p, epi, L, slots)) return GLAB_E_ARG;
+  auto kern = k_row_pipe<T, K, U, Epi, true>;
+  static int max_smem = 0;
+  if (!max_smem) {
+    cudaFuncAttributes fa;
+    GLAB_CUDA(cudaFuncGetAttributes(&fa, kern));
+    const int m = 227 * 1024 - (int)fa.sharedSizeBytes;
+    GLAB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, m));
+    max_smem = m;
+  }
+  if (2 * L.stage_bytes + 128 > max_smem) return GLAB_E_ARG;
+  int want_ctas = tuning().ctas ? tuning().ctas : ((K * (int)sizeof(T) <= 8) ? 4 : 2);
+  int stages = tuning().stages ? tuning().stages : (max_smem / want_ctas - 128) / L.stage_bytes;
+  if (stages > 4) stages = 4;
+  while (stages > 2 && (size_t)stages * L.stage_bytes + 128 > (size_t)max_smem) --stages;
+  if (stages < 2) stages = 2;
+  L.stages = stages;
+  const size_t smem = (size_t)stages * L.stage_bytes + 128;
+  int occ = 0;
+  GLAB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kPipeThreads, smem));
+  if (occ < 1) return GLAB_E_ARG;
+  if (tuning().ctas && occ > tuning().ctas) occ = tuning().ctas;
+  const int ntiles = (int)((n + kThreads - 1) / kThreads);
+  HaloCtl h;
+  h.int_tile0 = (int)(hs->interior_begin / kThreads);
+  h.int_tiles = (int)((hs->interior_end - hs->interior_begin + kThreads - 1) / kThreads);
+  h.lead_tiles = h.int_tile0;
+  h.trail_tile0 = h.int_tile0 + h.int_tiles;
+  h.n_wait = hs->n_wait;
+  h.n_push = hs->n_push;
+  h.push_k = K;
+  for (int i = 0; i < GLAB_MAX_PEERS; ++i) {
+    h.wait_flag[i] = i < hs->n_wait ? hs->wait_flags[i] : nullptr;
+    if (i < hs->n_push) h.push[i] = hs->push[i];
+    else h.push[i] = glab_push_desc{nullptr, 0, nullptr, 0, nullptr};
+  }
+  h.wait_target = hs->wait_target;
+  h.pushed_counter = hs->pushed_counter;
+  h.push_src = hs->push_src;
+  h.done_counter = hs->done_counter;
+  int grid = p->sm_count * occ;
+  if (grid > kMaxReduceBlocks) grid = kMaxReduceBlocks;
+  if (grid > ntiles) grid = ntiles;
+  if (grid < 1) grid = 1;
+  TileArgs<T> a{p->rowptr, p->colidx, vals, 0, (int)n, (int)slots};
+  kern<<<grid, kPipeThreads, smem, as_stream(stream)>>>(a, x, epi, ntiles, L, h);
+  return (int)cudaGetLastError();
+}
 
 // TMA pipeline launch.  Returns kNoPipe if the operator does not fit the pipeline (caller falls
 // back to the generic chunked kernel), 0 on success, or an error code.
 template <typename T, int K, int U, class Epi>
 static int launch_pipe_u(const glab_plan* p, const T* vals, const T* x, const Epi& epi, int64_t row_begin,
-                         int64_t row_end, void* stream) {
+                         int64_t row_end, void* stream, const glab_halo_step* h) {
+  if (h) return launch_pipe_halo<T, K, U>(p, vals, x, epi, stream, h);
   if (!tuning().pipe) return kNoPipe;
   // 16-byte granule preconditions of the bulk copies (see k_row_pipe)
   if ((reinterpret_cast<uintptr_t>(p->rowptr) & 15) || ((row_begin * 4) & 15)) return kNoPipe;
@@ -369,7 +457,7 @@ static int launch_pipe_u(const glab_plan* p, const T* vals, const T* x, const Ep
     if (i < Epi::kStreams) off += round_up(kThreads * epi.stream_width(i) * (int)sizeof(T) + 32, 128);
   }
   L.stage_bytes = off;
-  auto kern = k_row_pipe<T, K, U, Epi>;
+  auto kern = k_row_pipe<T, K, U, Epi, false>;
   static int max_smem = 0;  // per instantiation: 227 KB minus the kernel's static shared memory
   if (!max_smem) {
     cudaFuncAttributes fa;
@@ -401,7 +489,7 @@ static int launch_pipe_u(const glab_plan* p, const T* vals, const T* x, const Ep
   if (grid > ntiles) grid = ntiles;
   if (grid < 1) grid = 1;
   TileArgs<T> a{p->rowptr, p->colidx, vals, (int)row_begin, (int)row_end, (int)slots};
-  kern<<<grid, kPipeThreads, smem, as_stream(stream)>>>(a, x, epi, ntiles, L);
+  kern<<<grid, kPipeThreads, smem, as_stream(stream)>>>(a, x, epi, ntiles, L, NoHalo{});
   return (int)cudaGetLastError();
 }
 
@@ -415,18 +503,18 @@ static int check_common(const glab_plan* p, const void* vals, const void* x, int
 // dispatch on K (and RPT for K == 1)
 template <typename T, template <typename, int> class EpiK, class Make>
 static int dispatch_k(const glab_plan* p, const T* vals, const T* x, int k, int64_t rb, int64_t re,
-                      void* stream, Make make) {
-  if (rb == re) return 0;
+                      void* stream, Make make, const glab_halo_step* h = nullptr) {
+  if (rb == re && !h) return 0;
   {
     int rc = kNoPipe;
     switch (k) {
-      case 1: rc = launch_pipe<T, 1>(p, vals, x, make(EpiK<T, 1>{}), rb, re, stream); break;
-      case 2: rc = launch_pipe<T, 2>(p, vals, x, make(EpiK<T, 2>{}), rb, re, stream); break;
-      case 4: rc = launch_pipe<T, 4>(p, vals, x, make(EpiK<T, 4>{}), rb, re, stream); break;
-      case 8: rc = launch_pipe<T, 8>(p, vals, x, make(EpiK<T, 8>{}), rb, re, stream); break;
+      case 1: rc = launch_pipe<T, 1>(p, vals, x, make(EpiK<T, 1>{}), rb, re, stream, h); break;
+      case 2: rc = launch_pipe<T, 2>(p, vals, x, make(EpiK<T, 2>{}), rb, re, stream, h); break;
+      case 4: rc = launch_pipe<T, 4>(p, vals, x, make(EpiK<T, 4>{}), rb, re, stream, h); break;
+      case 8: rc = launch_pipe<T, 8>(p, vals, x, make(EpiK<T, 8>{}), rb, re, stream, h); break;
       default: return GLAB_E_ARG;
     }
-    if (rc != kNoPipe) return rc;
+    if (rc != kNoPipe || h) return rc;
   }
   switch (k) {
     case 1:
@@ -441,21 +529,21 @@ static int dispatch_k(const glab_plan* p, const T* vals, const T* x, int k, int6
 
 template <typename T>
 static int spmm(const glab_plan* p, const T* vals, const T* x, int k, T* y, int64_t rb, int64_t re,
-                void* stream) {
+                void* stream, const glab_halo_step* h = nullptr) {
   int rc = check_common(p, vals, x, rb, re);
   if (rc) return rc;
   if (!y || (const void*)y == (const void*)x) return GLAB_E_ARG;
-  return dispatch_k<T, EpiSpmm>(p, vals, x, k, rb, re, stream, [&](auto e) { e.y = y; return e; });
+  return dispatch_k<T, EpiSpmm>(p, vals, x, k, rb, re, stream, [&](auto e) { e.y = y; return e; }, h);
 }
 
 template <typename T>
 static int residual(const glab_plan* p, const T* vals, const T* x, const T* b, int k, T* r,
-                    int64_t rb, int64_t re, void* stream) {
+                    int64_t rb, int64_t re, void* stream, const glab_halo_step* h = nullptr) {
   int rc = check_common(p, vals, x, rb, re);
   if (rc) return rc;
   if (!b || !r || (const void*)r == (const void*)x) return GLAB_E_ARG;
   return dispatch_k<T, EpiResidual>(p, vals, x, k, rb, re, stream, [&](auto e) {
-    e.b = b; e.out = r; return e; });
+    e.b = b; e.out = r; return e; }, h);
 }
 
 template <typename T>
@@ -470,43 +558,45 @@ static int spmm_add(const glab_plan* p, const T* vals, const T* x, const T* b, i
 
 template <typename T>
 static int jacobi(const glab_plan* p, const T* vals, const T* diag, const T* b, const T* x_in,
-                  T* x_out, const T* omega, int k, int64_t rb, int64_t re, void* stream) {
+                  T* x_out, const T* omega, int k, int64_t rb, int64_t re, void* stream,
+                  const glab_halo_step* h = nullptr) {
   int rc = check_common(p, vals, x_in, rb, re);
   if (rc) return rc;
   if (!diag || !b || !x_out || !omega || x_out == x_in) return GLAB_E_ARG;
   return dispatch_k<T, EpiJacobi>(p, vals, x_in, k, rb, re, stream, [&](auto e) {
-    e.diag = diag; e.b = b; e.x = x_in; e.xo = x_out; e.omega = omega; return e; });
+    e.diag = diag; e.b = b; e.x = x_in; e.xo = x_out; e.omega = omega; return e; }, h);
 }
 
 template <typename T>
 static int cheby_first(const glab_plan* p, const T* vals, const T* b, const T* x_in, T* x_out, T* r,
-                       T* pv, const T* alpha, int k, int64_t rb, int64_t re, void* stream) {
+                       T* pv, const T* alpha, int k, int64_t rb, int64_t re, void* stream,
+                       const glab_halo_step* h = nullptr) {
   int rc = check_common(p, vals, x_in, rb, re);
   if (rc) return rc;
   if (!b || !x_out || !r || !pv || !alpha || x_out == x_in) return GLAB_E_ARG;
   return dispatch_k<T, EpiChebyFirst>(p, vals, x_in, k, rb, re, stream, [&](auto e) {
-    e.b = b; e.x = x_in; e.xo = x_out; e.r_ = r; e.p_ = pv; e.alpha = alpha; return e; });
+    e.b = b; e.x = x_in; e.xo = x_out; e.r_ = r; e.p_ = pv; e.alpha = alpha; return e; }, h);
 }
 
 template <typename T>
 static int cheby_next(const glab_plan* p, const T* vals, const T* p_in, T* p_out, T* r, T* x,
                       const T* alpha_old, const T* alpha, const T* beta, int k, int64_t rb,
-                      int64_t re, void* stream) {
+                      int64_t re, void* stream, const glab_halo_step* h = nullptr) {
   int rc = check_common(p, vals, p_in, rb, re);
   if (rc) return rc;
   if (!p_out || !r || !x || !alpha_old || !alpha || !beta || p_out == p_in) return GLAB_E_ARG;
   return dispatch_k<T, EpiChebyNext>(p, vals, p_in, k, rb, re, stream, [&](auto e) {
     e.p_in = p_in; e.p_out = p_out; e.r_ = r; e.x_ = x;
-    e.alpha_old = alpha_old; e.alpha = alpha; e.beta = beta; return e; });
+    e.alpha_old = alpha_old; e.alpha = alpha; e.beta = beta; return e; }, h);
 }
 
 template <typename T, class Epi>
 static int launch_reducing(const glab_plan* p, const T* vals, const T* x, const Epi& epi,
-                           int64_t rb, int64_t re, void* stream) {
+                           int64_t rb, int64_t re, void* stream, const glab_halo_step* h = nullptr) {
   // rb == re still launches one (empty) tile so the output sums are written (as zeros).
   {
-    const int rc = launch_pipe<T, 1>(p, vals, x, epi, rb, re, stream);
-    if (rc != kNoPipe) return rc;
+    const int rc = launch_pipe<T, 1>(p, vals, x, epi, rb, re, stream, h);
+    if (rc != kNoPipe || h) return rc;
   }
   if (tuning().rpt == 2) return launch_tiles<T, 1, 2>(p, vals, x, epi, rb, re, true, stream);
   return launch_tiles<T, 1, 1>(p, vals, x, epi, rb, re, true, stream);
@@ -514,23 +604,24 @@ static int launch_reducing(const glab_plan* p, const T* vals, const T* x, const 
 
 template <typename T>
 static int power_step(const glab_plan* p, const T* vals, const T* b_in, T* y, const double* ss_in,
-                      double* ss_out, void* ws, int64_t rb, int64_t re, void* stream) {
+                      double* ss_out, void* ws, int64_t rb, int64_t re, void* stream,
+                      const glab_halo_step* h = nullptr) {
   int rc = check_common(p, vals, b_in, rb, re);
   if (rc) return rc;
   if (!y || !ss_out || !ws || y == b_in) return GLAB_E_ARG;
   EpiPower<T> e{y, ss_in, ss_out, ws};
-  return launch_reducing<T>(p, vals, b_in, e, rb, re, stream);
+  return launch_reducing<T>(p, vals, b_in, e, rb, re, stream, h);
 }
 
 template <typename T>
 static int rayleigh(const glab_plan* p, const T* vals, const T* b_in, T* b_out, T* y_out,
                     const double* ss_in, double* sums_out, void* ws, int64_t rb, int64_t re,
-                    void* stream) {
+                    void* stream, const glab_halo_step* h = nullptr) {
   int rc = check_common(p, vals, b_in, rb, re);
   if (rc) return rc;
   if (!b_out || !y_out || !sums_out || !ws || b_out == b_in) return GLAB_E_ARG;
   EpiRayleigh<T> e{b_in, b_out, y_out, ss_in, sums_out, ws};
-  return launch_reducing<T>(p, vals, b_in, e, rb, re, stream);
+  return launch_reducing<T>(p, vals, b_in, e, rb, re, stream, h);
 }
 
 template <typename T>
@@ -592,5 +683,49 @@ extern "C" int64_t glab_reduce_workspace_bytes(void) { return 64 + (int64_t)kMax
     return xtax<T>(p, v, x, so, ws, rb, re, s);                                                    \
   }
 
+#define GLAB_HALO_INST(SUF, T)                                                                     \
+  extern "C" int glab_spmm_halo_##SUF(const glab_plan* p, const T* v, const T* x, int k, T* y,     \
+                                      const glab_halo_step* h, void* s) {                          \
+    if (!p || !h) return GLAB_E_ARG;                                                               \
+    return spmm<T>(p, v, x, k, y, 0, p->n_rows, s, h);                                             \
+  }                                                                                                \
+  extern "C" int glab_residual_halo_##SUF(const glab_plan* p, const T* v, const T* x, const T* b,  \
+                                          int k, T* r, const glab_halo_step* h, void* s) {         \
+    if (!p || !h) return GLAB_E_ARG;                                                               \
+    return residual<T>(p, v, x, b, k, r, 0, p->n_rows, s, h);                                      \
+  }                                                                                                \
+  extern "C" int glab_jacobi_halo_##SUF(const glab_plan* p, const T* v, const T* d, const T* b,    \
+                                        const T* xi, T* xo, const T* w, int k,                     \
+                                        const glab_halo_step* h, void* s) {                        \
+    if (!p || !h) return GLAB_E_ARG;                                                               \
+    return jacobi<T>(p, v, d, b, xi, xo, w, k, 0, p->n_rows, s, h);                                \
+  }                                                                                                \
+  extern "C" int glab_cheby_first_halo_##SUF(const glab_plan* p, const T* v, const T* b,           \
+                                             const T* xi, T* xo, T* r, T* pv, const T* a, int k,   \
+                                             const glab_halo_step* h, void* s) {                   \
+    if (!p || !h) return GLAB_E_ARG;                                                               \
+    return cheby_first<T>(p, v, b, xi, xo, r, pv, a, k, 0, p->n_rows, s, h);                       \
+  }                                                                                                \
+  extern "C" int glab_cheby_next_halo_##SUF(const glab_plan* p, const T* v, const T* pi, T* po,    \
+                                            T* r, T* x, const T* ao, const T* a, const T* b,       \
+                                            int k, const glab_halo_step* h, void* s) {             \
+    if (!p || !h) return GLAB_E_ARG;                                                               \
+    return cheby_next<T>(p, v, pi, po, r, x, ao, a, b, k, 0, p->n_rows, s, h);                     \
+  }                                                                                                \
+  extern "C" int glab_power_step_halo_##SUF(const glab_plan* p, const T* v, const T* bi, T* y,     \
+                                            const double* si, double* so, void* ws,                \
+                                            const glab_halo_step* h, void* s) {                    \
+    if (!p || !h) return GLAB_E_ARG;                                                               \
+    return power_step<T>(p, v, bi, y, si, so, ws, 0, p->n_rows, s, h);                             \
+  }                                                                                                \
+  extern "C" int glab_rayleigh_halo_##SUF(const glab_plan* p, const T* v, const T* bi, T* bo,      \
+                                          T* yo, const double* si, double* so, void* ws,           \
+                                          const glab_halo_step* h, void* s) {                      \
+    if (!p || !h) return GLAB_E_ARG;                                                               \
+    return rayleigh<T>(p, v, bi, bo, yo, si, so, ws, 0, p->n_rows, s, h);                          \
+  }
+
 GLAB_INST(f32, float)
 GLAB_INST(f64, double)
+GLAB_HALO_INST(f32, float)
+GLAB_HALO_INST(f64, double)

@@ -14,6 +14,7 @@
 // are dealt round-robin so that concurrently running CTAs work on neighbouring row blocks and
 // share their gather windows in L2.
 #pragma once
+#include <type_traits>
 #include "glab_tiles.cuh"
 
 namespace glab {
@@ -78,6 +79,46 @@ __device__ __forceinline__ int lead_elems(const void* p, int esz) {
   return static_cast<int>(reinterpret_cast<uintptr_t>(p) & 15) / esz;
 }
 
+// Multi-GPU control block of a fused step (HALO = true): logical tile order puts the rows that
+// read the halo tail LAST; the producer lane acquires the neighbours' arrival counters before it
+// feeds the first such tile; after the grid's last CTA has finished, that CTA pushes this rank's
+// boundary values of the produced vector straight into the neighbours' halo tails (peer stores
+// over NVLink) and release-increments their arrival counters.  One launch per sweep.
+struct HaloCtl {
+  int int_tile0, int_tiles;    // interior tiles [int_tile0, int_tile0 + int_tiles)
+  int lead_tiles, trail_tile0; // boundary tiles [0, lead_tiles) and [trail_tile0, ntiles)
+  int n_wait, n_push, push_k;
+  uint32_t* wait_flag[GLAB_MAX_PEERS];
+  const uint32_t* wait_target;
+  glab_push_desc push[GLAB_MAX_PEERS];
+  uint32_t* pushed_counter;
+  const void* push_src;
+  unsigned int* done_counter;
+};
+struct NoHalo {};
+
+template <typename T, int K>
+__device__ __forceinline__ void load_vec_cg(T (&dst)[K], const T* p) {
+  constexpr int bytes = K * (int)sizeof(T);
+  if constexpr (bytes >= 16) {
+    constexpr int per = 16 / (int)sizeof(T);
+#pragma unroll
+    for (int i = 0; i < bytes / 16; ++i) {
+      int4 q = __ldcg(reinterpret_cast<const int4*>(p) + i);
+      const T* t = reinterpret_cast<const T*>(&q);
+#pragma unroll
+      for (int j = 0; j < per; ++j) dst[i * per + j] = t[j];
+    }
+  } else if constexpr (bytes == 8) {
+    int2 q = __ldcg(reinterpret_cast<const int2*>(p));
+    const T* t = reinterpret_cast<const T*>(&q);
+#pragma unroll
+    for (int j = 0; j < K; ++j) dst[j] = t[j];
+  } else {
+    dst[0] = __ldcg(p);
+  }
+}
+
 // Epilogue protocol for the pipeline (all in glab_layers.cu):
 //   static constexpr int kStreams;  const T* stream_ptr(i);  int stream_width(i)  (elements/row)
 //   State, init(State&), finish(State&)
@@ -88,9 +129,10 @@ __device__ __forceinline__ int lead_elems(const void* p, int esz) {
 // (only the colidx / vals slices, which start at an arbitrary CSR slot, carry a lead offset).
 // U = gathers kept in flight per thread per pass; rows of exactly U entries (every interior row
 // of a U-point stencil) take an unpredicated straight-line path.
-template <typename T, int K, int U, class Epi>
+template <typename T, int K, int U, class Epi, bool HALO>
 __global__ void __launch_bounds__(kPipeThreads, (K * sizeof(T) <= 8) ? 4 : 2)
-k_row_pipe(TileArgs<T> a, const T* __restrict__ x, Epi epi, int ntiles, PipeLayout L) {
+k_row_pipe(TileArgs<T> a, const T* __restrict__ x, Epi epi, int ntiles, PipeLayout L,
+           typename std::conditional<HALO, HaloCtl, NoHalo>::type h) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw);
   uint64_t* empty = full + L.stages;
@@ -110,27 +152,56 @@ k_row_pipe(TileArgs<T> a, const T* __restrict__ x, Epi epi, int ntiles, PipeLayo
   typename Epi::State st;
   epi.init(st);
 
+  // logical tile -> (physical tile, reads-halo flag)
+  auto phys = [&](int t, bool& boundary) -> int {
+    if constexpr (HALO) {
+      if (t < h.int_tiles) { boundary = false; return h.int_tile0 + t; }
+      const int u = t - h.int_tiles;
+      boundary = true;
+      return u < h.lead_tiles ? u : h.trail_tile0 + (u - h.lead_tiles);
+    } else {
+      boundary = false;
+      return t;
+    }
+  };
+
   if (tid >= kThreads) {
     // ------------------------------------------------------------------ producer warp
     if (tid == kThreads) {
-      int tile = blockIdx.x;
+      int lt = blockIdx.x;
       int e0n = 0, e1n = 0;
-      if (tile < ntiles) {
-        const int r0 = a.row_begin + tile * kThreads;
+      bool bnd = false, waited = false;
+      if (lt < ntiles) {
+        const int r0 = a.row_begin + phys(lt, bnd) * kThreads;
         e0n = __ldg(a.rowptr + r0);
         e1n = __ldg(a.rowptr + min(r0 + kThreads, a.row_end));
       }
       int s = 0;
       uint32_t phase = 0;
-      for (; tile < ntiles; tile += gridDim.x) {
-        const int r0 = a.row_begin + tile * kThreads;
+      for (; lt < ntiles; lt += gridDim.x) {
+        const int r0 = a.row_begin + phys(lt, bnd) * kThreads;
         const int r1 = min(r0 + kThreads, a.row_end);
         const int e0 = e0n, e1 = e1n;
-        const int nt = tile + gridDim.x;
+        const int nt = lt + gridDim.x;
         if (nt < ntiles) {  // prefetch the next tile's extents while this stage drains
-          const int q0 = a.row_begin + nt * kThreads;
+          bool b2;
+          const int q0 = a.row_begin + phys(nt, b2) * kThreads;
           e0n = __ldg(a.rowptr + q0);
           e1n = __ldg(a.rowptr + min(q0 + kThreads, a.row_end));
+        }
+        if constexpr (HALO) {
+          if (bnd && !waited) {  // neighbours' halo rows must have landed before consumers gather them
+            const uint32_t want = *reinterpret_cast<const volatile uint32_t*>(h.wait_target);
+            for (int i = 0; i < h.n_wait; ++i) {
+              uint32_t v;
+              do {
+                asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(h.wait_flag[i]) : "memory");
+                if ((int32_t)(v - want) >= 0) break;
+                __nanosleep(32);
+              } while (true);
+            }
+            waited = true;
+          }
         }
         mbar_wait(empty + s, phase ^ 1u);
         unsigned char* sb = stage0 + (size_t)s * L.stage_bytes;
@@ -169,8 +240,9 @@ k_row_pipe(TileArgs<T> a, const T* __restrict__ x, Epi epi, int ntiles, PipeLayo
     // ------------------------------------------------------------------ consumer warps
     int s = 0;
     uint32_t phase = 0;
-    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-      const int r0 = a.row_begin + tile * kThreads;
+    for (int lt = blockIdx.x; lt < ntiles; lt += gridDim.x) {
+      bool bnd;
+      const int r0 = a.row_begin + phys(lt, bnd) * kThreads;
       const int r1 = min(r0 + kThreads, a.row_end);
       const int r = r0 + tid;
       unsigned char* sb = stage0 + (size_t)s * L.stage_bytes;
@@ -184,7 +256,16 @@ k_row_pipe(TileArgs<T> a, const T* __restrict__ x, Epi epi, int ntiles, PipeLayo
         T acc[K];
 #pragma unroll
         for (int c = 0; c < K; ++c) acc[c] = T(0);
-        if (re - rs == U) {
+        if (HALO && bnd) {
+          // rows that read the halo tail: L2-coherent gathers (the tail was written by peers)
+          for (int j = rs; j < re; ++j) {
+            T xv[K];
+            load_vec_cg<T, K>(xv, x + (size_t)scol[j] * K);
+            const T v = sval[j];
+#pragma unroll
+            for (int c = 0; c < K; ++c) acc[c] = acc[c] + v * xv[c];
+          }
+        } else if (re - rs == U) {
           T vv[U];
           T xv[U][K];
 #pragma unroll
@@ -232,6 +313,40 @@ k_row_pipe(TileArgs<T> a, const T* __restrict__ x, Epi epi, int ntiles, PipeLayo
     }
   }
   epi.finish(st);
+
+  if constexpr (HALO) {
+    // ---- fused halo push: the last CTA of the grid ships the boundary rows of the produced vector
+    __shared__ bool is_last_cta;
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) {
+      const unsigned int t = atomicAdd(h.done_counter, 1u);
+      is_last_cta = (t == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (is_last_cta) {
+      __threadfence();
+      const T* src = reinterpret_cast<const T*>(h.push_src);
+      for (int q = 0; q < h.n_push; ++q) {
+        const glab_push_desc d = h.push[q];
+        T* dst = reinterpret_cast<T*>(d.dst);
+        for (int64_t i = tid; i < d.count; i += kPipeThreads) {
+          T v[K];
+          load_vec_cg<T, K>(v, src + (size_t)d.send_idx[i] * K);
+          store_vec<T, K>(dst + (size_t)(d.dst_offset + i) * K, v);
+        }
+      }
+      __threadfence_system();
+      __syncthreads();
+      if (tid == 0) {
+        for (int q = 0; q < h.n_push; ++q)
+          if (h.push[q].flag)
+            asm volatile("red.release.sys.global.add.u32 [%0], 1;" ::"l"(h.push[q].flag) : "memory");
+        if (h.pushed_counter) *h.pushed_counter += 1u;
+        *h.done_counter = 0u;
+      }
+    }
+  }
 }
 
 }  // namespace glab

@@ -215,7 +215,8 @@ class PeerHalo:
         # words (16-byte spaced): arrival counter [name][peer] (bumped remotely by that peer) and
         # pushed counter [name] (how often THIS rank has pushed the vector; the wait target)
         self.flag_index = {nm: i for i, nm in enumerate(names)}
-        self.flags = PeerBuffer(2 * len(names) * world * 4, torch.int32, device, group)
+        self.flags = PeerBuffer((2 * len(names) * world + 4) * 4, torch.int32, device, group)
+        self._steps = {}
         offs = [None] * world
         if world > 1:
             dist.all_gather_object(offs, halo.recv_offsets, group=group)
@@ -244,6 +245,35 @@ class PeerHalo:
             self._wait_args[nm] = (nf, fl, ctypes.c_void_p(pushed))
         if world > 1:
             dist.barrier(group=group)
+
+    def step(self, name_in, name_out, interior):
+        """glab_halo_step for a FUSED step that gathers vector `name_in` and produces `name_out`
+        (None: nothing to push): wait on the arrivals of name_in, push name_out from the kernel."""
+        from ._lib import HaloStep
+        key = (name_in, name_out, interior)
+        hit = self._steps.get(key)
+        if hit is not None:
+            return hit
+        world = self.halo.part.world
+        st = HaloStep()
+        st.interior_begin, st.interior_end = interior
+        nf, fl, pushed_in = self._wait_args[name_in]
+        st.n_wait = nf
+        st.wait_flags = fl
+        st.wait_target = pushed_in
+        if name_out is not None:
+            st.n_push = len(self.halo.peers_send)
+            st.push = self._push_desc[name_out]
+            st.pushed_counter = self._wait_args[name_out][2]
+            st.push_src = self.views[name_out].data_ptr()
+        else:
+            st.n_push = 0
+            st.push = None
+            st.pushed_counter = None
+            st.push_src = None
+        st.done_counter = self.flags.peer_ptr[self.rank] + (2 * len(self.flag_index) * world) * 16
+        self._steps[key] = st
+        return st
 
     def push(self, name):
         """After the kernel that produced vector `name`: send boundary rows to every neighbour."""
@@ -281,9 +311,10 @@ class DistOperator:
         boundary rows                    -> kernel(s) on the two edge ranges
         push the new boundary values     -> glab_halo_push
 
-    engine = "peer" (NVLink peer memory, default on GPUs) or "torch" (isend/irecv through
-    torch.distributed: NCCL on GPUs, gloo in the CPU tests -- there the kernels are replaced by
-    the caller's own local step, see tests/test_dist_cpu.py)."""
+    engine = "peer" (NVLink peer memory, fused one-kernel steps; default on GPUs), "peer-split"
+    (peer memory, separate wait / boundary / push kernels) or "torch" (isend/irecv through
+    torch.distributed: NCCL on GPUs; the same HaloPlan logic is what tests/test_dist_cpu.py
+    exercises with gloo)."""
 
     def __init__(self, local_edge_index, local_vals, halo, k=1, engine="peer", group=None):
         self.halo, self.k, self.group, self.engine = halo, k, group, engine
@@ -295,7 +326,7 @@ class DistOperator:
         self._keep = (local_edge_index, local_vals)
         self.lo, self.hi = halo.interior_rows(local_edge_index[0], local_edge_index[1])
         self.names = ["v0", "va", "vb"]
-        if engine == "peer":
+        if engine in ("peer", "peer-split"):
             self.peer = PeerHalo(halo, k, self.dtype, self.device, self.names, group)
             self.vec = self.peer.views
         else:
@@ -328,20 +359,26 @@ class DistOperator:
         return (self.lo, self.hi), out
 
     def run_step(self, name_in, launch, name_out=None):
-        """launch(rows) issues the fused kernel for a row range; the gathered vector is `name_in`
+        """launch(rows=None, halo=None) issues the fused kernel; the gathered vector is `name_in`
         (already published by the producer of its values).  If `name_out` is given, the vector of
-        that name -- which the step writes -- is published to the neighbours as soon as the
-        boundary rows are done.
+        that name -- which the step writes -- is published to the neighbours.
 
-        Peer engine: fork/join over two streams.  The interior rows run on the caller's stream
-        while a side stream waits for the neighbours' halo, processes the boundary rows and
-        pushes the new boundary values, so the exchange latency and the small launches hide
-        behind the interior kernel.  Captured in a CUDA graph the events become plain edges."""
+        engine "peer"       ONE kernel: interior tiles first, boundary tiles after an in-kernel
+                            acquire of the neighbours' arrival counters, halo push by the grid's
+                            last CTA (glab_*_halo_*).
+        engine "peer-split" separate kernels with fork/join over two streams: interior rows on the
+                            caller's stream; wait kernel, boundary rows and push kernel on a side
+                            stream (kept as the comparison point and for operators that do not fit
+                            the pipeline).
+        engine "torch"      whole block, then isend/irecv."""
         interior, boundary = self._ranges()
         if self.halo.part.world == 1 or self.peer is None:
-            launch((0, self.n_local))
+            launch(rows=(0, self.n_local))
             if name_out is not None:
                 self.publish(name_out)
+            return
+        if self.engine == "peer":
+            launch(halo=self.peer.step(name_in, name_out, interior))
             return
         main = torch.cuda.current_stream(self.device)
         fork = torch.cuda.Event()
@@ -351,12 +388,12 @@ class DistOperator:
             self.side.wait_event(fork)
             self.acquire(name_in)
             for rng in boundary:
-                launch(rng)
+                launch(rows=rng)
             if name_out is not None:
                 self.publish(name_out)
             join.record(self.side)
         if interior[1] > interior[0]:
-            launch(interior)
+            launch(rows=interior)
         main.wait_event(join)
 
     # -- fused layer steps -------------------------------------------------------------------
@@ -372,7 +409,7 @@ class DistOperator:
         for _ in range(n_iters):
             nxt = "va" if cur != "va" else "vb"
             xin, xout = self.vec[cur], self.vec[nxt]
-            self.run_step(cur, lambda rows: rt.jacobi(self.plan, self.vals, diag, b, xin, xout, omega_dev, rows),
+            self.run_step(cur, lambda **kw: rt.jacobi(self.plan, self.vals, diag, b, xin, xout, omega_dev, **kw),
                           nxt)
             cur = nxt
         return cur
@@ -380,9 +417,9 @@ class DistOperator:
     def spmv(self, name_in, out, b=None):
         xin = self.vec[name_in]
         if b is None:
-            self.run_step(name_in, lambda rows: rt.spmm(self.plan, self.vals, xin, out, rows))
+            self.run_step(name_in, lambda **kw: rt.spmm(self.plan, self.vals, xin, out, **kw))
         else:
-            self.run_step(name_in, lambda rows: rt.residual(self.plan, self.vals, xin, b, out, rows))
+            self.run_step(name_in, lambda **kw: rt.residual(self.plan, self.vals, xin, b, out, **kw))
         return out
 
     def chebyshev(self, deg, b, table, start="va", x=None, r=None):
@@ -395,13 +432,13 @@ class DistOperator:
         x = torch.empty(n, k, dtype=self.dtype, device=self.device) if x is None else x
         r = torch.empty_like(x) if r is None else r
         pv = self.vec[other]
-        self.run_step(start, lambda rows: rt.cheby_first(self.plan, self.vals, b, xin, x, r, pv, table[0, 1:2], rows),
+        self.run_step(start, lambda **kw: rt.cheby_first(self.plan, self.vals, b, xin, x, r, pv, table[0, 1:2], **kw),
                       other)
         cur, nxt = other, start
         for it in range(1, deg):
             pin, pout = self.vec[cur], self.vec[nxt]
-            self.run_step(cur, lambda rows: rt.cheby_next(self.plan, self.vals, pin, pout, r, x,
-                                                          table[it, 0:1], table[it, 1:2], table[it, 2:3], rows), nxt)
+            self.run_step(cur, lambda **kw: rt.cheby_next(self.plan, self.vals, pin, pout, r, x,
+                                                          table[it, 0:1], table[it, 1:2], table[it, 2:3], **kw), nxt)
             cur, nxt = nxt, cur
         return x, r, cur
 
@@ -419,20 +456,28 @@ class DistOperator:
             ss = sums[2 * it:2 * it + 2]
             bin_, yout = self.vec[cur], self.vec[nxt]
             part = torch.zeros(2, dtype=torch.float64, device=self.device)
-            self._reduced_step(cur, lambda rows, acc: rt.power_step(self.plan, self.vals, bin_, yout, prev, acc, rows),
-                               part)
+            if multi and self.engine == "peer":
+                rt.power_step(self.plan, self.vals, bin_, yout, prev, part,
+                              halo=self.peer.step(cur, nxt, self._ranges()[0]))
+            else:
+                self._reduced_step(cur, lambda rows, acc: rt.power_step(self.plan, self.vals, bin_, yout, prev, acc,
+                                                                        rows), part)
+                self.publish(nxt)
             if multi:
                 dist.all_reduce(part, group=self.group)
             ss.copy_(part)
-            self.publish(nxt)
             cur = nxt
             prev = ss
         bout = torch.empty(n, self.k, dtype=self.dtype, device=self.device)
         yout = torch.empty_like(bout)
         part = torch.zeros(2, dtype=torch.float64, device=self.device)
         bin_ = self.vec[cur]
-        self._reduced_step(cur, lambda rows, acc: rt.rayleigh(self.plan, self.vals, bin_, bout, yout, prev, acc, rows),
-                           part)
+        if multi and self.engine == "peer":
+            rt.rayleigh(self.plan, self.vals, bin_, bout, yout, prev, part,
+                        halo=self.peer.step(cur, None, self._ranges()[0]))
+        else:
+            self._reduced_step(cur, lambda rows, acc: rt.rayleigh(self.plan, self.vals, bin_, bout, yout, prev, acc,
+                                                                  rows), part)
         if multi:
             dist.all_reduce(part, group=self.group)
         norm = torch.sqrt(prev[0]) if prev is not None else torch.ones((), dtype=torch.float64, device=self.device)

@@ -270,6 +270,69 @@ int glab_halo_push_f64(const double* src, int k, int n_peers, const glab_push_de
  * flags is a HOST array of device pointers. */
 int glab_halo_wait(int n_flags, uint32_t* const* flags, const uint32_t* pushed_local, void* stream);
 
+/* ------------------------------------------------------------------------------------------
+ * Fused step + halo exchange: ONE kernel per sweep on a row-partitioned operator.
+ * The step processes the rows of [interior_begin, interior_end) first (they gather only local
+ * values), then the remaining boundary rows, whose producer acquires the arrival counters
+ * wait_flags[i] (until each has reached *wait_target -- the neighbours' pushes of the GATHERED
+ * vector); when the whole grid has finished, its last CTA stores this rank's boundary rows of
+ * `push_src` (the vector the step PRODUCED and the next step will gather: x_out for Jacobi,
+ * p_out for Chebyshev, y for the power step) into the neighbours' halo tails through the
+ * peer-mapped pointers of `push`, release-increments their arrival counters and ++*pushed_counter.
+ * interior_begin / interior_end must be multiples of 256.  All arrays are HOST arrays copied at
+ * launch; done_counter is a zero-initialised device word owned by the caller.
+ * ------------------------------------------------------------------------------------------ */
+typedef struct glab_halo_step {
+  int64_t interior_begin, interior_end;
+  int32_t n_wait;
+  uint32_t* const* wait_flags;
+  const uint32_t* wait_target;
+  int32_t n_push;
+  const glab_push_desc* push;
+  uint32_t* pushed_counter;
+  const void* push_src;
+  uint32_t* done_counter;
+} glab_halo_step;
+
+int glab_spmm_halo_f32(const glab_plan*, const float* vals, const float* x, int k, float* y,
+                       const glab_halo_step* halo, void* stream);
+int glab_spmm_halo_f64(const glab_plan*, const double* vals, const double* x, int k, double* y,
+                       const glab_halo_step* halo, void* stream);
+int glab_residual_halo_f32(const glab_plan*, const float* vals, const float* x, const float* b, int k,
+                           float* r, const glab_halo_step* halo, void* stream);
+int glab_residual_halo_f64(const glab_plan*, const double* vals, const double* x, const double* b, int k,
+                           double* r, const glab_halo_step* halo, void* stream);
+int glab_jacobi_halo_f32(const glab_plan*, const float* vals, const float* diag, const float* b,
+                         const float* x_in, float* x_out, const float* omega_dev, int k,
+                         const glab_halo_step* halo, void* stream);
+int glab_jacobi_halo_f64(const glab_plan*, const double* vals, const double* diag, const double* b,
+                         const double* x_in, double* x_out, const double* omega_dev, int k,
+                         const glab_halo_step* halo, void* stream);
+int glab_cheby_first_halo_f32(const glab_plan*, const float* vals, const float* b, const float* x_in,
+                              float* x_out, float* r, float* p, const float* alpha_dev, int k,
+                              const glab_halo_step* halo, void* stream);
+int glab_cheby_first_halo_f64(const glab_plan*, const double* vals, const double* b, const double* x_in,
+                              double* x_out, double* r, double* p, const double* alpha_dev, int k,
+                              const glab_halo_step* halo, void* stream);
+int glab_cheby_next_halo_f32(const glab_plan*, const float* vals, const float* p_in, float* p_out,
+                             float* r, float* x, const float* alpha_old_dev, const float* alpha_dev,
+                             const float* beta_dev, int k, const glab_halo_step* halo, void* stream);
+int glab_cheby_next_halo_f64(const glab_plan*, const double* vals, const double* p_in, double* p_out,
+                             double* r, double* x, const double* alpha_old_dev, const double* alpha_dev,
+                             const double* beta_dev, int k, const glab_halo_step* halo, void* stream);
+int glab_power_step_halo_f32(const glab_plan*, const float* vals, const float* b_in, float* y,
+                             const double* sumsq_in, double* sumsq_out, void* workspace,
+                             const glab_halo_step* halo, void* stream);
+int glab_power_step_halo_f64(const glab_plan*, const double* vals, const double* b_in, double* y,
+                             const double* sumsq_in, double* sumsq_out, void* workspace,
+                             const glab_halo_step* halo, void* stream);
+int glab_rayleigh_halo_f32(const glab_plan*, const float* vals, const float* b_in, float* b_out,
+                           float* y_out, const double* sumsq_in, double* sums_out, void* workspace,
+                           const glab_halo_step* halo, void* stream);
+int glab_rayleigh_halo_f64(const glab_plan*, const double* vals, const double* b_in, double* b_out,
+                           double* y_out, const double* sumsq_in, double* sums_out, void* workspace,
+                           const glab_halo_step* halo, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -54,7 +54,7 @@ def main():
         va = torch.cat([x0, torch.zeros_like(x0)], 1)
         ea = torch.cat([ev, torch.zeros_like(ev)], 1)
         g_ref = G.PowerMethodGNN.PowerMethodGNN(20)(va, ei, ea, torch.zeros(3, dtype=dt), None)[2]
-        for engine in ("peer", "torch"):
+        for engine in ("peer", "peer-split", "torch"):
             part = gd.RowPartition(n, world, align=256)
             r0, r1 = part.bounds(rank)
             lei, lev, halo = gd.partition_coo(ei, ev, part, rank)

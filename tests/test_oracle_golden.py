@@ -111,8 +111,8 @@ def test_known_answers(golden):
     # SOCClassicGNN.py:151-186: all S_ij = 0.75 for theta = 0.25
     assert torch.all(port.soc_classic(0.25, torch.zeros(25, 1, dtype=torch.float64), eo, ao) == 0.75)
     # analytic: extreme eigenvalue of laplacianfun_torch(5) is -4 - 2*sqrt(3)
-    x = torch.rand(25, 1, dtype=torch.float64)
+    x = torch.rand(25, 1, dtype=torch.float64, generator=torch.Generator().manual_seed(24601))
     ea = torch.cat([ev, torch.zeros_like(ev)], 1)
     lam = port.power_method(100, torch.cat([x, torch.zeros_like(x)], 1), ei, ea,
                             torch.zeros(3, dtype=torch.float64))[2][2].item()
-    assert abs(lam - (-4 - 2 * 3 ** 0.5)) < 1e-9
+    assert abs(lam - (-4 - 2 * 3 ** 0.5)) < 1e-6   # 100 iterations, gap ratio 0.93: not fully converged
