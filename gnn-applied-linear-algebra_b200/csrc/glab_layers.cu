@@ -423,9 +423,9 @@ static int launch_pipe_halo(const glab_plan* p, const T* vals, const T* x, const
   h.pushed_counter = hs->pushed_counter;
   h.push_src = hs->push_src;
   h.done_counter = hs->done_counter;
-  int grid = p->sm_count * occ;
+  int grid = p->sm_count * occ;   // all co-resident: the communication CTA (block 0) must run
   if (grid > kMaxReduceBlocks) grid = kMaxReduceBlocks;
-  if (grid > ntiles) grid = ntiles;
+  if (grid > ntiles + 1) grid = ntiles + 1;
   if (grid < 1) grid = 1;
   TileArgs<T> a{p->rowptr, p->colidx, vals, 0, (int)n, (int)slots};
   kern<<<grid, kPipeThreads, smem, as_stream(stream)>>>(a, x, epi, ntiles, L, h);

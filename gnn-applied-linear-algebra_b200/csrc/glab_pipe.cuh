@@ -79,11 +79,15 @@ __device__ __forceinline__ int lead_elems(const void* p, int esz) {
   return static_cast<int>(reinterpret_cast<uintptr_t>(p) & 15) / esz;
 }
 
-// Multi-GPU control block of a fused step (HALO = true): logical tile order puts the rows that
-// read the halo tail LAST; the producer lane acquires the neighbours' arrival counters before it
-// feeds the first such tile; after the grid's last CTA has finished, that CTA pushes this rank's
-// boundary values of the produced vector straight into the neighbours' halo tails (peer stores
-// over NVLink) and release-increments their arrival counters.  One launch per sweep.
+// Multi-GPU control block of a fused step (HALO = true).  One launch per sweep:
+//   * logical tile order puts the rows that read the halo tail FIRST; the producer lane acquires
+//     the neighbours' arrival counters before it feeds the first such tile (the neighbours pushed
+//     early in THEIR previous kernel, so this never stalls in steady state);
+//   * every finished boundary tile bumps a device counter; CTA 0 is a communication CTA that does
+//     no row work: it waits for that counter, then stores this rank's boundary values of the
+//     produced vector straight into the neighbours' halo tails (peer stores over NVLink) and
+//     release-increments their arrival counters -- all while the other CTAs are still busy with
+//     the interior tiles, so neither the exchange latency nor the flag round trip is exposed.
 struct HaloCtl {
   int int_tile0, int_tiles;    // interior tiles [int_tile0, int_tile0 + int_tiles)
   int lead_tiles, trail_tile0; // boundary tiles [0, lead_tiles) and [trail_tile0, ntiles)
@@ -152,23 +156,67 @@ k_row_pipe(TileArgs<T> a, const T* __restrict__ x, Epi epi, int ntiles, PipeLayo
   typename Epi::State st;
   epi.init(st);
 
-  // logical tile -> (physical tile, reads-halo flag)
+  // logical tile -> (physical tile, reads-halo flag); boundary tiles come first
   auto phys = [&](int t, bool& boundary) -> int {
     if constexpr (HALO) {
-      if (t < h.int_tiles) { boundary = false; return h.int_tile0 + t; }
-      const int u = t - h.int_tiles;
+      const int nb = ntiles - h.int_tiles;
+      if (t >= nb) { boundary = false; return h.int_tile0 + (t - nb); }
       boundary = true;
-      return u < h.lead_tiles ? u : h.trail_tile0 + (u - h.lead_tiles);
+      return t < h.lead_tiles ? t : h.trail_tile0 + (t - h.lead_tiles);
     } else {
       boundary = false;
       return t;
     }
   };
+  // CTA roles: with a push to do, CTA 0 only communicates and the rest share the tiles
+  int cta = blockIdx.x, ncta = gridDim.x;
+  bool comm_cta = false;
+  if constexpr (HALO) {
+    if (h.n_push > 0 && gridDim.x > 1) {
+      comm_cta = (blockIdx.x == 0);
+      cta = (int)blockIdx.x - 1;
+      ncta = (int)gridDim.x - 1;
+    }
+  }
 
-  if (tid >= kThreads) {
+  if (comm_cta) {
+    if constexpr (HALO) {
+      // ---------------------------------------------------------------- communication CTA
+      const unsigned int nb = (unsigned int)(ntiles - h.int_tiles);
+      if (tid == 0) {
+        unsigned int v;
+        do {
+          asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(h.done_counter) : "memory");
+          if (v >= nb) break;
+          __nanosleep(200);
+        } while (true);
+      }
+      __syncthreads();
+      __threadfence();
+      const T* src = reinterpret_cast<const T*>(h.push_src);
+      for (int q = 0; q < h.n_push; ++q) {
+        const glab_push_desc d = h.push[q];
+        T* dst = reinterpret_cast<T*>(d.dst);
+        for (int64_t i = tid; i < d.count; i += kPipeThreads) {
+          T v[K];
+          load_vec_cg<T, K>(v, src + (size_t)d.send_idx[i] * K);
+          store_vec<T, K>(dst + (size_t)(d.dst_offset + i) * K, v);
+        }
+      }
+      __threadfence_system();
+      __syncthreads();
+      if (tid == 0) {
+        for (int q = 0; q < h.n_push; ++q)
+          if (h.push[q].flag)
+            asm volatile("red.release.sys.global.add.u32 [%0], 1;" ::"l"(h.push[q].flag) : "memory");
+        if (h.pushed_counter) *h.pushed_counter += 1u;
+        *h.done_counter = 0u;
+      }
+    }
+  } else if (tid >= kThreads) {
     // ------------------------------------------------------------------ producer warp
     if (tid == kThreads) {
-      int lt = blockIdx.x;
+      int lt = cta;
       int e0n = 0, e1n = 0;
       bool bnd = false, waited = false;
       if (lt < ntiles) {
@@ -178,11 +226,11 @@ k_row_pipe(TileArgs<T> a, const T* __restrict__ x, Epi epi, int ntiles, PipeLayo
       }
       int s = 0;
       uint32_t phase = 0;
-      for (; lt < ntiles; lt += gridDim.x) {
+      for (; lt < ntiles; lt += ncta) {
         const int r0 = a.row_begin + phys(lt, bnd) * kThreads;
         const int r1 = min(r0 + kThreads, a.row_end);
         const int e0 = e0n, e1 = e1n;
-        const int nt = lt + gridDim.x;
+        const int nt = lt + ncta;
         if (nt < ntiles) {  // prefetch the next tile's extents while this stage drains
           bool b2;
           const int q0 = a.row_begin + phys(nt, b2) * kThreads;
@@ -240,7 +288,7 @@ k_row_pipe(TileArgs<T> a, const T* __restrict__ x, Epi epi, int ntiles, PipeLayo
     // ------------------------------------------------------------------ consumer warps
     int s = 0;
     uint32_t phase = 0;
-    for (int lt = blockIdx.x; lt < ntiles; lt += gridDim.x) {
+    for (int lt = cta; lt < ntiles; lt += ncta) {
       bool bnd;
       const int r0 = a.row_begin + phys(lt, bnd) * kThreads;
       const int r1 = min(r0 + kThreads, a.row_end);
@@ -310,43 +358,19 @@ k_row_pipe(TileArgs<T> a, const T* __restrict__ x, Epi epi, int ntiles, PipeLayo
       __syncwarp();
       if ((tid & 31) == 0) mbar_arrive(empty + s);
       if (++s == S) { s = 0; phase ^= 1u; }
+      if constexpr (HALO) {
+        if (bnd && h.n_push > 0) {  // tell the communication CTA that this boundary tile is stored
+          asm volatile("bar.sync 1, 256;" ::: "memory");
+          if (tid == 0) {
+            __threadfence();
+            atomicAdd(h.done_counter, 1u);
+          }
+        }
+      }
     }
   }
   epi.finish(st);
 
-  if constexpr (HALO) {
-    // ---- fused halo push: the last CTA of the grid ships the boundary rows of the produced vector
-    __shared__ bool is_last_cta;
-    __threadfence();
-    __syncthreads();
-    if (tid == 0) {
-      const unsigned int t = atomicAdd(h.done_counter, 1u);
-      is_last_cta = (t == gridDim.x - 1);
-    }
-    __syncthreads();
-    if (is_last_cta) {
-      __threadfence();
-      const T* src = reinterpret_cast<const T*>(h.push_src);
-      for (int q = 0; q < h.n_push; ++q) {
-        const glab_push_desc d = h.push[q];
-        T* dst = reinterpret_cast<T*>(d.dst);
-        for (int64_t i = tid; i < d.count; i += kPipeThreads) {
-          T v[K];
-          load_vec_cg<T, K>(v, src + (size_t)d.send_idx[i] * K);
-          store_vec<T, K>(dst + (size_t)(d.dst_offset + i) * K, v);
-        }
-      }
-      __threadfence_system();
-      __syncthreads();
-      if (tid == 0) {
-        for (int q = 0; q < h.n_push; ++q)
-          if (h.push[q].flag)
-            asm volatile("red.release.sys.global.add.u32 [%0], 1;" ::"l"(h.push[q].flag) : "memory");
-        if (h.pushed_counter) *h.pushed_counter += 1u;
-        *h.done_counter = 0u;
-      }
-    }
-  }
 }
 
 }  // namespace glab

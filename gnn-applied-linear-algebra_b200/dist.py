@@ -98,10 +98,13 @@ class HaloPlan:
         return torch.where(inside, global_cols - r0, pos + self.n_local)
 
     def interior_rows(self, local_rows, local_cols, align=256):
-        """[lo, hi): a contiguous range of rows none of which reads the halo tail (aligned to the
-        kernel's 256-row tiles).  Rows outside it must wait for the exchange."""
+        """[lo, hi): a contiguous range of rows none of which reads the halo tail or is sent to a
+        neighbour (aligned to the kernel's 256-row tiles).  Rows outside it are the boundary rows:
+        they wait for the exchange and are finished before the push."""
         touches = torch.zeros(self.n_local, dtype=torch.bool, device=local_rows.device)
         touches[local_rows[local_cols >= self.n_local]] = True
+        for q in self.peers_send:   # rows we ship to neighbours must be finished before the push
+            touches[self.send_rows[q].long().to(local_rows.device)] = True
         idx = torch.nonzero(touches).reshape(-1)
         if idx.numel() == 0:
             return 0, self.n_local
