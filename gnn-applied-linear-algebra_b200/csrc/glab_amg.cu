@@ -2,7 +2,8 @@
 // direct-interpolation weights, and the per-edge message column.  All are row-local single
 // passes over the CSR slots with bit-exact element-wise chains (IEEE div, no FMA contraction,
 // the reference's operation order); citations are in include/glab.h.
-#include "glab_tiles.cuh"
+#include <cstdlib>
+#include "glab_pipe.cuh"
 
 namespace glab {
 
@@ -10,6 +11,7 @@ namespace glab {
 template <typename T> struct OpSocClassic {
   static constexpr bool kReduce = true;
   static constexpr int kNarr = 1;
+  static constexpr bool kNeedCol = false;
   T theta;
   T* rowmax;  // optional [n_rows]
   struct RowState { T v; bool any; };
@@ -35,6 +37,7 @@ template <typename T> struct OpSocClassic {
 template <typename T> struct OpSocSA {
   static constexpr bool kReduce = false;
   static constexpr int kNarr = 1;
+  static constexpr bool kNeedCol = true;
   const T* diag;
   struct RowState { T dii; };
   __device__ void begin_row(RowState& s, int r) const { s.dii = __ldg(diag + r); }
@@ -49,6 +52,7 @@ template <typename T> struct OpSocSA {
 template <typename T> struct OpDirectInterp {
   static constexpr bool kReduce = true;
   static constexpr int kNarr = 2;
+  static constexpr bool kNeedCol = true;
   const T* diag;
   const T* cflag;
   struct RowState { T num, den, alpha, omc; };
@@ -65,12 +69,59 @@ template <typename T> struct OpDirectInterp {
   __device__ T edge(const RowState& s, T a, T, int) const { return s.omc * ((-a) * s.alpha); }
 };
 
+static inline int round_up128(int x) { return (x + 127) / 128 * 128; }
+
+// TMA pipeline variant; returns -1000 when the operator does not fit (caller falls back).
+template <typename T, class Op>
+static int launch_edge_pipe(const glab_plan* p, const T* vals, const T* aux, const Op& op, T* out,
+                            void* stream) {
+  if (getenv("GLAB_PIPE") && atoi(getenv("GLAB_PIPE")) == 0) return -1000;
+  if (reinterpret_cast<uintptr_t>(p->rowptr) & 15) return -1000;
+  const int64_t slots = (int64_t)kThreads * (p->max_row_nnz > 0 ? p->max_row_nnz : 1);
+  if (slots > 16384) return -1000;
+  EdgePipeLayout L;
+  int off = 0;
+  L.off_row = off; off += round_up128((kThreads + 1) * 4 + 32);
+  L.off_val = off; off += round_up128((int)slots * (int)sizeof(T) + 32);
+  L.off_col = off; if (Op::kNeedCol) off += round_up128((int)slots * 4 + 32);
+  L.off_aux = off; if (Op::kNarr > 1) off += round_up128((int)slots * (int)sizeof(T) + 32);
+  L.stage_bytes = off;
+  auto kern = k_edge_pipe<T, Op>;
+  static int max_smem = 0;
+  if (!max_smem) {
+    cudaFuncAttributes fa;
+    GLAB_CUDA(cudaFuncGetAttributes(&fa, kern));
+    const int m = 227 * 1024 - (int)fa.sharedSizeBytes;
+    GLAB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, m));
+    max_smem = m;
+  }
+  if (2 * L.stage_bytes + 128 > max_smem) return -1000;
+  int stages = (max_smem / 4 - 128) / L.stage_bytes;
+  if (stages > 4) stages = 4;
+  if (stages < 2) stages = 2;
+  L.stages = stages;
+  const size_t smem = (size_t)stages * L.stage_bytes + 128;
+  int occ = 0;
+  GLAB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kPipeThreads, smem));
+  if (occ < 1) return -1000;
+  const int ntiles = (int)((p->n_rows + kThreads - 1) / kThreads);
+  int grid = p->sm_count * occ;
+  if (grid > ntiles) grid = ntiles;
+  TileArgs<T> a{p->rowptr, p->colidx, vals, 0, (int)p->n_rows, (int)slots};
+  kern<<<grid, kPipeThreads, smem, as_stream(stream)>>>(a, aux ? aux : vals, p->perm, op, out, ntiles, L);
+  return (int)cudaGetLastError();
+}
+
 template <typename T, class Op>
 static int launch_edge_tiles(const glab_plan* p, const T* vals, const T* aux, const Op& op, T* out,
                              void* stream) {
   if (!p) return GLAB_E_ARG;
   if (p->nnz == 0 || p->n_rows == 0) return 0;  // no edges -> no per-edge outputs
   if (!out || !vals) return GLAB_E_ARG;
+  {
+    const int rc = launch_edge_pipe<T, Op>(p, vals, aux, op, out, stream);
+    if (rc != -1000) return rc;
+  }
   const int ntiles = (int)((p->n_rows + kThreads - 1) / kThreads);
   int64_t want = (int64_t)kThreads * (p->max_row_nnz > 0 ? p->max_row_nnz : 1);
   int cap = (int)(want < 4096 ? want : 4096);

@@ -373,4 +373,189 @@ k_row_pipe(TileArgs<T> a, const T* __restrict__ x, Epi epi, int ntiles, PipeLayo
 
 }
 
+// ------------------------------------------------------------------------------------------
+// Per-edge-output pipeline (AMG setup): same producer / ring as k_row_pipe, but the consumers
+// (1) reduce over their row in shared memory, (2) overwrite the staged values with the per-edge
+// result in place, (3) meet at a named barrier and (4) write the tile's contiguous slot range
+// out coalesced (out[perm[slot]] when the caller's edge order is not the CSR order).
+//   Op::kReduce / kNarr (1: vals, 2: vals + aux) / kNeedCol;  RowState, begin_row, accumulate,
+//   end_row, edge -- see glab_amg.cu.
+// Rows are read with 16-byte shared-memory loads whenever the row start is 16-byte aligned in
+// every staged array (always true for the fixed-degree stencil operators), which avoids the
+// 8-way bank conflicts a stride-8 scalar walk would have.
+// ------------------------------------------------------------------------------------------
+struct EdgePipeLayout {
+  int stages, stage_bytes, off_row, off_col, off_val, off_aux;
+};
+
+template <typename E, int V> __device__ __forceinline__ void lds_vec(E (&d)[V], const E* p) {
+  if constexpr (V * sizeof(E) == 16) {
+    const int4 q = *reinterpret_cast<const int4*>(p);
+    const E* t = reinterpret_cast<const E*>(&q);
+#pragma unroll
+    for (int i = 0; i < V; ++i) d[i] = t[i];
+  } else if constexpr (V * sizeof(E) == 8) {
+    const int2 q = *reinterpret_cast<const int2*>(p);
+    const E* t = reinterpret_cast<const E*>(&q);
+#pragma unroll
+    for (int i = 0; i < V; ++i) d[i] = t[i];
+  } else {
+#pragma unroll
+    for (int i = 0; i < V; ++i) d[i] = p[i];
+  }
+}
+template <typename E, int V> __device__ __forceinline__ void sts_vec(E* p, const E (&d)[V]) {
+  if constexpr (V * sizeof(E) == 16) {
+    int4 q;
+    E* t = reinterpret_cast<E*>(&q);
+#pragma unroll
+    for (int i = 0; i < V; ++i) t[i] = d[i];
+    *reinterpret_cast<int4*>(p) = q;
+  } else {
+#pragma unroll
+    for (int i = 0; i < V; ++i) p[i] = d[i];
+  }
+}
+
+template <typename T, class Op>
+__global__ void __launch_bounds__(kPipeThreads, 4)
+k_edge_pipe(TileArgs<T> a, const T* __restrict__ aux, const int32_t* __restrict__ perm, Op op,
+            T* __restrict__ out, int ntiles, EdgePipeLayout L) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw);
+  uint64_t* empty = full + L.stages;
+  unsigned char* stage0 = smem_raw + 128;
+  const int tid = threadIdx.x;
+  const int S = L.stages;
+  constexpr int V = 16 / (int)sizeof(T);  // elements per 16-byte value vector
+
+  if (tid == 0) {
+    for (int s = 0; s < S; ++s) {
+      mbar_init(full + s, 1);
+      mbar_init(empty + s, kThreads / 32);
+    }
+    mbar_fence_init();
+  }
+  __syncthreads();
+
+  if (tid >= kThreads) {
+    if (tid == kThreads) {  // ---------------------------------------------------- producer
+      int tile = blockIdx.x;
+      int e0n = 0, e1n = 0;
+      if (tile < ntiles) {
+        const int r0 = tile * kThreads;
+        e0n = __ldg(a.rowptr + r0);
+        e1n = __ldg(a.rowptr + min(r0 + kThreads, a.row_end));
+      }
+      int s = 0;
+      uint32_t phase = 0;
+      for (; tile < ntiles; tile += gridDim.x) {
+        const int r0 = tile * kThreads;
+        const int r1 = min(r0 + kThreads, a.row_end);
+        const int e0 = e0n, e1 = e1n;
+        const int nt = tile + gridDim.x;
+        if (nt < ntiles) {
+          const int q0 = nt * kThreads;
+          e0n = __ldg(a.rowptr + q0);
+          e1n = __ldg(a.rowptr + min(q0 + kThreads, a.row_end));
+        }
+        mbar_wait(empty + s, phase ^ 1u);
+        unsigned char* sb = stage0 + (size_t)s * L.stage_bytes;
+        const void *src_c = nullptr, *src_v = nullptr, *src_a = nullptr;
+        uint32_t nb_c = 0, nb_v = 0, nb_a = 0;
+        const uint32_t nb_r = (uint32_t)(((r1 - r0 + 1) * 4 + 15) & ~15);
+        uint32_t total = nb_r;
+        if (e1 > e0) {
+          align16(a.vals + e0, (e1 - e0) * (int)sizeof(T), src_v, nb_v);
+          total += nb_v;
+          if (Op::kNeedCol) {
+            align16(a.colidx + e0, (e1 - e0) * 4, src_c, nb_c);
+            total += nb_c;
+          }
+          if (Op::kNarr > 1) {
+            align16(aux + e0, (e1 - e0) * (int)sizeof(T), src_a, nb_a);
+            total += nb_a;
+          }
+        }
+        mbar_expect_tx(full + s, total);
+        bulk_g2s(sb + L.off_row, a.rowptr + r0, nb_r, full + s);
+        if (nb_v) bulk_g2s(sb + L.off_val, src_v, nb_v, full + s);
+        if (nb_c) bulk_g2s(sb + L.off_col, src_c, nb_c, full + s);
+        if (nb_a) bulk_g2s(sb + L.off_aux, src_a, nb_a, full + s);
+        if (++s == S) { s = 0; phase ^= 1u; }
+      }
+    }
+  } else {
+    int s = 0;  // ------------------------------------------------------------------ consumers
+    uint32_t phase = 0;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+      const int r0 = tile * kThreads;
+      const int r1 = min(r0 + kThreads, a.row_end);
+      const int r = r0 + tid;
+      unsigned char* sb = stage0 + (size_t)s * L.stage_bytes;
+      const int32_t* srow = reinterpret_cast<const int32_t*>(sb + L.off_row);
+      mbar_wait(full + s, phase);
+      const int e0 = srow[0];
+      const int e1 = srow[r1 - r0];
+      T* sval = reinterpret_cast<T*>(sb + L.off_val) + lead_elems(a.vals + e0, sizeof(T)) - e0;
+      const int32_t* scol = reinterpret_cast<const int32_t*>(sb + L.off_col) + lead_elems(a.colidx + e0, 4) - e0;
+      const T* saux = reinterpret_cast<const T*>(sb + L.off_aux) + lead_elems(aux + e0, sizeof(T)) - e0;
+      if (r < r1) {
+        const int rs = srow[tid], re = srow[tid + 1];
+        typename Op::RowState st;
+        op.begin_row(st, r);
+        // 16-byte alignment of the row start in every staged array -> vector walk
+        const bool vec = ((re - rs) % V == 0) && ((reinterpret_cast<uintptr_t>(sval + rs) & 15) == 0) &&
+                         (!Op::kNeedCol || (reinterpret_cast<uintptr_t>(scol + rs) & (V * 4 - 1)) == 0) &&
+                         (Op::kNarr < 2 || (reinterpret_cast<uintptr_t>(saux + rs) & 15) == 0);
+        if (vec) {
+          if (Op::kReduce) {
+            for (int j = rs; j < re; j += V) {
+              T v[V], x2[V];
+              int32_t c[V];
+              lds_vec<T, V>(v, sval + j);
+              if (Op::kNeedCol) lds_vec<int32_t, V>(c, scol + j);
+              if (Op::kNarr > 1) lds_vec<T, V>(x2, saux + j);
+#pragma unroll
+              for (int u = 0; u < V; ++u)
+                op.accumulate(st, v[u], Op::kNarr > 1 ? x2[u] : T(0), Op::kNeedCol ? c[u] : 0);
+            }
+          }
+          op.end_row(st, r);
+          for (int j = rs; j < re; j += V) {
+            T v[V], x2[V], o[V];
+            int32_t c[V];
+            lds_vec<T, V>(v, sval + j);
+            if (Op::kNeedCol) lds_vec<int32_t, V>(c, scol + j);
+            if (Op::kNarr > 1) lds_vec<T, V>(x2, saux + j);
+#pragma unroll
+            for (int u = 0; u < V; ++u)
+              o[u] = op.edge(st, v[u], Op::kNarr > 1 ? x2[u] : T(0), Op::kNeedCol ? c[u] : 0);
+            sts_vec<T, V>(sval + j, o);
+          }
+        } else {
+          if (Op::kReduce)
+            for (int j = rs; j < re; ++j)
+              op.accumulate(st, sval[j], Op::kNarr > 1 ? saux[j] : T(0), Op::kNeedCol ? scol[j] : 0);
+          op.end_row(st, r);
+          for (int j = rs; j < re; ++j)
+            sval[j] = op.edge(st, sval[j], Op::kNarr > 1 ? saux[j] : T(0), Op::kNeedCol ? scol[j] : 0);
+        }
+      }
+      asm volatile("bar.sync 1, 256;" ::: "memory");  // whole tile's results are in shared memory
+      if (perm == nullptr) {
+        for (int j = e0 + tid; j < e1; j += kThreads) out[j] = sval[j];
+      } else {
+        for (int j = e0 + tid; j < e1; j += kThreads) out[__ldg(perm + j)] = sval[j];
+      }
+      // our in-place (generic-proxy) writes to the stage must be ordered before the TMA
+      // (async-proxy) refill that the producer issues once the stage is released
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      __syncwarp();
+      if ((tid & 31) == 0) mbar_arrive(empty + s);
+      if (++s == S) { s = 0; phase ^= 1u; }
+    }
+  }
+}
+
 }  // namespace glab

@@ -108,8 +108,18 @@ def amg_kernels(op_name, ei, ev, dt):
 
 def main():
     quick = "--quick" in sys.argv
+    only_amg = "--amg" in sys.argv
     dev = torch.device("cuda:0")
     torch.cuda.set_device(0)
+    if only_amg:
+        for dt in (torch.float32, torch.float64):
+            ei, ev = G.generators.constant_diffusion_fem(1.0, 0.01, 4096, dt, dev)
+            amg_kernels("D4096 anisotropic periodic FEM", ei, ev.contiguous(), dt)
+            del ei, ev
+            torch.cuda.empty_cache()
+        ei, ev = G.generators.laplacian_2d(4096, torch.float32, dev)
+        amg_kernels("L4096 5-pt Laplacian", ei, ev.contiguous(), torch.float32)
+        return
     NL = 2048 if quick else 4096
     ei, ev = G.generators.laplacian_2d(NL, torch.float64, dev)
     layer_kernels("L%d 5-pt Laplacian" % NL, ei, ev.float().contiguous(), torch.float32, ks=(1, 8))
