@@ -279,16 +279,18 @@ struct Tuning {
   int pipe;       // 1 = use the TMA pipeline kernel when the tile fits (default), 0 = never
   int stages;     // 0 = auto, else forced ring depth
   int ctas;       // 0 = auto (occupancy API), else forced CTAs per SM for the pipeline
+  int pdl;        // 1 = programmatic dependent launch between consecutive pipeline kernels
 };
 
 static const Tuning& tuning() {
   static Tuning t = [] {
-    Tuning v{1, 4096, 8, 1, 0, 0};
+    Tuning v{1, 4096, 8, 1, 0, 0, 1};
     if (const char* e = getenv("GLAB_RPT")) v.rpt = atoi(e) == 2 ? 2 : 1;
     if (const char* e = getenv("GLAB_CAP")) { int c = atoi(e); if (c >= 256 && c <= 8192) v.cap_max = c & ~31; }
     if (const char* e = getenv("GLAB_PIPE")) v.pipe = atoi(e) != 0;
     if (const char* e = getenv("GLAB_STAGES")) { int c = atoi(e); if (c >= 2 && c <= 8) v.stages = c; }
     if (const char* e = getenv("GLAB_CTAS")) { int c = atoi(e); if (c >= 1 && c <= 8) v.ctas = c; }
+    if (const char* e = getenv("GLAB_PDL")) v.pdl = atoi(e) != 0;
     if (const char* e = getenv("GLAB_PERSIST")) { int c = atoi(e); if (c >= 1 && c <= 16) v.persist = c; }
     return v;
   }();
@@ -324,6 +326,23 @@ static int launch_tiles(const glab_plan* p, const T* vals, const T* x, const Epi
 }
 
 constexpr int kNoPipe = -1000;
+
+// Launch with the programmatic-stream-serialization attribute (PDL) so that consecutive sweeps
+// overlap the next kernel's launch + prologue with the previous kernel's tail.
+template <typename Kern, typename... Args>
+static int launch_pdl(Kern kern, int grid, int block, size_t smem, cudaStream_t st, bool pdl, Args... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3((unsigned)grid);
+  cfg.blockDim = dim3((unsigned)block);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = pdl ? 1 : 0;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return (int)cudaLaunchKernelEx(&cfg, kern, args...);
+}
 static inline int round_up(int x, int m) { return (x + m - 1) / m * m; }
 template <typename T, int K, int U, class Epi>
 static int launch_pipe_halo(const glab_plan*, const T*, const T*, const Epi&, void*, const glab_halo_step*);
@@ -394,7 +413,7 @@ static int launch_pipe_halo(const glab_plan* p, const T* vals, const T* x, const
     max_smem = m;
   }
   if (2 * L.stage_bytes + 128 > max_smem) return GLAB_E_ARG;
-  int want_ctas = tuning().ctas ? tuning().ctas : ((K * (int)sizeof(T) <= 8) ? 4 : 2);
+  int want_ctas = tuning().ctas ? tuning().ctas : 4;  // measured: shallow rings + more CTAs win for wide k too
   int stages = tuning().stages ? tuning().stages : (max_smem / want_ctas - 128) / L.stage_bytes;
   if (stages > 4) stages = 4;
   while (stages > 2 && (size_t)stages * L.stage_bytes + 128 > (size_t)max_smem) --stages;
@@ -428,8 +447,7 @@ static int launch_pipe_halo(const glab_plan* p, const T* vals, const T* x, const
   if (grid > ntiles + 1) grid = ntiles + 1;
   if (grid < 1) grid = 1;
   TileArgs<T> a{p->rowptr, p->colidx, vals, 0, (int)n, (int)slots};
-  kern<<<grid, kPipeThreads, smem, as_stream(stream)>>>(a, x, epi, ntiles, L, h);
-  return (int)cudaGetLastError();
+  return launch_pdl(kern, grid, kPipeThreads, smem, as_stream(stream), tuning().pdl != 0, a, x, epi, ntiles, L, h);
 }
 
 // TMA pipeline launch.  Returns kNoPipe if the operator does not fit the pipeline (caller falls
@@ -468,7 +486,7 @@ static int launch_pipe_u(const glab_plan* p, const T* vals, const T* x, const Ep
   }
   if (2 * L.stage_bytes + 128 > max_smem) return kNoPipe;
   // ring depth: enough stages that (CTAs/SM x stages) keeps >= ~128 KB in flight per SM, within smem
-  int want_ctas = tuning().ctas ? tuning().ctas : ((K * (int)sizeof(T) <= 8) ? 4 : 2);
+  int want_ctas = tuning().ctas ? tuning().ctas : 4;  // measured: shallow rings + more CTAs win for wide k too
   int stages = tuning().stages;
   if (!stages) {
     stages = (max_smem / want_ctas - 128) / L.stage_bytes;
@@ -489,8 +507,8 @@ static int launch_pipe_u(const glab_plan* p, const T* vals, const T* x, const Ep
   if (grid > ntiles) grid = ntiles;
   if (grid < 1) grid = 1;
   TileArgs<T> a{p->rowptr, p->colidx, vals, (int)row_begin, (int)row_end, (int)slots};
-  kern<<<grid, kPipeThreads, smem, as_stream(stream)>>>(a, x, epi, ntiles, L, NoHalo{});
-  return (int)cudaGetLastError();
+  return launch_pdl(kern, grid, kPipeThreads, smem, as_stream(stream), tuning().pdl != 0, a, x, epi, ntiles, L,
+                    NoHalo{});
 }
 
 static int check_common(const glab_plan* p, const void* vals, const void* x, int64_t rb, int64_t re) {

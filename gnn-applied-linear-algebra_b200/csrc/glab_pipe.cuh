@@ -68,6 +68,14 @@ __device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, u
       : "memory");
 }
 
+// Programmatic dependent launch (PDL): a kernel launched with the programmatic-stream-
+// serialization attribute may start while its predecessor in the stream is still draining.
+// Everything it does before pdl_wait() must touch only data that no kernel of the sequence
+// writes (rowptr / barrier set-up); pdl_wait() returns once the predecessor grid has completed
+// and its writes are visible.  pdl_launch_dependents() lets the successor start early.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 // [p, p + n*esz) widened to 16-byte granules: returns aligned start, bytes (multiple of 16).
 __device__ __forceinline__ void align16(const void* p, int nbytes, const void*& start, uint32_t& bytes) {
   const uintptr_t p0 = reinterpret_cast<uintptr_t>(p);
@@ -152,9 +160,9 @@ k_row_pipe(TileArgs<T> a, const T* __restrict__ x, Epi epi, int ntiles, PipeLayo
     mbar_fence_init();
   }
   __syncthreads();
+  pdl_launch_dependents();
 
   typename Epi::State st;
-  epi.init(st);
 
   // logical tile -> (physical tile, reads-halo flag); boundary tiles come first
   auto phys = [&](int t, bool& boundary) -> int {
@@ -180,6 +188,8 @@ k_row_pipe(TileArgs<T> a, const T* __restrict__ x, Epi epi, int ntiles, PipeLayo
   }
 
   if (comm_cta) {
+    pdl_wait();
+    epi.init(st);
     if constexpr (HALO) {
       // ---------------------------------------------------------------- communication CTA
       const unsigned int nb = (unsigned int)(ntiles - h.int_tiles);
@@ -215,7 +225,10 @@ k_row_pipe(TileArgs<T> a, const T* __restrict__ x, Epi epi, int ntiles, PipeLayo
     }
   } else if (tid >= kThreads) {
     // ------------------------------------------------------------------ producer warp
-    if (tid == kThreads) {
+    if (tid != kThreads) {
+      pdl_wait();
+      epi.init(st);
+    } else {
       int lt = cta;
       int e0n = 0, e1n = 0;
       bool bnd = false, waited = false;
@@ -224,6 +237,8 @@ k_row_pipe(TileArgs<T> a, const T* __restrict__ x, Epi epi, int ntiles, PipeLayo
         e0n = __ldg(a.rowptr + r0);
         e1n = __ldg(a.rowptr + min(r0 + kThreads, a.row_end));
       }
+      pdl_wait();  // rowptr is constant; everything copied below may come from the previous kernel
+      epi.init(st);
       int s = 0;
       uint32_t phase = 0;
       for (; lt < ntiles; lt += ncta) {
@@ -286,6 +301,8 @@ k_row_pipe(TileArgs<T> a, const T* __restrict__ x, Epi epi, int ntiles, PipeLayo
     }
   } else {
     // ------------------------------------------------------------------ consumer warps
+    pdl_wait();
+    epi.init(st);
     int s = 0;
     uint32_t phase = 0;
     for (int lt = cta; lt < ntiles; lt += ncta) {
