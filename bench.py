@@ -59,9 +59,15 @@ class ClockSampler:
     """nvidia-smi clocks / throttle reasons DURING the timed region."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
          "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap,utilization.gpu")
 
     def __init__(self, gpu_index):
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        if vis:
+            try:
+                gpu_index = int(vis.split(",")[gpu_index])
+            except (ValueError, IndexError):
+                pass
         self.idx = gpu_index
         self.proc = None
         self.path = None
@@ -72,7 +78,7 @@ class ClockSampler:
             os.close(fd)
             self.proc = subprocess.Popen(
                 ["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
-                 "-lms", "100"], stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+                 "-lms", "50"], stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
         except Exception:
             self.proc = None
 
@@ -85,7 +91,7 @@ class ClockSampler:
             self.proc.wait(timeout=5)
         except Exception:
             self.proc.kill()
-        sm, mx, reasons = [], [], set()
+        sm, mx, reasons, loaded = [], [], set(), []
         try:
             for line in open(self.path):
                 f = [t.strip() for t in line.split(",")]
@@ -94,6 +100,8 @@ class ClockSampler:
                 try:
                     sm.append(float(f[1]))
                     mx.append(float(f[2]))
+                    if len(f) > 9 and float(f[9]) >= 50:
+                        loaded.append(float(f[1]))
                 except ValueError:
                     continue
                 for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
@@ -103,8 +111,9 @@ class ClockSampler:
         except Exception:
             pass
         if sm:
-            sm.sort()
-            out.update(sm_mhz=sm[len(sm) // 2], sm_max_mhz=max(mx), samples=len(sm), reasons=sorted(reasons))
+            use = sorted(loaded) if loaded else sorted(sm)
+            out.update(sm_mhz=use[len(use) // 2], sm_max_mhz=max(mx), samples=len(sm),
+                       samples_under_load=len(loaded), reasons=sorted(reasons))
         return out
 
 
@@ -234,12 +243,13 @@ def main_gpu(args):
         torch.cuda.synchronize()
 
     # ---------------- kernels only (value) + roofline of the dominant kernel
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()      # nvidia-smi needs ~0.3 s to start: begin before the warm-up,
+        time.sleep(0.5)      # samples then cover warm-up + both timed regions
     for _ in range(args.warmup):
         prob.step_kernels()
     barrier()
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     jac_events = []
     launches0 = rt.launch_count
@@ -317,7 +327,7 @@ def main_gpu(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="glab", choices=["glab", "reference"])
     ap.add_argument("--workload", default=os.environ.get("GLAB_BENCH_WORKLOAD", "L4096"), choices=sorted(GRID))

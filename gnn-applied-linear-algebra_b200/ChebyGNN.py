@@ -45,8 +45,7 @@ class ChebyRelaxGNN(torch.nn.Module):
         plan = rt.get_plan(edgeij_pair, n)
         vals = rt.get_vals(plan, edge_attr, 0, dt)
         va = io.up(vertex_attr, dt)
-        b = rt.dense(va[:, :k])
-        x0 = rt.dense(va[:, k:2 * k])
+        b, x0 = rt.unpack(va, [(0, k), (k, k)])
         rows, g_out = _recurrence(self.deg, g)
         table = torch.stack([torch.stack(r) for r in rows]).to(device=io.device, dtype=dt,
                                                                non_blocking=True).contiguous()
@@ -61,5 +60,5 @@ class ChebyRelaxGNN(torch.nn.Module):
             gathered = p
             p, p_alt = p_alt, p
         e_out = rt.with_messages(plan, vals, gathered)
-        v_out = torch.cat([b, x, r, p], 1)
+        v_out = rt.pack([b, x, r, p])
         return io.down(v_out), io.down(e_out), g_out

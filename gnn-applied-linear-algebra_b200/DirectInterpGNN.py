@@ -20,5 +20,6 @@ class DirectInterpGNN(torch.nn.Module):
         vals = rt.get_vals(plan, edge_attr, 0, dt)
         S = rt.get_vals(plan, edge_attr, 1, dt)
         va = io.up(vertex_attr, dt)
-        w = rt.direct_interp(plan, vals, S, rt.column(va, 0), rt.column(va, 1))
+        diag, cflag = rt.unpack(va, [(0, 1), (1, 1)])
+        w = rt.direct_interp(plan, vals, S, diag.view(-1), cflag.view(-1))
         return io.down(w)

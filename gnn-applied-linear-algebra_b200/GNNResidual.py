@@ -17,6 +17,5 @@ class GNNResidual(torch.nn.Module):
         plan = rt.get_plan(edgeij_pair, n)
         vals = rt.get_vals(plan, edge_attr, 0, dt)
         va = io.up(vertex_attr, dt)
-        b = rt.dense(va[:, :k])
-        x = rt.dense(va[:, k:2 * k])
+        b, x = rt.unpack(va, [(0, k), (k, k)])
         return io.down(rt.residual(plan, vals, x, b))

@@ -19,9 +19,8 @@ class JacobiGNN(torch.nn.Module):
         plan = rt.get_plan(edgeij_pair, n)
         vals = rt.get_vals(plan, edge_attr, 0, dt)
         va = io.up(vertex_attr, dt)
-        diag = rt.column(va, 0)
-        b = rt.dense(va[:, 1:1 + k])
-        x = rt.dense(va[:, 1 + k:1 + 2 * k])
+        diag, b, x = rt.unpack(va, [(0, 1), (1, k), (1 + k, k)])
+        diag = diag.view(-1)
         w = rt.scalar(g[0] if isinstance(g, torch.Tensor) else g, io.device, dt)
         return io, dt, plan, vals, va, diag, b, x, w
 
@@ -29,7 +28,7 @@ class JacobiGNN(torch.nn.Module):
         io, dt, plan, vals, va, diag, b, x, w = self._setup(vertex_attr, edgeij_pair, edge_attr, g)
         x_new = rt.jacobi(plan, vals, diag, b, x, torch.empty_like(x), w)
         e_out = rt.with_messages(plan, vals, x)
-        v_out = torch.cat([diag.view(-1, 1), b, x_new], 1)
+        v_out = rt.pack([diag, b, x_new])
         return io.down(v_out), io.down(e_out), g
 
     def forward(self, n_iters, vertex_attr, edgeij_pair, edge_attr, g, batch=None):

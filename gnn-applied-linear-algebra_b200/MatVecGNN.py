@@ -49,7 +49,7 @@ class EdgeUpdate(torch.nn.Module):
         xd = rt.dense(io.up(x, dt))
         y = rt.spmm(plan, vals, xd)
         e_out = rt.with_messages(plan, vals, xd)
-        return io.down(torch.cat([xd, y], 1)), io.down(e_out), u
+        return io.down(rt.pack([xd, y])), io.down(e_out), u
 
 
 class VertexUpdate(torch.nn.Module):

@@ -23,7 +23,7 @@ class PowerMethodGNN(torch.nn.Module):
         plan = rt.get_plan(edgeij_pair, n)
         vals = rt.get_vals(plan, edge_attr, 0, dt)
         va = io.up(vertex_attr, dt)
-        cur = rt.column(va, 0)
+        cur = rt.unpack(va, [(0, 1)])[0].view(-1)
         nxt = torch.empty_like(cur)
         sums = torch.zeros(2 * (self.num_iter + 2), dtype=torch.float64, device=io.device)
         ss_prev = None
@@ -40,5 +40,5 @@ class PowerMethodGNN(torch.nn.Module):
         norm = torch.sqrt(ss_prev[0]) if ss_prev is not None else g_dev[0]
         g_out = torch.stack([norm, ray[0], ray[0] / ray[1]]).to(g.dtype if g.dtype.is_floating_point else dt)
         e_out = rt.with_messages(plan, vals, b_out)
-        v_out = torch.stack([b_out, y_out], 1)
+        v_out = rt.pack([b_out, y_out])
         return io.down(v_out), io.down(e_out), io.down(g_out)

@@ -54,8 +54,8 @@ _sig("glab_ipc_free", c_int, P)
 
 
 class PushDesc(ctypes.Structure):
-    _fields_ = [("send_idx", c_void_p), ("count", c_int64), ("dst", c_void_p), ("dst_offset", c_int64),
-                ("flag", c_void_p)]
+    _fields_ = [("send_idx", c_void_p), ("first_row", c_int64), ("count", c_int64), ("dst", c_void_p),
+                ("dst_offset", c_int64), ("flag", c_void_p)]
 
 
 class HaloStep(ctypes.Structure):
@@ -90,6 +90,8 @@ for _suf, _ct in (("f32", c_float), ("f64", c_double)):
     _sig("glab_cheby_next_halo_" + _suf, c_int, P, P, P, P, P, P, P, P, P, _INT, _H, P)
     _sig("glab_power_step_halo_" + _suf, c_int, P, P, P, P, P, P, P, _H, P)
     _sig("glab_rayleigh_halo_" + _suf, c_int, P, P, P, P, P, P, P, P, _H, P)
+    _sig("glab_pack_" + _suf, c_int, _I64, _I64, _INT, POINTER(c_void_p), POINTER(c_int32), POINTER(c_int32), P, P)
+    _sig("glab_unpack_" + _suf, c_int, _I64, _I64, _INT, POINTER(c_void_p), POINTER(c_int32), POINTER(c_int32), P, P)
     _sig("glab_segment_sum_" + _suf, c_int, P, P, _INT, P, P)
     _sig("glab_segment_max_" + _suf, c_int, P, P, P, P)
     _sig("glab_soc_classic_" + _suf, c_int, P, P, _ct, P, P, P)

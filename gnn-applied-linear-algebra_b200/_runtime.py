@@ -395,6 +395,42 @@ def with_messages(plan, vals, x, A_col=None):
     return out
 
 
+def pack(parts):
+    """torch.cat(parts, 1) for dense [n, w_j] device tensors, as one coalesced kernel."""
+    n = parts[0].shape[0]
+    dt, dev = parts[0].dtype, parts[0].device
+    parts = [p_.view(n, -1) for p_ in parts]
+    widths = [p_.shape[1] for p_ in parts]
+    ld = sum(widths)
+    out = torch.empty((n, ld), dtype=dt, device=dev)
+    if len(parts) > 8 or ld > 64:
+        return torch.cat(parts, 1)
+    ptrs = (ctypes.c_void_p * len(parts))(*[p_.data_ptr() for p_ in parts])
+    w = (ctypes.c_int32 * len(parts))(*widths)
+    offs, acc = [], 0
+    for x_ in widths:
+        offs.append(acc)
+        acc += x_
+    o = (ctypes.c_int32 * len(parts))(*offs)
+    _call("pack", dt, dev, n, ld, len(parts), ptrs, w, o, ptr(out), stream_ptr())
+    return out
+
+
+def unpack(src, spans):
+    """Dense copies of column blocks of an interleaved [n, F] device tensor: spans = [(offset,
+    width), ...] -> list of [n, width] tensors (one coalesced kernel instead of strided copies)."""
+    n, ld = src.shape
+    if len(spans) > 8 or ld > 64:
+        return [dense(src[:, o:o + w]) for o, w in spans]
+    src = src.contiguous()
+    outs = [torch.empty((n, w), dtype=src.dtype, device=src.device) for _, w in spans]
+    ptrs = (ctypes.c_void_p * len(spans))(*[t.data_ptr() for t in outs])
+    w = (ctypes.c_int32 * len(spans))(*[w_ for _, w_ in spans])
+    o = (ctypes.c_int32 * len(spans))(*[o_ for o_, _ in spans])
+    _call("unpack", src.dtype, src.device, n, ld, len(spans), ptrs, w, o, ptr(src), stream_ptr())
+    return outs
+
+
 def segment_sum(plan, src_slots, out=None):
     k = _k_of(src_slots)
     if out is None:

@@ -135,6 +135,45 @@ __device__ __forceinline__ int stage_to_smem(const E* __restrict__ g, int e_begi
   return lead / (int)sizeof(E);
 }
 
+// Copy this rank's boundary rows of `src` ([*, K]) into a neighbour's halo tail through the
+// peer-mapped pointer of `d`, cooperatively by `nthreads` threads.  Contiguous send blocks go as
+// 16-byte vectors with 4 independent loads in flight per thread; arbitrary row lists gather
+// through send_idx.  L2-coherent loads: the rows were just written by other SMs of this GPU.
+template <typename T, int K>
+__device__ __forceinline__ void push_rows(const T* __restrict__ src, const glab_push_desc& d, int tid,
+                                          int nthreads) {
+  T* __restrict__ dst = reinterpret_cast<T*>(d.dst) + (size_t)d.dst_offset * K;
+  if (d.first_row >= 0) {
+    const T* __restrict__ s = src + (size_t)d.first_row * K;
+    const int64_t total = d.count * K;
+    constexpr int per = 16 / (int)sizeof(T);
+    if ((reinterpret_cast<uintptr_t>(s) & 15) == 0 && (reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
+      const int64_t nvec = total / per;
+      const int4* sv = reinterpret_cast<const int4*>(s);
+      int4* dv = reinterpret_cast<int4*>(dst);
+      int64_t i = tid;
+      for (; i + 3 * (int64_t)nthreads < nvec; i += 4 * (int64_t)nthreads) {
+        const int4 a0 = __ldcg(sv + i), a1 = __ldcg(sv + i + nthreads), a2 = __ldcg(sv + i + 2 * nthreads),
+                   a3 = __ldcg(sv + i + 3 * nthreads);
+        dv[i] = a0;
+        dv[i + nthreads] = a1;
+        dv[i + 2 * nthreads] = a2;
+        dv[i + 3 * nthreads] = a3;
+      }
+      for (; i < nvec; i += nthreads) dv[i] = __ldcg(sv + i);
+      for (int64_t j = nvec * per + tid; j < total; j += nthreads) dst[j] = __ldcg(s + j);
+    } else {
+      for (int64_t j = tid; j < total; j += nthreads) dst[j] = __ldcg(s + j);
+    }
+    return;
+  }
+  for (int64_t i = tid; i < d.count; i += nthreads) {
+    const size_t r = (size_t)__ldg(d.send_idx + i);
+#pragma unroll
+    for (int c = 0; c < K; ++c) dst[(size_t)i * K + c] = __ldcg(src + r * K + c);
+  }
+}
+
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

@@ -21,13 +21,7 @@ __global__ void k_halo_push(const T* __restrict__ src, PushArgs a, unsigned int*
                             uint32_t* pushed_local) {
   if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0 && pushed_local) *pushed_local += 1u;
   const glab_push_desc d = a.d[blockIdx.y];
-  T* __restrict__ dst = reinterpret_cast<T*>(d.dst);
-  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < d.count;
-       i += (int64_t)gridDim.x * blockDim.x) {
-    T v[K];
-    load_vec_rw<T, K>(v, src + (size_t)d.send_idx[i] * K);
-    store_vec<T, K>(dst + (size_t)(d.dst_offset + i) * K, v);
-  }
+  push_rows<T, K>(src, d, (int)(blockIdx.x * blockDim.x + threadIdx.x), (int)(gridDim.x * blockDim.x));
   if (d.flag == nullptr) return;
   // the last CTA of this peer's slice publishes the arrival after all stores are visible
   __threadfence_system();
@@ -83,7 +77,8 @@ static int halo_push(const T* src, int k, int n_peers, const glab_push_desc* des
   int64_t mx = 1;
   for (int q = 0; q < n_peers; ++q) {
     a.d[q] = descs[q];
-    if (descs[q].count < 0 || (descs[q].count > 0 && (!descs[q].send_idx || !descs[q].dst))) return GLAB_E_ARG;
+    if (descs[q].count < 0 || (descs[q].count > 0 && ((!descs[q].send_idx && descs[q].first_row < 0) || !descs[q].dst)))
+      return GLAB_E_ARG;
     if (descs[q].count > mx) mx = descs[q].count;
   }
   unsigned int* ctr = done_counters();

@@ -436,7 +436,7 @@ static int launch_pipe_halo(const glab_plan* p, const T* vals, const T* x, const
   for (int i = 0; i < GLAB_MAX_PEERS; ++i) {
     h.wait_flag[i] = i < hs->n_wait ? hs->wait_flags[i] : nullptr;
     if (i < hs->n_push) h.push[i] = hs->push[i];
-    else h.push[i] = glab_push_desc{nullptr, 0, nullptr, 0, nullptr};
+    else h.push[i] = glab_push_desc{nullptr, -1, 0, nullptr, 0, nullptr};
   }
   h.wait_target = hs->wait_target;
   h.pushed_counter = hs->pushed_counter;

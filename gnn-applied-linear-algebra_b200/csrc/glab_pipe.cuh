@@ -204,17 +204,8 @@ k_row_pipe(TileArgs<T> a, const T* __restrict__ x, Epi epi, int ntiles, PipeLayo
       __syncthreads();
       __threadfence();
       const T* src = reinterpret_cast<const T*>(h.push_src);
-      for (int q = 0; q < h.n_push; ++q) {
-        const glab_push_desc d = h.push[q];
-        T* dst = reinterpret_cast<T*>(d.dst);
-        for (int64_t i = tid; i < d.count; i += kPipeThreads) {
-          T v[K];
-          load_vec_cg<T, K>(v, src + (size_t)d.send_idx[i] * K);
-          store_vec<T, K>(dst + (size_t)(d.dst_offset + i) * K, v);
-        }
-      }
-      __threadfence_system();
-      __syncthreads();
+      for (int q = 0; q < h.n_push; ++q) push_rows<T, K>(src, h.push[q], tid, kPipeThreads);
+      __syncthreads();  // the release below is cumulative over every thread's peer stores
       if (tid == 0) {
         for (int q = 0; q < h.n_push; ++q)
           if (h.push[q].flag)

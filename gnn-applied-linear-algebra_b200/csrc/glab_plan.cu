@@ -105,6 +105,70 @@ __global__ void k_scatter_edges(const T* __restrict__ in, const int32_t* __restr
   }
 }
 
+// ---- interleaved [n, ld] <-> dense column blocks (layout glue of the drop-in API) ------------
+template <typename T> struct PackArgs {
+  T* part[GLAB_MAX_PARTS];
+  int width[GLAB_MAX_PARTS];
+  int offset[GLAB_MAX_PARTS];
+  int n_parts;
+};
+
+// One CTA moves a tile of 256 rows through shared memory so that both sides are coalesced:
+// the interleaved side is one contiguous run of 256*ld elements, each dense part a run of 256*w.
+template <typename T, bool Pack>
+__global__ void __launch_bounds__(256) k_pack(PackArgs<T> a, int64_t n, int ld, T* __restrict__ inter) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  T* tile = reinterpret_cast<T*>(smem_raw);  // [256][ld]
+  const int64_t r0 = (int64_t)blockIdx.x * 256;
+  const int rows = (int)min((int64_t)256, n - r0);
+  const int total = rows * ld;
+  if (Pack) {
+    for (int j = 0; j < a.n_parts; ++j) {
+      const int w = a.width[j], off = a.offset[j];
+      const T* __restrict__ src = a.part[j] + r0 * w;
+      for (int i = threadIdx.x; i < rows * w; i += 256) tile[(i / w) * ld + off + (i % w)] = src[i];
+    }
+    __syncthreads();
+    T* dst = inter + r0 * ld;
+    for (int i = threadIdx.x; i < total; i += 256) dst[i] = tile[i];
+  } else {
+    const T* __restrict__ src = inter + r0 * ld;
+    for (int i = threadIdx.x; i < total; i += 256) tile[i] = src[i];
+    __syncthreads();
+    for (int j = 0; j < a.n_parts; ++j) {
+      const int w = a.width[j], off = a.offset[j];
+      T* dst = a.part[j] + r0 * w;
+      for (int i = threadIdx.x; i < rows * w; i += 256) dst[i] = tile[(i / w) * ld + off + (i % w)];
+    }
+  }
+}
+
+template <typename T, bool Pack>
+static int pack_launch(int64_t n, int64_t ld, int n_parts, T* const* parts, const int32_t* widths,
+                       const int32_t* offsets, T* inter, void* stream) {
+  if (n < 0 || ld < 1 || ld > 64 || n_parts < 0 || n_parts > GLAB_MAX_PARTS) return GLAB_E_ARG;
+  if (n == 0 || n_parts == 0) return 0;
+  if (!parts || !widths || !offsets || !inter) return GLAB_E_ARG;
+  PackArgs<T> a;
+  a.n_parts = n_parts;
+  for (int j = 0; j < n_parts; ++j) {
+    if (!parts[j] || widths[j] < 1 || offsets[j] < 0 || offsets[j] + widths[j] > ld) return GLAB_E_ARG;
+    a.part[j] = parts[j];
+    a.width[j] = widths[j];
+    a.offset[j] = offsets[j];
+  }
+  const int64_t blocks = (n + 255) / 256;
+  if (blocks > INT32_MAX) return GLAB_E_RANGE;
+  const size_t smem = (size_t)256 * ld * sizeof(T);
+  auto kern = k_pack<T, Pack>;
+  if (smem > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+  }
+  kern<<<(unsigned)blocks, 256, smem, as_stream(stream)>>>(a, n, (int)ld, inter);
+  return (int)cudaGetLastError();
+}
+
 static int grid_for(int64_t n, int sm_count) {
   int64_t b = (n + 255) / 256;
   int64_t cap = (int64_t)sm_count * 16;
@@ -331,3 +395,20 @@ extern "C" int glab_scatter_edges_f32(const glab_plan* p, const float* in, float
                                       int64_t c, void* s) { return scatter_edges<float>(p, in, out, ld, c, s); }
 extern "C" int glab_scatter_edges_f64(const glab_plan* p, const double* in, double* out, int64_t ld,
                                       int64_t c, void* s) { return scatter_edges<double>(p, in, out, ld, c, s); }
+
+extern "C" int glab_pack_f32(int64_t n, int64_t ld, int np, const float* const* parts, const int32_t* w,
+                             const int32_t* o, float* dst, void* s) {
+  return pack_launch<float, true>(n, ld, np, const_cast<float* const*>(parts), w, o, dst, s);
+}
+extern "C" int glab_pack_f64(int64_t n, int64_t ld, int np, const double* const* parts, const int32_t* w,
+                             const int32_t* o, double* dst, void* s) {
+  return pack_launch<double, true>(n, ld, np, const_cast<double* const*>(parts), w, o, dst, s);
+}
+extern "C" int glab_unpack_f32(int64_t n, int64_t ld, int np, float* const* parts, const int32_t* w,
+                               const int32_t* o, const float* src, void* s) {
+  return pack_launch<float, false>(n, ld, np, parts, w, o, const_cast<float*>(src), s);
+}
+extern "C" int glab_unpack_f64(int64_t n, int64_t ld, int np, double* const* parts, const int32_t* w,
+                               const int32_t* o, const double* src, void* s) {
+  return pack_launch<double, false>(n, ld, np, parts, w, o, const_cast<double*>(src), s);
+}

@@ -229,11 +229,19 @@ class PeerHalo:
         self._suf = rt.suffix(dtype)
         self._push_desc, self._wait_args = {}, {}
         nw = len(names) * world
+        # contiguous send blocks (every stencil slab) are copied without index loads
+        self._first_row = {}
+        for q in halo.peers_send:
+            idx = halo.send_rows[q].long()
+            first = int(idx[0].item())
+            contiguous = bool(torch.equal(idx, torch.arange(first, first + idx.numel(), device=idx.device)))
+            self._first_row[q] = first if contiguous else -1
         for nm in names:
             descs = (PushDesc * max(len(halo.peers_send), 1))()
             for i, q in enumerate(halo.peers_send):
                 idx = halo.send_rows[q]
                 descs[i].send_idx = idx.data_ptr()
+                descs[i].first_row = self._first_row[q]
                 descs[i].count = idx.numel()
                 descs[i].dst = self.bufs[nm].peer_ptr[q]
                 descs[i].dst_offset = peer_n_local[q] + offs[q][self.rank]

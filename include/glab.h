@@ -202,6 +202,22 @@ int glab_edge_attr_f32(const glab_plan*, const float* vals, const float* x, int 
 int glab_edge_attr_f64(const glab_plan*, const double* vals, const double* x, int k, double* out_edges,
                        int64_t ld, void* stream);
 
+/* Layout glue of the drop-in API: the reference's layers take and return INTERLEAVED attribute
+ * tensors (vertex_attr [n, F] = cat([A_ii, b, x], 1) ..., JacobiGNN.py:121, ChebyGNN.py:163,243,
+ * PowerMethodGNN.py:126), the kernels work on dense column blocks.
+ *   pack:   dst[i, off_j .. off_j + w_j) = src_j[i, 0..w_j)   for j < n_parts (dst is [n, ld])
+ *   unpack: dst_j[i, 0..w_j) = src[i, off_j .. off_j + w_j)   (src is [n, ld])
+ * parts / widths / offsets are HOST arrays (n_parts <= 8), copied at launch. */
+#define GLAB_MAX_PARTS 8
+int glab_pack_f32(int64_t n, int64_t ld, int n_parts, const float* const* parts, const int32_t* widths,
+                  const int32_t* offsets, float* dst, void* stream);
+int glab_pack_f64(int64_t n, int64_t ld, int n_parts, const double* const* parts, const int32_t* widths,
+                  const int32_t* offsets, double* dst, void* stream);
+int glab_unpack_f32(int64_t n, int64_t ld, int n_parts, float* const* parts, const int32_t* widths,
+                    const int32_t* offsets, const float* src, void* stream);
+int glab_unpack_f64(int64_t n, int64_t ld, int n_parts, double* const* parts, const int32_t* widths,
+                    const int32_t* offsets, const double* src, void* stream);
+
 /* ------------------------------------------------------------------------------------------
  * AMG setup kernels (row-local, one pass).  Per-edge outputs are written in the caller's
  * ORIGINAL edge order (out[perm[slot]]).
@@ -255,6 +271,8 @@ int glab_ipc_free(void* dev_ptr);
 #define GLAB_MAX_PEERS 8
 typedef struct glab_push_desc {
   const int32_t* send_idx;   /* device: local row ids to send to this peer        */
+  int64_t first_row;         /* >= 0: send_idx[i] == first_row + i for all i (contiguous block:
+                                copied with 16-byte vectors, no index loads); -1: use send_idx */
   int64_t count;
   void* dst;                 /* peer-mapped base of the destination vector        */
   int64_t dst_offset;        /* first destination row (the peer's halo tail slot) */

@@ -389,3 +389,33 @@ def test_large_operator_properties(G, dev, dt):
         bk = bk / bk.norm()
     lam = ((bk * (A @ bk)).sum() / (bk * bk).sum()).item()
     assert abs(g1[2].item() - lam) <= TOL[dt] * abs(lam)
+
+
+def test_vcycle_multi_rhs_and_large_grid(G, dev):
+    """Config-5 extension: 8 right-hand sides at once == the reference cycle run per column
+    (oracle), and a grid far beyond the reference's dense-P limit still contracts the residual."""
+    V = G.VCycle
+    N, k = 12, 8
+    n = N * N
+    torch.manual_seed(24601)
+    ei, ev = G.UtilsGNN.laplacianfun_torch(N, device=dev)
+    A = torch.sparse_coo_tensor(ei, ev.flatten(), dtype=torch.float)
+    b, x = torch.rand(n, k), torch.rand(n, k)
+    xo = V.runVCycle(A, b.to(dev), x.to(dev), 3, 3, 5, True).cpu()
+    split = torch.zeros(n)
+    split[0::2] = 1
+    oi, ov = port.laplacian_2d(N)
+    for c in range(k):
+        ref = port.two_grid_vcycle(oi, ov, b[:, c:c + 1], x[:, c:c + 1], split)
+        assert relerr(xo[:, c:c + 1], ref) <= 1e-5
+    N = 384
+    n = N * N
+    ei, ev = G.UtilsGNN.laplacianfun_torch(N, device=dev)
+    A = torch.sparse_coo_tensor(ei, ev.flatten(), dtype=torch.float)
+    b = torch.rand(n, k, device=dev)
+    x = torch.zeros(n, k, device=dev)
+    norms = [torch.norm(V.runResidual(A, b, x)).item()]
+    for _ in range(3):
+        x = V.runVCycle(A, b, x, 3, 3, 5, True)
+        norms.append(torch.norm(V.runResidual(A, b, x)).item())
+    assert all(b_ < a_ for a_, b_ in zip(norms, norms[1:])), norms
