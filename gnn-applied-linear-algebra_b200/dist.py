@@ -90,6 +90,29 @@ class HaloPlan:
             send_rows.append((wanted - r0).to(torch.int32).to(dev))
         return cls(part, rank, halo_cols, recv_counts, send_rows)
 
+    @classmethod
+    def build_all(cls, part, global_cols_per_rank):
+        """Single-process construction of every rank's plan (emulation / tests: all row blocks
+        live in one process, so the request lists are exchanged by plain assignment)."""
+        need_all, halo_all, counts_all = [], [], []
+        for rank, gcols in enumerate(global_cols_per_rank):
+            r0, r1 = part.bounds(rank)
+            outside = (gcols < r0) | (gcols >= r1)
+            halo_cols = torch.unique(gcols[outside])
+            owners = part.owner(halo_cols)
+            counts_all.append(torch.bincount(owners, minlength=part.world).tolist())
+            need_all.append([halo_cols[owners == q].cpu() for q in range(part.world)])
+            halo_all.append(halo_cols)
+        plans = []
+        for rank, gcols in enumerate(global_cols_per_rank):
+            r0, _ = part.bounds(rank)
+            send_rows = []
+            for q in range(part.world):
+                wanted = need_all[q][rank] if q != rank else torch.empty(0, dtype=torch.int64)
+                send_rows.append((wanted - r0).to(torch.int32).to(gcols.device))
+            plans.append(cls(part, rank, halo_all[rank], counts_all[rank], send_rows))
+        return plans
+
     def local_columns(self, global_cols):
         """Global -> local column numbering (local block first, halo tail after)."""
         r0, r1 = self.r0, self.r1

@@ -419,3 +419,108 @@ def test_vcycle_multi_rhs_and_large_grid(G, dev):
         x = V.runVCycle(A, b, x, 3, 3, 5, True)
         norms.append(torch.norm(V.runResidual(A, b, x)).item())
     assert all(b_ < a_ for a_, b_ in zip(norms, norms[1:])), norms
+
+
+@pytest.mark.parametrize("dt", [torch.float32, torch.float64])
+def test_fused_halo_step_two_ranks_emulated_on_one_gpu(G, dev, dt):
+    """The multi-GPU data path (glab_halo_push, the fused glab_jacobi_halo / glab_cheby_*_halo
+    kernels with in-kernel acquire + communication CTA) exercised on ONE GPU: two row blocks of
+    the operator live in the same process and their kernels run one after the other on one
+    stream, each storing its boundary rows into the other block's halo tail exactly as it would
+    through an NVLink peer mapping.  Results must equal the unpartitioned sweeps bit for bit."""
+    from glab_b200 import dist as gd
+    from glab_b200._lib import HaloStep, PushDesc
+    rt = G.runtime
+    N, world, sweeps = 80, 2, 4
+    n = N * N
+    ei, ev = G.generators.heat_fem_2d((N + 1, N + 1), (1.0, 2.0), torch.float64, dev)
+    ev = ev.to(dt).contiguous()
+    torch.manual_seed(24601)
+    b = torch.rand(n, 1, dtype=dt, device=dev)
+    x0 = torch.rand(n, 1, dtype=dt, device=dev)
+    diag = G.generators.diagonal_of(ei, ev, n).reshape(-1).contiguous()
+    w = torch.tensor([0.7], dtype=dt, device=dev)
+    plan = G.get_plan(ei, n)
+    vals = rt.get_vals(plan, ev)
+    xa, xb = x0.clone(), torch.empty_like(x0)
+    for _ in range(sweeps):
+        rt.jacobi(plan, vals, diag, b, xa, xb, w)
+        xa, xb = xb, xa
+    ref = xa
+
+    part = gd.RowPartition(n, world, align=256)
+    blocks = []
+    for r in range(world):
+        r0, r1 = part.bounds(r)
+        mine = (ei[0] >= r0) & (ei[0] < r1)
+        blocks.append((ei[0][mine] - r0, ei[1][mine], ev[mine].contiguous()))
+    halos = gd.HaloPlan.build_all(part, [blk[1] for blk in blocks])
+    ops = []
+    for r in range(world):
+        rows, gcols, v = blocks[r]
+        h = halos[r]
+        lei = torch.stack([rows, h.local_columns(gcols)]).contiguous()
+        p = G.Plan.from_coo(lei, h.n_local, h.n_local + h.n_halo)
+        lo, hi = h.interior_rows(lei[0], lei[1])
+        vec = [torch.zeros(h.n_local + h.n_halo, 1, dtype=dt, device=dev) for _ in range(2)]
+        flags = torch.zeros(64, dtype=torch.int32, device=dev)     # 16-byte spaced words
+        ops.append(dict(plan=p, vals=rt.get_vals(p, v), halo=h, vec=vec, flags=flags, lo=lo, hi=hi, keep=lei))
+    for r in range(world):
+        r0, r1 = part.bounds(r)
+        ops[r]["vec"][0][:r1 - r0].copy_(x0[r0:r1])
+
+    def word(t, i):
+        return t.data_ptr() + 16 * i
+
+    # per (rank, vector) flag words: arrival from the other rank = word v, pushed = word 2 + v, done = word 7
+    def push_descs(r, v):
+        h = ops[r]["halo"]
+        descs = (PushDesc * max(len(h.peers_send), 1))()
+        for i, q in enumerate(h.peers_send):
+            idx = h.send_rows[q]
+            first = int(idx[0].item())
+            descs[i].send_idx = idx.data_ptr()
+            descs[i].first_row = first if torch.equal(idx.long(), torch.arange(first, first + idx.numel(), device=dev)) else -1
+            descs[i].count = idx.numel()
+            descs[i].dst = ops[q]["vec"][v].data_ptr()
+            descs[i].dst_offset = ops[q]["halo"].n_local + ops[q]["halo"].recv_offsets[r]
+            descs[i].flag = word(ops[q]["flags"], v)
+        return descs
+
+    keep = []
+    # initial publication of vector 0 with the stand-alone push kernel
+    for r in range(world):
+        d = push_descs(r, 0)
+        keep.append(d)
+        rt._call("halo_push", dt, dev, rt.ptr(ops[r]["vec"][0]), 1, len(ops[r]["halo"].peers_send), d,
+                 ctypes.c_void_p(word(ops[r]["flags"], 2)), rt.stream_ptr())
+    cur = 0
+    for _ in range(sweeps):
+        nxt = 1 - cur
+        for r in range(world):
+            o = ops[r]
+            h = o["halo"]
+            r0, r1 = part.bounds(r)
+            st = HaloStep()
+            st.interior_begin, st.interior_end = o["lo"], o["hi"]
+            fl = (ctypes.c_void_p * 1)(word(o["flags"], cur))
+            st.n_wait = len(h.peers_recv)
+            st.wait_flags = fl
+            st.wait_target = word(o["flags"], 2 + cur)
+            d = push_descs(r, nxt)
+            st.n_push = len(h.peers_send)
+            st.push = d
+            st.pushed_counter = word(o["flags"], 2 + nxt)
+            st.push_src = o["vec"][nxt].data_ptr()
+            st.done_counter = word(o["flags"], 7)
+            keep += [fl, d, st]
+            rt.jacobi(o["plan"], o["vals"], diag[r0:r1].contiguous(), b[r0:r1].contiguous(), o["vec"][cur],
+                      o["vec"][nxt], w, halo=st)
+        cur = nxt
+    torch.cuda.synchronize()
+    for r in range(world):
+        r0, r1 = part.bounds(r)
+        assert torch.equal(ops[r]["vec"][cur][:r1 - r0], ref[r0:r1]), r
+    # both arrival counters saw 1 stand-alone push + one push per sweep of each vector
+    f0 = ops[0]["flags"].view(-1, 4)[:, 0].tolist()
+    assert f0[0] + f0[1] == 1 + sweeps and f0[7] == 0
