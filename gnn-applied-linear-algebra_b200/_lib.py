@@ -94,6 +94,8 @@ for _suf, _ct in (("f32", c_float), ("f64", c_double)):
     _sig("glab_unpack_" + _suf, c_int, _I64, _I64, _INT, POINTER(c_void_p), POINTER(c_int32), POINTER(c_int32), P, P)
     _sig("glab_segment_sum_" + _suf, c_int, P, P, _INT, P, P)
     _sig("glab_segment_max_" + _suf, c_int, P, P, P, P)
+    _sig("glab_segment_min_" + _suf, c_int, P, P, P, P)
+    _sig("glab_segment_mean_" + _suf, c_int, P, P, _INT, P, P)
     _sig("glab_soc_classic_" + _suf, c_int, P, P, _ct, P, P, P)
     _sig("glab_soc_sa_" + _suf, c_int, P, P, P, P, P)
     _sig("glab_direct_interp_" + _suf, c_int, P, P, P, P, P, P, P)

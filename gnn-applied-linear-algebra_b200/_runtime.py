@@ -447,6 +447,49 @@ def segment_max(plan, src_slots, out=None):
     return out
 
 
+def segment_min(plan, src_slots, out=None):
+    if out is None:
+        out = torch.empty(plan.n_rows, dtype=src_slots.dtype, device=plan.device)
+    _call("segment_min", src_slots.dtype, plan.device, plan.handle, ptr(src_slots), ptr(out), stream_ptr())
+    return out
+
+
+def segment_mean(plan, src_slots, out=None):
+    k = _k_of(src_slots)
+    if out is None:
+        out = torch.empty((plan.n_rows,) + tuple(src_slots.shape[1:]), dtype=src_slots.dtype,
+                          device=plan.device)
+    _call("segment_mean", src_slots.dtype, plan.device, plan.handle, ptr(src_slots), k, ptr(out), stream_ptr())
+    return out
+
+
+def scatter(src, index, dim=0, dim_size=None, reduce="sum"):
+    """torch_scatter.scatter(src, index, dim=0, dim_size=n, reduce=sum|max|min|mean) on the GPU:
+    the reference's seam as a drop-in function (index = edgeij_pair[0])."""
+    if dim != 0:
+        raise GlabError("only dim=0 (aggregation over edges) is supported")
+    device = compute_device(src, index)
+    host = not src.is_cuda
+    idx = to_device(index, device)
+    n = int(dim_size) if dim_size is not None else (int(idx.max().item()) + 1 if idx.numel() else 0)
+    ei = torch.stack([idx, torch.zeros_like(idx)]).contiguous()
+    plan = Plan.from_coo(ei, n, 1)
+    s2 = to_device(src, device)
+    s2 = s2.view(-1, 1) if s2.dim() == 1 else s2
+    slots = torch.stack([get_vals(plan, s2, j) for j in range(s2.shape[1])], 1).contiguous()
+    if reduce in ("sum", "add"):
+        out = segment_sum(plan, slots)
+    elif reduce == "mean":
+        out = segment_mean(plan, slots)
+    elif reduce in ("max", "min"):
+        fn = segment_max if reduce == "max" else segment_min
+        out = torch.stack([fn(plan, slots[:, j].contiguous()) for j in range(slots.shape[1])], 1)
+    else:
+        raise GlabError("unknown reduce %r" % (reduce,))
+    out = out.view(-1) if src.dim() == 1 else out
+    return out.cpu() if host else out
+
+
 def soc_classic(plan, vals, theta, rowmax=None):
     S = torch.empty(plan.nnz, dtype=vals.dtype, device=plan.device)
     _call("soc_classic", vals.dtype, plan.device, plan.handle, ptr(vals), float(theta), ptr(S), ptr(rowmax),

@@ -186,7 +186,9 @@ static int edge_messages(const glab_plan* p, const T* vals, const T* x, int k, T
 }
 
 // The bare seam: out[i,:] = reduce over the row's slots of src[slot,:]  (scatter sum / max).
-template <typename T, int K, bool IsMax>
+// Mode: 0 = sum, 1 = max, 2 = min, 3 = mean (sum / max(count, 1)); empty rows give 0 in every
+// mode, like torch_scatter (the 4-way aggregation of TrainableJacobiGNN.py:65-68).
+template <typename T, int K, int Mode>
 __global__ void k_segment_reduce(const int32_t* __restrict__ rowptr, const T* __restrict__ src,
                                  int64_t n_rows, T* __restrict__ out) {
   for (int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; r < n_rows;
@@ -200,15 +202,21 @@ __global__ void k_segment_reduce(const int32_t* __restrict__ rowptr, const T* __
       load_vec<T, K>(v, src + (size_t)j * K);
 #pragma unroll
       for (int c = 0; c < K; ++c) {
-        if (IsMax) acc[c] = (j == rs || v[c] > acc[c] || v[c] != v[c]) ? v[c] : acc[c];
+        if (Mode == 1) acc[c] = (j == rs || v[c] > acc[c] || v[c] != v[c]) ? v[c] : acc[c];
+        else if (Mode == 2) acc[c] = (j == rs || v[c] < acc[c] || v[c] != v[c]) ? v[c] : acc[c];
         else acc[c] = acc[c] + v[c];
       }
+    }
+    if (Mode == 3) {
+      const T cnt = (T)(re - rs > 0 ? re - rs : 1);
+#pragma unroll
+      for (int c = 0; c < K; ++c) acc[c] = acc[c] / cnt;
     }
     store_vec<T, K>(out + (size_t)r * K, acc);
   }
 }
 
-template <typename T, bool IsMax>
+template <typename T, int Mode>
 static int segment_reduce(const glab_plan* p, const T* src, int k, T* out, void* stream) {
   if (!p || !out || (p->nnz > 0 && !src)) return GLAB_E_ARG;
   if (p->n_rows == 0) return 0;
@@ -217,10 +225,10 @@ static int segment_reduce(const glab_plan* p, const T* src, int k, T* out, void*
   const int grid = (int)(b < capb ? b : capb);
   cudaStream_t st = as_stream(stream);
   switch (k) {
-    case 1: k_segment_reduce<T, 1, IsMax><<<grid, 256, 0, st>>>(p->rowptr, src, p->n_rows, out); break;
-    case 2: k_segment_reduce<T, 2, IsMax><<<grid, 256, 0, st>>>(p->rowptr, src, p->n_rows, out); break;
-    case 4: k_segment_reduce<T, 4, IsMax><<<grid, 256, 0, st>>>(p->rowptr, src, p->n_rows, out); break;
-    case 8: k_segment_reduce<T, 8, IsMax><<<grid, 256, 0, st>>>(p->rowptr, src, p->n_rows, out); break;
+    case 1: k_segment_reduce<T, 1, Mode><<<grid, 256, 0, st>>>(p->rowptr, src, p->n_rows, out); break;
+    case 2: k_segment_reduce<T, 2, Mode><<<grid, 256, 0, st>>>(p->rowptr, src, p->n_rows, out); break;
+    case 4: k_segment_reduce<T, 4, Mode><<<grid, 256, 0, st>>>(p->rowptr, src, p->n_rows, out); break;
+    case 8: k_segment_reduce<T, 8, Mode><<<grid, 256, 0, st>>>(p->rowptr, src, p->n_rows, out); break;
     default: return GLAB_E_ARG;
   }
   return (int)cudaGetLastError();
@@ -258,10 +266,16 @@ using namespace glab;
 
 #define GLAB_SEG_INST(SUF, T)                                                                      \
   extern "C" int glab_segment_sum_##SUF(const glab_plan* p, const T* src, int k, T* out, void* s) { \
-    return segment_reduce<T, false>(p, src, k, out, s);                                            \
+    return segment_reduce<T, 0>(p, src, k, out, s);                                                \
   }                                                                                                \
   extern "C" int glab_segment_max_##SUF(const glab_plan* p, const T* src, T* out, void* s) {       \
-    return segment_reduce<T, true>(p, src, 1, out, s);                                             \
+    return segment_reduce<T, 1>(p, src, 1, out, s);                                                \
+  }                                                                                                \
+  extern "C" int glab_segment_min_##SUF(const glab_plan* p, const T* src, T* out, void* s) {       \
+    return segment_reduce<T, 2>(p, src, 1, out, s);                                                \
+  }                                                                                                \
+  extern "C" int glab_segment_mean_##SUF(const glab_plan* p, const T* src, int k, T* out, void* s) { \
+    return segment_reduce<T, 3>(p, src, k, out, s);                                                \
   }
 
 GLAB_SEG_INST(f32, float)

@@ -193,6 +193,12 @@ int glab_segment_sum_f32(const glab_plan*, const float* src_slots, int k, float*
 int glab_segment_sum_f64(const glab_plan*, const double* src_slots, int k, double* out, void* stream);
 int glab_segment_max_f32(const glab_plan*, const float* src_slots, float* out, void* stream);
 int glab_segment_max_f64(const glab_plan*, const double* src_slots, double* out, void* stream);
+/* reduce="min" / reduce="mean" (sum / max(count, 1)), the other two members of the 4-way
+ * aggregation of TrainableJacobiDiag/TrainableJacobiGNN.py:65-68; empty rows give 0. */
+int glab_segment_min_f32(const glab_plan*, const float* src_slots, float* out, void* stream);
+int glab_segment_min_f64(const glab_plan*, const double* src_slots, double* out, void* stream);
+int glab_segment_mean_f32(const glab_plan*, const float* src_slots, int k, float* out, void* stream);
+int glab_segment_mean_f64(const glab_plan*, const double* src_slots, int k, double* out, void* stream);
 
 /* out_edges[e, 0] = A_ij and out_edges[e, 1..k] = A_ij * x_j in ONE pass: the reference layers'
  * returned edge_attr = torch.cat([A_ij, c_ij], 1) (MatVecGNN.py:84, JacobiGNN.py:88,
