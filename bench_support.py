@@ -71,13 +71,42 @@ class SingleGpuSmoother:
         self.result = dst
         return ev
 
+    def _e2e_setup(self):
+        """Double-buffered staging so that consecutive steps overlap their PCIe copies with compute:
+        step i+1's H2D and step i-1's D2H run on copy streams while step i computes.  Every step
+        still uploads its own inputs from pinned host memory and downloads its own result."""
+        dev, n = self.dev, self.n
+        self.s_in, self.s_out = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+        self.va_dev = [torch.empty(n, 3, device=dev) for _ in range(2)]
+        self.res_dev = [torch.empty(n, 1, device=dev) for _ in range(2)]
+        self.out_hosts = [torch.empty(n, 1).pin_memory() for _ in range(2)]
+        self.ev_in = [torch.cuda.Event() for _ in range(2)]
+        self.ev_comp = [torch.cuda.Event() for _ in range(2)]
+        self.ev_out = [torch.cuda.Event() for _ in range(2)]
+        self.e2e_i = 0
+
     def step_e2e(self):
-        dev = self.dev
-        va = self.va_host.to(dev, non_blocking=True)
+        if not hasattr(self, "s_in"):
+            self._e2e_setup()
+        i = self.e2e_i % 2
+        self.e2e_i += 1
+        cur = torch.cuda.current_stream(self.dev)
+        with torch.cuda.stream(self.s_in):
+            self.s_in.wait_event(self.ev_comp[i])            # the step that last read this buffer is done
+            self.va_dev[i].copy_(self.va_host, non_blocking=True)   # H2D of this step's inputs
+            self.ev_in[i].record(self.s_in)
+        cur.wait_event(self.ev_in[i])
+        cur.wait_event(self.ev_out[i])                       # this result buffer has been downloaded
+        va = self.va_dev[i]
         x1 = self.jac(self.N_JACOBI, va, self.ei, self.ea2, self.gw)
-        v, e, g = self.cheb(torch.cat([va[:, 1:2], x1], 1), self.ei, self.ev, self.gc)
-        self.out_host.copy_(v[:, 1:2])          # D2H of the step's result (synchronous)
-        return self.out_host
+        v, e, g = self.cheb(self.rt.pack([va[:, 1:2].contiguous(), x1]), self.ei, self.ev, self.gc)
+        self.res_dev[i].copy_(v[:, 1:2])
+        self.ev_comp[i].record(cur)
+        with torch.cuda.stream(self.s_out):
+            self.s_out.wait_event(self.ev_comp[i])
+            self.out_hosts[i].copy_(self.res_dev[i], non_blocking=True)   # D2H of this step's result
+            self.ev_out[i].record(self.s_out)
+        return self.out_hosts[i]
 
 
 class PartitionedSmoother:

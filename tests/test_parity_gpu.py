@@ -524,3 +524,28 @@ def test_fused_halo_step_two_ranks_emulated_on_one_gpu(G, dev, dt):
     # both arrival counters saw 1 stand-alone push + one push per sweep of each vector
     f0 = ops[0]["flags"].view(-1, 4)[:, 0].tolist()
     assert f0[0] + f0[1] == 1 + sweeps and f0[7] == 0
+
+
+@pytest.mark.parametrize("dt", [torch.float32, torch.float64])
+def test_scatter_seam_four_way(G, dev, dt):
+    """The reference's seam as a function: torch_scatter.scatter(..., reduce=sum|max|min|mean)
+    (4-way aggregation of TrainableJacobiGNN.py:65-68) against the oracle's stand-in."""
+    import os
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle", "shim"))
+    import torch_scatter as ts
+    g = torch.Generator().manual_seed(5)
+    n, z = 97, 1200
+    idx = torch.randint(0, n, (z,), generator=g)
+    idx[idx == 11] = 12                        # an empty segment
+    src = (torch.rand(z, 2, generator=g, dtype=torch.float64) - 0.5).to(dt)
+    for red in ("sum", "max", "min", "mean"):
+        ref = ts.scatter(src, idx, dim=0, dim_size=n, reduce=red)
+        out = G.runtime.scatter(src.to(dev), idx.to(dev), dim=0, dim_size=n, reduce=red).cpu()
+        if red == "mean":
+            assert relerr(out, ref) <= TOL[dt]
+        else:
+            assert same(out, ref), red
+        assert torch.all(out[11] == 0)
+    out1 = G.runtime.scatter(src[:, 0].contiguous().to(dev), idx.to(dev), dim=0, dim_size=n, reduce="max").cpu()
+    assert same(out1, ts.scatter(src[:, 0].contiguous(), idx, dim=0, dim_size=n, reduce="max"))
