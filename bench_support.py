@@ -213,14 +213,44 @@ class PartitionedSmoother:
             self.op.chebyshev(self.CHEB_DEG, self.b, self.table, cur, self.x, self.r)
         return ev
 
+    def _e2e_setup(self):
+        dev, nl = self.dev, self.n_local
+        self.s_in, self.s_out = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+        self.b_stage = [torch.empty(nl, 1, device=dev) for _ in range(2)]
+        self.x_stage2 = [torch.empty(nl, 1, device=dev) for _ in range(2)]
+        self.res_dev = [torch.empty(nl, 1, device=dev) for _ in range(2)]
+        self.out_hosts = [torch.empty(nl, 1).pin_memory() for _ in range(2)]
+        self.ev_in = [torch.cuda.Event() for _ in range(2)]
+        self.ev_comp = [torch.cuda.Event() for _ in range(2)]
+        self.ev_out = [torch.cuda.Event() for _ in range(2)]
+        self.e2e_i = 0
+
     def step_e2e(self):
-        dev = self.dev
-        self.b.copy_(self.b_host, non_blocking=True)
-        self.x_stage.copy_(self.x_host, non_blocking=True)
-        self.op.vec["v0"][:self.n_local].copy_(self.x_stage)
+        """Per step: this rank's slab of b and x0 is uploaded from pinned host memory, the captured
+        smoothing pass runs, the slab of the result is downloaded; double-buffered staging lets the
+        copies of neighbouring steps overlap the compute."""
+        if not hasattr(self, "s_in"):
+            self._e2e_setup()
+        i = self.e2e_i % 2
+        self.e2e_i += 1
+        cur = torch.cuda.current_stream(self.dev)
+        with torch.cuda.stream(self.s_in):
+            self.s_in.wait_event(self.ev_comp[i])
+            self.b_stage[i].copy_(self.b_host, non_blocking=True)
+            self.x_stage2[i].copy_(self.x_host, non_blocking=True)
+            self.ev_in[i].record(self.s_in)
+        cur.wait_event(self.ev_in[i])
+        cur.wait_event(self.ev_out[i])
+        self.b.copy_(self.b_stage[i])
+        self.op.vec["v0"][:self.n_local].copy_(self.x_stage2[i])
         self.step_kernels()
-        self.out_host.copy_(self.x)
-        return self.out_host
+        self.res_dev[i].copy_(self.x)
+        self.ev_comp[i].record(cur)
+        with torch.cuda.stream(self.s_out):
+            self.s_out.wait_event(self.ev_comp[i])
+            self.out_hosts[i].copy_(self.res_dev[i], non_blocking=True)
+            self.ev_out[i].record(self.s_out)
+        return self.out_hosts[i]
 
     def close(self):
         self.op.close()

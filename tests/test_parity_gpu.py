@@ -303,6 +303,13 @@ def test_vcycle_golden(G, dev, golden):
             assert relerr(x.cpu(), ref_x) <= 1e-5
             rn = torch.norm(V.runResidual(A, b, x)).item()
             assert abs(rn - ref_norm) <= 1e-5 * max(ref_norm, 1e-2)
+    # the cached fast path issues the same kernels as the public run* functions: bit-identical
+    c = golden["vcycle"][1]
+    ei, ev = G.UtilsGNN.laplacianfun_torch(c["N"], device=dev)
+    A = torch.sparse_coo_tensor(ei, ev.flatten(), dtype=torch.float)
+    xa = V.runVCycle(A, c["b"].to(dev), c["x0"].to(dev), 3, 3, 5, True)
+    xb = V._runVCycle_layers(A, c["b"].to(dev), c["x0"].to(dev), 3, 3, 5, True)
+    assert torch.equal(xa, xb)
     # host-tensor entry, like the reference script
     c = golden["vcycle"][0]
     ei, ev = G.UtilsGNN.laplacianfun_torch(c["N"])
