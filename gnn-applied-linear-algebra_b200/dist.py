@@ -15,9 +15,11 @@ Layout per rank r (P ranks):
 Two exchange engines share the same plan:
   * `exchange()`  -- torch.distributed isend/irecv of packed rows (gloo on CPU for the tests,
     NCCL on GPUs): the portable baseline;
-  * `PeerHalo`    -- CUDA-IPC peer memory over NVLink: a pack kernel STORES this rank's boundary
-    rows directly into the neighbour's halo tail and publishes an epoch flag; the consumer waits
-    on its flag in-stream (glab_halo_push_* / glab_halo_wait).  No NCCL call on the data path.
+  * `PeerHalo`    -- CUDA-IPC peer memory over NVLink: this rank's boundary rows are STORED
+    directly into the neighbour's halo tail and the neighbour's arrival counter is release-
+    incremented; the consumer acquires its counters on the device.  Either fused into the step
+    kernel (glab_*_halo_*: one launch per sweep, communication CTA) or as stand-alone kernels
+    (glab_halo_push_* / glab_halo_wait).  No NCCL call on the data path.
 The partition logic (this file's torch index arithmetic) is covered on CPU by
 tests/test_dist_cpu.py with world_size-2 gloo.
 """
