@@ -10,6 +10,30 @@ namespace glab {
 // ---------------------------------------------------------------- epilogues (row sums in regs)
 struct NoState {};
 
+// K contiguous elements of a TMA-staged stream row in shared memory, read with 16-byte loads
+// (a per-column scalar walk has an 8-way bank conflict for K = 8: lanes are 32 bytes apart).
+template <typename T, int K>
+__device__ __forceinline__ void lds_row(T (&d)[K], const T* p) {
+  constexpr int bytes = K * (int)sizeof(T);
+  if constexpr (bytes >= 16) {
+    constexpr int per = 16 / (int)sizeof(T);
+#pragma unroll
+    for (int i = 0; i < bytes / 16; ++i) {
+      const int4 q = *(reinterpret_cast<const int4*>(p) + i);
+      const T* t = reinterpret_cast<const T*>(&q);
+#pragma unroll
+      for (int j = 0; j < per; ++j) d[i * per + j] = t[j];
+    }
+  } else if constexpr (bytes == 8) {
+    const int2 q = *reinterpret_cast<const int2*>(p);
+    const T* t = reinterpret_cast<const T*>(&q);
+#pragma unroll
+    for (int j = 0; j < K; ++j) d[j] = t[j];
+  } else {
+    d[0] = p[0];
+  }
+}
+
 template <typename T, int K> struct EpiSpmm {  // y = A x            (MatVecGNN.py:109-114)
   T* y;
   using State = NoState;
@@ -38,9 +62,10 @@ template <typename T, int K> struct EpiResidual {  // r = b - A x  (GNNResidual.
   __host__ __device__ const T* stream_ptr(int) const { return b; }
   __host__ __device__ int stream_width(int) const { return K; }
   __device__ void row_staged(State&, int r, const T (&acc)[K], const T* sb, const T*, const T*) const {
-    T o[K];
+    T bb[K], o[K];
+    lds_row<T, K>(bb, sb);
 #pragma unroll
-    for (int c = 0; c < K; ++c) o[c] = sb[c] - acc[c];
+    for (int c = 0; c < K; ++c) o[c] = bb[c] - acc[c];
     store_vec<T, K>(out + (size_t)r * K, o);
   }
   __device__ void finish(State&) const {}
@@ -62,9 +87,10 @@ template <typename T, int K> struct EpiAdd {  // out = b + A x  (coarse-grid cor
   __host__ __device__ const T* stream_ptr(int) const { return b; }
   __host__ __device__ int stream_width(int) const { return K; }
   __device__ void row_staged(State&, int r, const T (&acc)[K], const T* sb, const T*, const T*) const {
-    T o[K];
+    T bb[K], o[K];
+    lds_row<T, K>(bb, sb);
 #pragma unroll
-    for (int c = 0; c < K; ++c) o[c] = sb[c] + acc[c];
+    for (int c = 0; c < K; ++c) o[c] = bb[c] + acc[c];
     store_vec<T, K>(out + (size_t)r * K, o);
   }
   __device__ void finish(State&) const {}
@@ -91,10 +117,12 @@ template <typename T, int K> struct EpiJacobi {  // x + w*(b - Ax)/d  (JacobiGNN
   __host__ __device__ const T* stream_ptr(int i) const { return i == 0 ? diag : (i == 1 ? b : x); }
   __host__ __device__ int stream_width(int i) const { return i == 0 ? 1 : K; }
   __device__ void row_staged(State& s, int r, const T (&acc)[K], const T* sd, const T* sb, const T* sx) const {
-    T o[K];
+    T o[K], bb[K], xx[K];
     const T d = sd[0];
+    lds_row<T, K>(bb, sb);
+    lds_row<T, K>(xx, sx);
 #pragma unroll
-    for (int c = 0; c < K; ++c) o[c] = sx[c] + (s.w * (sb[c] - acc[c])) / d;
+    for (int c = 0; c < K; ++c) o[c] = xx[c] + (s.w * (bb[c] - acc[c])) / d;
     store_vec<T, K>(xo + (size_t)r * K, o);
   }
   __device__ void finish(State&) const {}
@@ -126,11 +154,13 @@ template <typename T, int K> struct EpiChebyFirst {  // ChebyGNN.py:117, :160-16
   __host__ __device__ const T* stream_ptr(int i) const { return i == 0 ? b : x; }
   __host__ __device__ int stream_width(int) const { return K; }
   __device__ void row_staged(State& s, int r, const T (&acc)[K], const T* sb, const T* sx, const T*) const {
-    T rr[K], o[K];
+    T rr[K], o[K], bb[K], xx[K];
+    lds_row<T, K>(bb, sb);
+    lds_row<T, K>(xx, sx);
 #pragma unroll
     for (int c = 0; c < K; ++c) {
-      rr[c] = sb[c] - acc[c];
-      o[c] = sx[c] + s.a * rr[c];
+      rr[c] = bb[c] - acc[c];
+      o[c] = xx[c] + s.a * rr[c];
     }
     store_vec<T, K>(r_ + (size_t)r * K, rr);
     store_vec<T, K>(p_ + (size_t)r * K, rr);
@@ -173,11 +203,14 @@ template <typename T, int K> struct EpiChebyNext {  // ChebyGNN.py:214, :240-241
   __host__ __device__ int stream_width(int) const { return K; }
   __device__ void row_staged(State& s, int r, const T (&acc)[K], const T* sp, const T* sr, const T* sx) const {
     T pp[K], rr[K], xx[K];
+    lds_row<T, K>(pp, sp);
+    lds_row<T, K>(rr, sr);
+    lds_row<T, K>(xx, sx);
 #pragma unroll
     for (int c = 0; c < K; ++c) {
-      rr[c] = sr[c] - s.ao * acc[c];
-      pp[c] = rr[c] + s.b * sp[c];
-      xx[c] = sx[c] + s.a * pp[c];
+      rr[c] = rr[c] - s.ao * acc[c];
+      pp[c] = rr[c] + s.b * pp[c];
+      xx[c] = xx[c] + s.a * pp[c];
     }
     store_vec<T, K>(r_ + (size_t)r * K, rr);
     store_vec<T, K>(p_out + (size_t)r * K, pp);
