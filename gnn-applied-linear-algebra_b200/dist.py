@@ -35,11 +35,12 @@ from ._lib import check, lib
 class RowPartition:
     """Contiguous row blocks: rank r owns rows [offsets[r], offsets[r+1])."""
 
-    def __init__(self, n, world, align=1):
-        base = (n // world) // align * align
-        offs = [min(r * base, n) for r in range(world)] + [n]
+    def __init__(self, n, world, align=1, offsets=None):
+        if offsets is None:
+            base = (n // world) // align * align
+            offsets = [min(r * base, n) for r in range(world)] + [n]
         self.n, self.world = n, world
-        self.offsets = torch.tensor(offs, dtype=torch.int64)
+        self.offsets = torch.tensor([int(o) for o in offsets], dtype=torch.int64)
 
     def bounds(self, rank):
         return int(self.offsets[rank]), int(self.offsets[rank + 1])
@@ -122,23 +123,25 @@ class HaloPlan:
         pos = torch.searchsorted(self.halo_cols, global_cols.clamp(min=0))
         return torch.where(inside, global_cols - r0, pos + self.n_local)
 
-    def interior_rows(self, local_rows, local_cols, align=256):
+    def interior_rows(self, local_rows, local_cols, align=256, n_rows=None, mark_send_rows=True):
         """[lo, hi): a contiguous range of rows none of which reads the halo tail or is sent to a
         neighbour (aligned to the kernel's 256-row tiles).  Rows outside it are the boundary rows:
         they wait for the exchange and are finished before the push."""
-        touches = torch.zeros(self.n_local, dtype=torch.bool, device=local_rows.device)
+        n_rows = self.n_local if n_rows is None else n_rows
+        touches = torch.zeros(n_rows, dtype=torch.bool, device=local_rows.device)
         touches[local_rows[local_cols >= self.n_local]] = True
-        for q in self.peers_send:   # rows we ship to neighbours must be finished before the push
-            touches[self.send_rows[q].long().to(local_rows.device)] = True
+        if mark_send_rows:
+            for q in self.peers_send:   # rows we ship to neighbours must be finished before the push
+                touches[self.send_rows[q].long().to(local_rows.device)] = True
         idx = torch.nonzero(touches).reshape(-1)
         if idx.numel() == 0:
-            return 0, self.n_local
-        mid = self.n_local // 2
+            return 0, n_rows
+        mid = n_rows // 2
         lead = idx[idx < mid]
         trail = idx[idx >= mid]
         lo = int(lead.max()) + 1 if lead.numel() else 0
-        hi = int(trail.min()) if trail.numel() else self.n_local
-        lo = min((lo + align - 1) // align * align, self.n_local)
+        hi = int(trail.min()) if trail.numel() else n_rows
+        lo = min((lo + align - 1) // align * align, n_rows)
         hi = max(hi // align * align, lo)
         return lo, hi
 
@@ -160,14 +163,17 @@ class HaloPlan:
             w.wait()
 
 
-def partition_coo(edge_index, edge_val, part, rank, group=None):
-    """Rows of a GLOBAL COO that belong to `rank`, renumbered for the local plan.
-    Returns (local_edge_index [2, z_loc], local_vals [z_loc, F], HaloPlan)."""
+def partition_coo(edge_index, edge_val, part, rank, group=None, col_part=None):
+    """Rows of a GLOBAL COO that belong to `rank` (row partition `part`), with the columns
+    renumbered for the local plan against the partition of the GATHERED vector (`col_part`,
+    default: the same partition -- square operators; a prolongator gathers coarse vectors and
+    produces fine ones, so its two partitions differ).
+    Returns (local_edge_index [2, z_loc], local_vals [z_loc, F], HaloPlan of the gathered vector)."""
     r0, r1 = part.bounds(rank)
     mine = (edge_index[0] >= r0) & (edge_index[0] < r1)
     rows = edge_index[0][mine] - r0
     gcols = edge_index[1][mine]
-    halo = HaloPlan.build(part, rank, gcols, group)
+    halo = HaloPlan.build(part if col_part is None else col_part, rank, gcols, group)
     cols = halo.local_columns(gcols)
     return torch.stack([rows, cols]), edge_val[mine], halo
 
@@ -352,16 +358,23 @@ class DistOperator:
     torch.distributed: NCCL on GPUs; the same HaloPlan logic is what tests/test_dist_cpu.py
     exercises with gloo)."""
 
-    def __init__(self, local_edge_index, local_vals, halo, k=1, engine="peer", group=None):
+    def __init__(self, local_edge_index, local_vals, halo, k=1, engine="peer", group=None, n_rows=None,
+                 names=("v0", "va", "vb")):
+        """n_rows: number of local ROWS when it differs from the local length of the gathered
+        vector (rectangular operators: restriction / prolongation); such operators are applied
+        with apply_rect() (stand-alone wait, whole-block kernel), not with the fused steps."""
         self.halo, self.k, self.group, self.engine = halo, k, group, engine
         self.device = local_vals.device
         self.dtype = local_vals.dtype
         n_loc, n_ext = halo.n_local, halo.n_local + halo.n_halo
-        self.plan = rt.Plan.from_coo(local_edge_index.contiguous(), n_loc, n_ext)
+        self.square = n_rows is None or n_rows == n_loc
+        self.n_rows = n_loc if n_rows is None else n_rows
+        self.plan = rt.Plan.from_coo(local_edge_index.contiguous(), self.n_rows, n_ext)
         self.vals = rt.get_vals(self.plan, local_vals.view(-1, 1))
         self._keep = (local_edge_index, local_vals)
-        self.lo, self.hi = halo.interior_rows(local_edge_index[0], local_edge_index[1])
-        self.names = ["v0", "va", "vb"]
+        self.lo, self.hi = halo.interior_rows(local_edge_index[0], local_edge_index[1], n_rows=self.n_rows,
+                                              mark_send_rows=self.square)
+        self.names = list(names)
         if engine in ("peer", "peer-split"):
             self.peer = PeerHalo(halo, k, self.dtype, self.device, self.names, group)
             self.vec = self.peer.views
@@ -437,6 +450,21 @@ class DistOperator:
         self.vec[name][:self.n_local].copy_(x_local.view(self.n_local, self.k))
         self.publish(name)
 
+    def local(self, name):
+        """The locally owned rows of gathered vector `name` (a view into the peer buffer)."""
+        return self.vec[name][:self.n_local]
+
+    def apply_rect(self, name_in, out, add_to=None):
+        """out = A x (or add_to + A x) for a gathered vector that was publish()-ed by its producer;
+        works for rectangular row blocks.  Stand-alone wait + one whole-block kernel."""
+        self.acquire(name_in)
+        xin = self.vec[name_in]
+        if add_to is None:
+            rt.spmm(self.plan, self.vals, xin, out)
+        else:
+            rt.spmm_add(self.plan, self.vals, xin, add_to, out)
+        return out
+
     def jacobi(self, n_iters, diag, b, omega_dev, start="v0"):
         """n_iters sweeps starting from vector `start` (already load()-ed / published), ping-ponging
         through "va"/"vb" (never overwriting `start` if it is "v0"); returns the name of the
@@ -463,14 +491,17 @@ class DistOperator:
         own local buffer after iteration 1 (only p is gathered), so the named peer vectors
         ping-pong p.  Returns (x, r, name of p)."""
         n, k = self.n_local, self.k
-        other = "vb" if start == "va" else "va"
+        # p ping-pongs between two named vectors, never `start` if that is "v0" (kept intact so
+        # that the same start vector can be reused by the next call)
+        other = "va" if start != "va" else "vb"
+        second = "vb" if start == "v0" else start
         xin = self.vec[start]
         x = torch.empty(n, k, dtype=self.dtype, device=self.device) if x is None else x
         r = torch.empty_like(x) if r is None else r
         pv = self.vec[other]
         self.run_step(start, lambda **kw: rt.cheby_first(self.plan, self.vals, b, xin, x, r, pv, table[0, 1:2], **kw),
                       other)
-        cur, nxt = other, start
+        cur, nxt = other, second
         for it in range(1, deg):
             pin, pout = self.vec[cur], self.vec[nxt]
             self.run_step(cur, lambda **kw: rt.cheby_next(self.plan, self.vals, pin, pout, r, x,

@@ -74,6 +74,23 @@ def _worker(rank, world, port_no, kind, q):
         x_ext[:halo.n_local] *= 2
         halo.exchange(x_ext)
         assert torch.equal(x_ext[halo.n_local:], 2 * x[halo.halo_cols])
+        # rectangular operator (restriction / prolongation): rows and gathered vector live in
+        # DIFFERENT partitions
+        m = 61
+        g2 = torch.Generator().manual_seed(11)
+        rr = torch.randint(0, n, (900,), generator=g2)
+        cc = torch.randint(0, m, (900,), generator=g2)
+        order2 = torch.argsort(rr, stable=True)
+        ri = torch.stack([rr[order2], cc[order2]])
+        rv = torch.rand(900, 1, generator=g2, dtype=torch.float64)
+        xc = torch.rand(m, 2, generator=g2, dtype=torch.float64)
+        cpart = gd.RowPartition(m, world, offsets=[0] + [min(m, 7 + (m // world) * (q + 1)) for q in range(world - 1)] + [m])
+        li, lv, lh = gd.partition_coo(ri, rv, part, rank, col_part=cpart)
+        c0, c1 = cpart.bounds(rank)
+        xe = gd.extend(xc[c0:c1].clone(), lh.n_halo)
+        lh.exchange(xe)
+        yr = port.scatter_sum(lv * xe[li[1]], li[0], r1 - r0)
+        assert torch.equal(yr, port.scatter_sum(rv * xc[ri[1]], ri[0], n)[r0:r1])
         # allreduce of partial sums (power-method norms)
         ss = (y_loc ** 2).sum(0)
         dist.all_reduce(ss)
