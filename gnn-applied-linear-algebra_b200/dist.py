@@ -159,6 +159,8 @@ class HaloPlan:
             buf = x_ext.index_select(0, self.send_rows[q].long())
             keep.append(buf)
             ops.append(dist.P2POp(dist.isend, buf, q, group=group))
+        if not ops:
+            return
         for w in dist.batch_isend_irecv(ops):
             w.wait()
 
