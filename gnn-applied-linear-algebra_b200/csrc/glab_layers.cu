@@ -427,9 +427,10 @@ static int launch_pipe_halo(const glab_plan* p, const T* vals, const T* x, const
       !hs->done_counter)
     return GLAB_E_ARG;
   const int64_t n = p->n_rows;
-  if (hs->interior_begin < 0 || hs->interior_end < hs->interior_begin || hs->interior_end > n ||
-      (hs->interior_begin % kThreads) || (hs->interior_end % kThreads && hs->interior_end != n))
-    return GLAB_E_ARG;
+  int64_t ib = hs->interior_begin, ie = hs->interior_end;
+  if (ib < 0 || ie < ib || ie > n) return GLAB_E_ARG;
+  if (ib == ie) ib = ie = 0;  // no interior rows (tiny blocks): every tile is a boundary tile
+  else if ((ib % kThreads) || (ie % kThreads && ie != n)) return GLAB_E_ARG;
   if (reinterpret_cast<uintptr_t>(p->rowptr) & 15) return GLAB_E_ARG;
   for (int i = 0; i < Epi::kStreams; ++i)
     if (reinterpret_cast<uintptr_t>(epi.stream_ptr(i)) & 15) return GLAB_E_ARG;
@@ -459,8 +460,8 @@ static int launch_pipe_halo(const glab_plan* p, const T* vals, const T* x, const
   if (tuning().ctas && occ > tuning().ctas) occ = tuning().ctas;
   const int ntiles = (int)((n + kThreads - 1) / kThreads);
   HaloCtl h;
-  h.int_tile0 = (int)(hs->interior_begin / kThreads);
-  h.int_tiles = (int)((hs->interior_end - hs->interior_begin + kThreads - 1) / kThreads);
+  h.int_tile0 = (int)(ib / kThreads);
+  h.int_tiles = (int)((ie - ib + kThreads - 1) / kThreads);
   h.lead_tiles = h.int_tile0;
   h.trail_tile0 = h.int_tile0 + h.int_tiles;
   h.n_wait = hs->n_wait;

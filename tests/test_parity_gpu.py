@@ -428,8 +428,9 @@ def test_vcycle_multi_rhs_and_large_grid(G, dev):
     assert all(b_ < a_ for a_, b_ in zip(norms, norms[1:])), norms
 
 
+@pytest.mark.parametrize("N,align", [(80, 256), (20, 16)])
 @pytest.mark.parametrize("dt", [torch.float32, torch.float64])
-def test_fused_halo_step_two_ranks_emulated_on_one_gpu(G, dev, dt):
+def test_fused_halo_step_two_ranks_emulated_on_one_gpu(G, dev, dt, N, align):
     """The multi-GPU data path (glab_halo_push, the fused glab_jacobi_halo / glab_cheby_*_halo
     kernels with in-kernel acquire + communication CTA) exercised on ONE GPU: two row blocks of
     the operator live in the same process and their kernels run one after the other on one
@@ -438,7 +439,7 @@ def test_fused_halo_step_two_ranks_emulated_on_one_gpu(G, dev, dt):
     from glab_b200 import dist as gd
     from glab_b200._lib import HaloStep, PushDesc
     rt = G.runtime
-    N, world, sweeps = 80, 2, 4
+    world, sweeps = 2, 4
     n = N * N
     ei, ev = G.generators.heat_fem_2d((N + 1, N + 1), (1.0, 2.0), torch.float64, dev)
     ev = ev.to(dt).contiguous()
@@ -455,7 +456,7 @@ def test_fused_halo_step_two_ranks_emulated_on_one_gpu(G, dev, dt):
         xa, xb = xb, xa
     ref = xa
 
-    part = gd.RowPartition(n, world, align=256)
+    part = gd.RowPartition(n, world, align=align)    # align=16: blocks too small for an interior range
     blocks = []
     for r in range(world):
         r0, r1 = part.bounds(r)
