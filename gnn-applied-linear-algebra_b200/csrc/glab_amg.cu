@@ -87,7 +87,8 @@ static int launch_edge_pipe(const glab_plan* p, const T* vals, const T* aux, con
   L.off_aux = off; if (Op::kNarr > 1) off += round_up128((int)slots * (int)sizeof(T) + 32);
   L.stage_bytes = off;
   auto kern = k_edge_pipe<T, Op>;
-  static int max_smem = 0;
+  static int max_smem_dev[kMaxDevices] = {};
+  int& max_smem = max_smem_dev[p->device % kMaxDevices];
   if (!max_smem) {
     cudaFuncAttributes fa;
     GLAB_CUDA(cudaFuncGetAttributes(&fa, kern));
@@ -128,10 +129,10 @@ static int launch_edge_tiles(const glab_plan* p, const T* vals, const T* aux, co
   cap = (cap + 31) & ~31;
   const size_t smem = tile_smem_bytes<T>(cap, Op::kNarr);
   auto kern = k_edge_tiles<T, Op>;
-  static bool attr_done = false;
-  if (!attr_done) {
+  static bool attr_done[kMaxDevices] = {};
+  if (!attr_done[p->device % kMaxDevices]) {
     GLAB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024));
-    attr_done = true;
+    attr_done[p->device % kMaxDevices] = true;
   }
   TileArgs<T> a{p->rowptr, p->colidx, vals, 0, (int)p->n_rows, cap};
   kern<<<ntiles, kThreads, smem, as_stream(stream)>>>(a, aux, p->perm, op, out, ntiles);

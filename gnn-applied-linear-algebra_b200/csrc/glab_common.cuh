@@ -29,6 +29,7 @@ namespace glab {
 
 constexpr int kThreads = 256;          // threads per CTA of every row-tile kernel
 constexpr int kMaxReduceBlocks = 4096; // upper bound on the persistent grid of reducing kernels
+constexpr int kMaxDevices = 64;        // per-device caches of one-time kernel attributes
 
 static inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
 

@@ -57,7 +57,10 @@ __global__ void k_halo_wait(WaitArgs a, int n, const uint32_t* pushed_local) {
 static unsigned int* done_counters() {
   // GLAB_MAX_PEERS 4-byte counters per process/device, zero-initialised; pushes on one stream
   // are ordered, and every launch leaves them at zero.
-  static unsigned int* ctr = nullptr;
+  static unsigned int* ctrs[kMaxDevices] = {};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return nullptr;
+  unsigned int*& ctr = ctrs[dev % kMaxDevices];
   if (!ctr) {
     if (cudaMalloc(&ctr, 256) != cudaSuccess) return nullptr;
     cudaMemset(ctr, 0, 256);

@@ -341,10 +341,10 @@ static int launch_tiles(const glab_plan* p, const T* vals, const T* x, const Epi
   cap = (cap + 31) & ~31;
   const size_t smem = tile_smem_bytes<T>(cap, 1);
   auto kern = k_row_tiles<T, K, RPT, Epi>;
-  static bool attr_done = false;  // one per template instantiation
-  if (!attr_done) {
+  static bool attr_done[kMaxDevices] = {};  // per template instantiation and device
+  if (!attr_done[p->device % kMaxDevices]) {
     GLAB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024));
-    attr_done = true;
+    attr_done[p->device % kMaxDevices] = true;
   }
   int grid = ntiles;
   if (persistent) {
@@ -438,7 +438,8 @@ static int launch_pipe_halo(const glab_plan* p, const T* vals, const T* x, const
   int64_t slots;
   if (!make_pipe_layout<T>(p, epi, L, slots)) return GLAB_E_ARG;
   auto kern = k_row_pipe<T, K, U, Epi, true>;
-  static int max_smem = 0;
+  static int max_smem_dev[kMaxDevices] = {};
+  int& max_smem = max_smem_dev[p->device % kMaxDevices];
   if (!max_smem) {
     cudaFuncAttributes fa;
     GLAB_CUDA(cudaFuncGetAttributes(&fa, kern));
@@ -510,7 +511,8 @@ static int launch_pipe_u(const glab_plan* p, const T* vals, const T* x, const Ep
   }
   L.stage_bytes = off;
   auto kern = k_row_pipe<T, K, U, Epi, false>;
-  static int max_smem = 0;  // per instantiation: 227 KB minus the kernel's static shared memory
+  static int max_smem_dev[kMaxDevices] = {};  // per instantiation and device: 227 KB minus static smem
+  int& max_smem = max_smem_dev[p->device % kMaxDevices];
   if (!max_smem) {
     cudaFuncAttributes fa;
     GLAB_CUDA(cudaFuncGetAttributes(&fa, kern));

@@ -14,6 +14,10 @@
  *   - extern "C", plain pointers and sizes, no C++/torch types.
  *   - every function returns int: 0 = ok, >0 = cudaError_t, <0 = GLAB_E_* argument error.
  *     Nothing throws, nothing aborts, nothing synchronises the device unless documented.
+ *   - calls operate on the CURRENT CUDA device, which must be the device the plan / pointers
+ *     live on (one process per GPU is the intended model; several devices per process work as
+ *     long as the caller switches devices).  The library keeps no data-path state besides
+ *     opaque plans; calls are safe from one host thread per device.
  *   - all data pointers are BORROWED DEVICE pointers (owned by the caller, e.g. torch tensors);
  *     the library allocates only inside opaque plans (glab_plan_*, glab_halo_*).
  *   - `stream` is a cudaStream_t passed as void* (torch.cuda.current_stream().cuda_stream).
