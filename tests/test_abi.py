@@ -50,3 +50,28 @@ def test_no_cpu_fallback(G):
     with pytest.raises(G.GlabError):
         G.JacobiGNN.JacobiGNN()(1, torch.zeros(4, 3), torch.zeros(2, 4, dtype=torch.long), torch.zeros(4, 2),
                                 torch.tensor([0.7]))
+
+
+def test_plan_cache_validity_rules(G):
+    """The plan / value caches key on (storage pointer, shape, strides, dtype, device, version) and
+    are valid only while the tensor that created the entry is alive and unmodified."""
+    import torch
+    C = G.runtime._Cache(capacity=2)
+    t = torch.arange(10)
+    assert C.get(t) is None
+    C.put(t, "plan-A", extra=(5,))
+    assert C.get(t, extra=(5,)) == "plan-A" and C.get(t, extra=(6,)) is None
+    view = t[:]                      # another tensor object on the same storage: valid while `t` lives
+    assert C.get(view, extra=(5,)) == "plan-A"
+    t.add_(1)                        # in-place modification bumps _version -> miss
+    assert C.get(t, extra=(5,)) is None
+    u = torch.arange(10)
+    C.put(u, "plan-B")
+    del u                            # creator gone: its address may be recycled -> entry must not be served
+    import gc
+    gc.collect()
+    w = torch.arange(10)
+    assert C.get(w) is None
+    for i in range(4):               # LRU capacity
+        C.put(torch.zeros(3 + i), i)
+    assert len(C.d) <= 2
