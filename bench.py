@@ -36,7 +36,7 @@ sys.path.insert(0, ROOT)
 
 import torch  # noqa: E402
 
-GRID = {"L4096": 4096, "L8192": 8192, "L2048": 2048, "L1024": 1024, "L256": 256}
+GRID = {"L4096": 4096, "L8192": 8192, "L2048": 2048, "L1448": 1448, "L1024": 1024, "L256": 256}
 N_JACOBI, CHEB_DEG, OMEGA, CHEB_C, CHEB_D = 10, 4, 0.7, -3.4, -4.0
 LAUNCHES_PER_STEP = N_JACOBI + CHEB_DEG
 

@@ -22,6 +22,10 @@ class SingleGpuSmoother:
         t1 = time.perf_counter()
         self.plan = G.get_plan(self.ei, n)
         self.vals = rt.get_vals(self.plan, self.ev)
+        import os
+        if os.environ.get("GLAB_L2_PERSIST", "0") == "1":      # experiment knob (L2-sized operators)
+            self.vals = rt.adopt_vals(self.plan, self.vals)
+            rt.l2_persist(self.plan, True)
         torch.cuda.synchronize()
         t2 = time.perf_counter()
         self.n_local = self.n = n

@@ -147,6 +147,26 @@ class Plan:
         return wrap(rp, self.n_rows + 1), wrap(ci, self.nnz), (wrap(pm, self.nnz) if pm.value else None)
 
 
+def adopt_vals(plan, vals):
+    """Copy the CSR-ordered values into plan-owned storage right behind colidx (so that ONE L2
+    access-policy window can cover the whole operator) and return a zero-copy tensor over it."""
+    out = P()
+    with torch.cuda.device(plan.device):
+        check(getattr(lib, "glab_plan_adopt_vals_" + suffix(vals.dtype))(plan.handle, ptr(vals), ctypes.byref(out),
+                                                                        stream_ptr()), "glab_plan_adopt_vals")
+        typestr = "<f4" if vals.dtype == torch.float32 else "<f8"
+        if plan.nnz == 0:
+            return vals
+        return torch.as_tensor(_DevArray(out.value, plan.nnz, typestr, plan), device=plan.device)
+
+
+def l2_persist(plan, enable=True):
+    """Mark the plan's [colidx | adopted values] as persisting in L2 for kernels launched on (or
+    captured from) the current stream."""
+    with torch.cuda.device(plan.device):
+        check(lib.glab_plan_l2_persist(plan.handle, 1 if enable else 0, stream_ptr()), "glab_plan_l2_persist")
+
+
 # --------------------------------------------------------------------------- caches
 class _Cache:
     """Small LRU keyed on (storage pointer, shape, strides, version, extra).  An entry is valid

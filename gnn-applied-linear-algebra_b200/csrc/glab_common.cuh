@@ -23,6 +23,8 @@ struct glab_plan {
   int32_t* colidx;
   int32_t* perm;
   int32_t max_row_nnz;
+  void* owned_vals;        // optional plan-owned copy of the values (glab_plan_adopt_vals_*), else NULL
+  size_t owned_vals_bytes;
 };
 
 namespace glab {

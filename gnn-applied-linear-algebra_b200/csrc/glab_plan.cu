@@ -10,6 +10,7 @@
 // Slow path (arbitrary edge order): stable LSD radix sort of (row, edge id) with CUB -- setup
 // only, never on a layer step -- then the same boundary pass.
 #include <cub/device/device_radix_sort.cuh>
+#include <cstring>
 #include <new>
 #include "glab_common.cuh"
 
@@ -181,6 +182,7 @@ static void plan_free(glab_plan* p) {
   if (p->rowptr) cudaFree(p->rowptr);
   if (p->colidx) cudaFree(p->colidx);
   if (p->perm) cudaFree(p->perm);
+  if (p->owned_vals) cudaFree(p->owned_vals);
   delete p;
 }
 
@@ -198,6 +200,8 @@ static int plan_alloc(int64_t n_rows, int64_t n_cols, int64_t nnz, glab_plan** o
   p->colidx = nullptr;
   p->perm = nullptr;
   p->max_row_nnz = 0;
+  p->owned_vals = nullptr;
+  p->owned_vals_bytes = 0;
   cudaError_t e = cudaGetDevice(&p->device);
   if (e == cudaSuccess)
     e = cudaDeviceGetAttribute(&p->sm_count, cudaDevAttrMultiProcessorCount, p->device);
@@ -411,4 +415,59 @@ extern "C" int glab_unpack_f32(int64_t n, int64_t ld, int np, float* const* part
 extern "C" int glab_unpack_f64(int64_t n, int64_t ld, int np, double* const* parts, const int32_t* w,
                                const int32_t* o, const double* src, void* s) {
   return pack_launch<double, false>(n, ld, np, parts, w, o, const_cast<double*>(src), s);
+}
+
+// ---- L2 residency (optional) ------------------------------------------------------------------
+template <typename T>
+static int adopt_vals(glab_plan* p, const T* vals, const T** out, void* stream) {
+  if (!p || !out || (p->nnz > 0 && !vals)) return GLAB_E_ARG;
+  // one allocation [colidx | vals] so that a single access-policy window covers the operator
+  const size_t col_bytes = ((size_t)(p->nnz + 8) * 4 + 255) & ~(size_t)255;
+  const size_t val_bytes = (size_t)(p->nnz + 8) * sizeof(T);
+  void* buf = nullptr;
+  cudaError_t e = cudaMalloc(&buf, col_bytes + val_bytes);
+  if (e != cudaSuccess) { cudaGetLastError(); return GLAB_E_NOMEM; }
+  cudaStream_t st = as_stream(stream);
+  GLAB_CUDA(cudaMemcpyAsync(buf, p->colidx, (size_t)p->nnz * 4, cudaMemcpyDeviceToDevice, st));
+  GLAB_CUDA(cudaMemcpyAsync((char*)buf + col_bytes, vals, (size_t)p->nnz * sizeof(T), cudaMemcpyDeviceToDevice, st));
+  GLAB_CUDA(cudaStreamSynchronize(st));
+  cudaFree(p->colidx);
+  if (p->owned_vals) { /* previous adoption lived inside the old colidx allocation */ }
+  p->colidx = reinterpret_cast<int32_t*>(buf);
+  p->owned_vals = nullptr;  // the values live inside the colidx allocation: freed with it
+  p->owned_vals_bytes = col_bytes + val_bytes;
+  *out = reinterpret_cast<const T*>((char*)buf + col_bytes);
+  return 0;
+}
+
+extern "C" int glab_plan_adopt_vals_f32(glab_plan* p, const float* v, const float** o, void* s) {
+  return adopt_vals<float>(p, v, o, s);
+}
+extern "C" int glab_plan_adopt_vals_f64(glab_plan* p, const double* v, const double** o, void* s) {
+  return adopt_vals<double>(p, v, o, s);
+}
+
+extern "C" int glab_plan_l2_persist(const glab_plan* p, int enable, void* stream) {
+  if (!p) return GLAB_E_ARG;
+  cudaStreamAttrValue attr;
+  memset(&attr, 0, sizeof(attr));
+  if (enable) {
+    int dev = p->device, max_window = 0, max_persist = 0;
+    GLAB_CUDA(cudaDeviceGetAttribute(&max_window, cudaDevAttrMaxAccessPolicyWindowSize, dev));
+    GLAB_CUDA(cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, dev));
+    if (max_window <= 0 || max_persist <= 0) return 0;  // not supported: silently a no-op
+    GLAB_CUDA(cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, (size_t)max_persist));
+    size_t bytes = p->owned_vals_bytes ? p->owned_vals_bytes : (size_t)p->nnz * 4;
+    if (bytes > (size_t)max_window) bytes = (size_t)max_window;
+    attr.accessPolicyWindow.base_ptr = p->colidx;
+    attr.accessPolicyWindow.num_bytes = bytes;
+    double ratio = (double)max_persist * 0.9 / (double)bytes;
+    attr.accessPolicyWindow.hitRatio = (float)(ratio > 1.0 ? 1.0 : ratio);
+    attr.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+    attr.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+  } else {
+    attr.accessPolicyWindow.num_bytes = 0;
+  }
+  GLAB_CUDA(cudaStreamSetAttribute(as_stream(stream), cudaStreamAttributeAccessPolicyWindow, &attr));
+  return 0;
 }

@@ -76,6 +76,18 @@ int glab_plan_info(const glab_plan* plan, int64_t* n_rows, int64_t* n_cols, int6
                    int32_t* max_row_nnz, int32_t* identity_perm);
 int glab_plan_csr(const glab_plan* plan, const int32_t** rowptr, const int32_t** colidx,
                   const int32_t** perm);
+/* L2 residency for operators that fit the 126 MB L2 (e.g. one rank's block of a row-partitioned
+ * operator): adopt copies the CSR-ordered values into plan-owned storage directly behind colidx
+ * (*vals_out points at the copy; use it instead of the caller's array), l2_persist then marks
+ * [colidx .. values] as persisting in L2 for every kernel subsequently launched on (or captured
+ * from) `stream` (cudaStreamAttributeAccessPolicyWindow; hit ratio scaled to the device's
+ * persisting-L2 capacity), so repeated sweeps stream the operator from L2 instead of HBM.
+ * enable = 0 removes the window.  Both are optional and change no result.  EXPERIMENTAL: on B200 the
+ * measured effect for an 84 MB operator was negative, so no layer enables it. */
+int glab_plan_adopt_vals_f32(glab_plan* plan, const float* vals, const float** vals_out, void* stream);
+int glab_plan_adopt_vals_f64(glab_plan* plan, const double* vals, const double** vals_out, void* stream);
+int glab_plan_l2_persist(const glab_plan* plan, int enable, void* stream);
+
 /* vals[slot] = edge_attr[perm[slot]*ld + column]  (CSR-ordered contiguous copy of A_ij). */
 int glab_gather_vals_f32(const glab_plan* plan, const float* edge_attr, int64_t ld, int64_t column,
                          float* vals, void* stream);
