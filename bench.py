@@ -233,8 +233,19 @@ def main_gpu(args):
         prob = SingleGpuSmoother(G, N, dev)
     else:
         from bench_support import PartitionedSmoother
-        prob = PartitionedSmoother(G, N, dev, rank, world, engine=os.environ.get("GLAB_DIST_ENGINE", "peer"),
-                                   use_graph=os.environ.get("GLAB_DIST_GRAPH", "1") != "0")
+        engine = os.environ.get("GLAB_DIST_ENGINE", "peer")
+        import torch.distributed as dist
+        try:
+            prob = PartitionedSmoother(G, N, dev, rank, world, engine=engine,
+                                       use_graph=os.environ.get("GLAB_DIST_GRAPH", "1") != "0")
+            ok = 1
+        except G.GlabError as exc:      # e.g. CUDA IPC / peer access not permitted on this box
+            print("rank %d: peer-memory engine unavailable (%s)" % (rank, exc), file=sys.stderr)
+            ok = 0
+        flag = torch.tensor([ok], device=dev)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        if flag.item() == 0:            # every rank falls back together: halo rows via NCCL send/recv
+            prob = PartitionedSmoother(G, N, dev, rank, world, engine="torch", use_graph=False)
     z_global = prob.nnz_global
 
     def barrier():
