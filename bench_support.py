@@ -166,6 +166,7 @@ class PartitionedSmoother:
         self.graph = None
         self.jac_graph = None
         self.use_graph = use_graph and engine in ("peer", "peer-split")
+        self.setup_info["cuda_graph"] = self.use_graph
         if self.use_graph:
             self._capture()
 
