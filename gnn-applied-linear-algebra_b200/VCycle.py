@@ -5,15 +5,16 @@ residual, Chebyshev coarse solve, correction).
 Same function names and call order as the reference's free functions (VCycle.py:58-237).
 Differences, all on the glue side (the layer calls are the reference's):
   * nothing runs at import time (the reference executes its N=5 demo on import, :239-277);
-  * the prolongator P = [I + W](:, C) is assembled SPARSE on the device -- the reference builds a
-    dense n x n matrix (:129-134), which caps it at n ~ 1e4;
+  * the prolongator P = [I + W](:, C) is assembled SPARSE on the device (glab_interp_*) -- the
+    reference builds a dense n x n matrix (:129-134), which caps it at n ~ 1e4 -- and the Galerkin
+    product P^T A P (:209) runs as two device SpGEMMs (glab_spgemm_*), not through torch.sparse;
   * the AMG hierarchy (SOC, P, P^T, A_c and their CSR plans) is cached per operator instead of
     being rebuilt inside every runVCycle call;
   * the diagonal A_ii is read from A (the reference hard-codes -4, :117,165; identical for
     laplacianfun_torch matrices);
-  * pyamg's CLJP (:114) is not available: pass `splitting=` (any 0/1 vector) or get the
-    reference's own deterministic alternative C(1:2:end)=1 (matlab/test_vcycle.m:66-67).
-    The splitting is an input of the hot path, not part of it.
+  * pyamg's CLJP (:114) is not available: pass `splitting=` (any 0/1 vector, e.g. the device
+    PMIS splitting of runCFSplit) or get the reference's own deterministic alternative
+    C(1:2:end)=1 (matlab/test_vcycle.m:66-67).  The splitting is an input of the hot path.
 """
 import weakref
 
@@ -99,24 +100,38 @@ def runSOC(A):
     return S if A.is_cuda else S.cpu()
 
 
-def runDirectInterp(A, S, N=None, splitting=None):
-    """Prolongator P (sparse [n, n_coarse]) from direct interpolation  (VCycle.py:94-137)."""
+def runCFSplit(A, S, seed=0):
+    """Coarse/fine splitting of A's strength graph on the device (PMIS with integer keys),
+    [n, 1] with 1 = coarse -- the stand-in for `CLJP(S_csr)` at VCycle.py:106-115 (pyamg is an
+    un-pinned, absent dependency; parity is against oracle/cf_split.py instead).  Note that
+    runVCycle's coarse solve keeps the reference's hard-coded Chebyshev bounds (d = -4, c = -3.4,
+    :221-222), which fit the Galerkin operator of the alternating splitting on laplacianfun_torch
+    matrices, not that of an arbitrary splitting."""
+    op = _operator(A)
+    plan_off = rt.get_plan(op.off_index, op.n)
+    S_slots = rt.slot_order(plan_off, _place(op, S).reshape(-1).to(op.off_attr.dtype))
+    cflag, _ = rt.cf_split_pmis(plan_off, S_slots, seed)
+    cflag = cflag.view(-1, 1)
+    return cflag if A.is_cuda else cflag.cpu()
+
+
+def runDirectInterp(A, S, N=None, splitting=None, coarse_rows="reference"):
+    """Prolongator P (sparse [n, n_coarse]) from direct interpolation  (VCycle.py:94-137).
+    P = [I + W](:, C) is assembled sparse by glab_interp_* (the reference goes through a dense
+    n x n matrix, :129-134).  coarse_rows="identity" applies the MATLAB twin's rule for coarse
+    rows (matlab/test_direct_interpolation.m:130-132) instead of keeping their W entries."""
     op = _operator(A)
     n = op.n
+    dt = op.off_attr.dtype
     split = default_splitting(n, op.device) if splitting is None else _place(op, splitting).reshape(-1)
-    split = split.to(op.off_attr.dtype)
-    e_di = torch.hstack([op.off_attr, _place(op, S).reshape(-1, 1).to(op.off_attr.dtype)])
-    v_di = torch.hstack([op.diag.to(op.off_attr.dtype), split.view(-1, 1)])
-    w = DIGNN(v_di, op.off_index, e_di, None)
-    coarse = split > 0
-    new_id = torch.cumsum(coarse.to(torch.int64), 0) - 1
-    rows, cols = op.off_index[0], op.off_index[1]
-    keep = coarse[cols] & ((w != 0) | torch.isnan(w))   # .to_sparse() of the reference drops exact zeros
-    cidx = torch.nonzero(coarse).reshape(-1)
-    p_rows = torch.cat([rows[keep], cidx])
-    p_cols = torch.cat([new_id[cols[keep]], new_id[cidx]])
-    p_vals = torch.cat([w[keep], torch.ones(cidx.numel(), dtype=w.dtype, device=op.device)])
-    P = torch.sparse_coo_tensor(torch.stack([p_rows, p_cols]), p_vals, (n, int(cidx.numel()))).coalesce()
+    split = split.to(dt)
+    e_di = torch.hstack([op.off_attr, _place(op, S).reshape(-1, 1).to(dt)])
+    v_di = torch.hstack([op.diag.to(dt), split.view(-1, 1)])
+    w = DIGNN(v_di, op.off_index, e_di, None)                                  # :123
+    plan_off = rt.get_plan(op.off_index, n)
+    mode = {"reference": 0, "identity": 1}[coarse_rows]
+    pi, pv, nc = rt.interp_assemble(plan_off, rt.slot_order(plan_off, w), split, mode)   # :126-137
+    P = torch.sparse_coo_tensor(pi, pv, (n, nc), is_coalesced=True)
     return P if A.is_cuda else P.cpu()
 
 
@@ -143,30 +158,37 @@ def runJacobi(n_iters, w, A, b, x):
 
 
 class _TwoGrid:
-    def __init__(self, A, splitting):
+    def __init__(self, A, splitting, coarse_rows="reference"):
         op = _operator(A)
         S = runSOC(A)
-        P = runDirectInterp(A, S, None, splitting)
+        P = runDirectInterp(A, S, None, splitting, coarse_rows)
         P = rt.to_device(P, op.device).coalesce()
-        Ad = rt.to_device(A, op.device).coalesce().to(P.dtype)
-        self.Ac = torch.sparse.mm(P.t(), torch.sparse.mm(Ad, P)).coalesce()      # VCycle.py:209
         self.P = P
+        n, nc = P.shape
         pi, pv = P.indices().contiguous(), P.values().contiguous()
-        self.plan_P = rt.Plan.from_coo(pi, P.shape[0], P.shape[1])
+        self.plan_P = rt.Plan.from_coo(pi, n, nc)
         self.vals_P = rt.get_vals(self.plan_P, pv.view(-1, 1))
         ti = torch.stack([pi[1], pi[0]]).contiguous()
-        self.plan_PT = rt.Plan.from_coo(ti, P.shape[1], P.shape[0])
+        self.plan_PT = rt.Plan.from_coo(ti, nc, n)
         self.vals_PT = rt.get_vals(self.plan_PT, pv.view(-1, 1))
+        # Galerkin operator A_c = P^T (A P), VCycle.py:209, as two device SpGEMMs (glab_spgemm_*)
+        plan_A = rt.get_plan(op.edge_index, n)
+        vals_A = rt.get_vals(plan_A, op.edge_attr, 0, pv.dtype)
+        ap_i, ap_v = rt.spgemm(plan_A, vals_A, self.plan_P, self.vals_P)
+        plan_AP = rt.Plan.from_coo(ap_i, n, nc)
+        ac_i, ac_v = rt.spgemm(self.plan_PT, self.vals_PT, plan_AP, ap_v)
+        self.Ac = torch.sparse_coo_tensor(ac_i, ac_v, (nc, nc), is_coalesced=True)
         self._keep = (pi, pv, ti)
         self.fast = {}
 
 
-def _two_grid(A, splitting):
+def _two_grid(A, splitting, coarse_rows="reference"):
     op = _operator(A)
-    key = "two_grid" if splitting is None else ("two_grid", splitting.data_ptr(), splitting._version)
+    key = ("two_grid", coarse_rows) if splitting is None else ("two_grid", coarse_rows, splitting.data_ptr(),
+                                                              splitting._version)
     tg = op.hierarchy.get(key)
     if tg is None:
-        tg = _TwoGrid(A, splitting)
+        tg = _TwoGrid(A, splitting, coarse_rows)
         op.hierarchy[key] = tg
     return tg
 

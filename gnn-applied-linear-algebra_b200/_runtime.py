@@ -528,3 +528,67 @@ def direct_interp(plan, vals, S_slots, diag, cflag):
     _call("direct_interp", vals.dtype, plan.device, plan.handle, ptr(vals), ptr(S_slots), ptr(diag),
           ptr(cflag), ptr(w), stream_ptr())
     return w
+
+
+# --------------------------------------------------------------------------- AMG setup (device)
+def interp_assemble(plan_off, w_slots, cflag, mode=0):
+    """Sparse prolongator P = [I + W](:, C) from the DirectInterpGNN weights (slot order) and the
+    C/F flags: returns (edge_index int64 [2, nnz_P] sorted by (row, col), values [nnz_P],
+    n_coarse).  mode 0 = Python reference (VCycle.py:126-137), 1 = coarse rows are identity rows
+    (matlab/test_direct_interpolation.m:130-132)."""
+    dev, n, dt = plan_off.device, plan_off.n_rows, w_slots.dtype
+    cflag = dense(to_device(cflag, dev, dt).reshape(-1))
+    prow = torch.empty(n + 1, dtype=torch.int32, device=dev)
+    cid = torch.empty(n + 1, dtype=torch.int32, device=dev)
+    nnz_p, n_coarse = ctypes.c_int64(), ctypes.c_int64()
+    _call("interp_count", dt, dev, plan_off.handle, ptr(w_slots), ptr(cflag), int(mode), ptr(prow), ptr(cid),
+          ctypes.byref(nnz_p), ctypes.byref(n_coarse), stream_ptr())
+    ei = torch.empty((2, nnz_p.value), dtype=torch.int64, device=dev)
+    vals = torch.empty(nnz_p.value, dtype=dt, device=dev)
+    if nnz_p.value:
+        _call("interp_fill", dt, dev, plan_off.handle, ptr(w_slots), ptr(cflag), int(mode), ptr(prow), ptr(cid),
+              ptr(ei[0]), ptr(ei[1]), ptr(vals), stream_ptr())
+    return ei, vals, int(n_coarse.value)
+
+
+def spgemm(plan_x, vals_x, plan_y, vals_y):
+    """Z = X * Y (expand - sort - compress on the device): returns (edge_index int64 [2, nnz_Z]
+    sorted by (row, col) without duplicates, values [nnz_Z]) -- the reference's COO layout."""
+    global launch_count
+    dev, dt = plan_x.device, vals_x.dtype
+    if vals_y.dtype != dt:
+        raise GlabError("spgemm: operand dtypes differ (%s, %s)" % (dt, vals_y.dtype))
+    scratch = torch.zeros(1, dtype=torch.int64, device=dev)
+    n_prod = ctypes.c_int64()
+    with torch.cuda.device(dev):
+        launch_count += 1
+        check(lib.glab_spgemm_products(plan_x.handle, plan_y.handle, ptr(scratch), ctypes.byref(n_prod),
+                                       stream_ptr()), "glab_spgemm_products")
+        ws_bytes = int(lib.glab_spgemm_workspace_bytes(plan_x.n_rows, n_prod.value, vals_x.element_size()))
+    if ws_bytes < 0:
+        check(ws_bytes, "glab_spgemm_workspace_bytes")
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+    nnz = ctypes.c_int64()
+    _call("spgemm_symbolic", dt, dev, plan_x.handle, ptr(vals_x), plan_y.handle, ptr(vals_y), ptr(ws), ws_bytes,
+          n_prod.value, ctypes.byref(nnz), stream_ptr())
+    ei = torch.empty((2, nnz.value), dtype=torch.int64, device=dev)
+    vals = torch.empty(nnz.value, dtype=dt, device=dev)
+    if nnz.value:
+        _call("spgemm_numeric", dt, dev, plan_x.handle, plan_y.handle, ptr(ws), ws_bytes, n_prod.value, nnz.value,
+              ptr(ei[0]), ptr(ei[1]), ptr(vals), stream_ptr())
+    return ei, vals
+
+
+def cf_split_pmis(plan_off, S_slots, seed=0):
+    """PMIS coarse/fine splitting on the strength graph (strong <=> S > 0): returns (cflag [n] in
+    S's dtype with 1 = coarse, number of rounds).  Bit-exact against oracle/cf_split.py."""
+    dev, n, dt = plan_off.device, plan_off.n_rows, S_slots.dtype
+    ws_bytes = int(lib.glab_cf_split_workspace_bytes(n))
+    if ws_bytes < 0:
+        check(ws_bytes, "glab_cf_split_workspace_bytes")
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+    cflag = torch.empty(n, dtype=dt, device=dev)
+    rounds = ctypes.c_int32()
+    _call("cf_split_pmis", dt, dev, plan_off.handle, ptr(S_slots), ctypes.c_uint32(int(seed) & 0xFFFFFFFF), ptr(ws),
+          ws_bytes, ptr(cflag), ctypes.byref(rounds), stream_ptr())
+    return cflag, int(rounds.value)

@@ -1,0 +1,569 @@
+// glab_setup.cu -- AMG setup on the device: the glue either side of the SOC / direct-interpolation
+// layers in the reference's two-grid cycle.
+//
+//   glab_interp_*    prolongator P = [I + W](:, C) assembled SPARSE, sorted COO, from the per-edge
+//                    weights of DirectInterpGNN.  Replaces VCycle.py:126-137 (dense eye(n) + W,
+//                    column slice, .to_sparse()).
+//   glab_spgemm_*    C = X * Y for two CSR plans (expand - sort - compress), used twice for the
+//                    Galerkin operator A_c = P^T (A P).  Replaces VCycle.py:209 (torch.sparse @).
+//   glab_cf_split_*  PMIS coarse/fine splitting on the strength graph with integer keys
+//                    (deterministic, order-independent).  Stands in for pyamg's CLJP call at
+//                    VCycle.py:114 / DirectInterpGNN.py:194 (un-pinned third-party, absent).
+//
+// All of this is SETUP work (once per operator), HBM-bound integer/key traffic; the radix sort and
+// the scans are CUB device primitives, everything else is hand-written.  Duplicates produced by the
+// expansion are summed SEQUENTIALLY in expansion order (X slot order, then Y slot order; the radix
+// sort is stable), so the result is deterministic and independent of the launch geometry.
+#include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_scan.cuh>
+#include <cub/device/device_select.cuh>
+#include <thrust/iterator/counting_iterator.h>
+#include "glab_common.cuh"
+
+namespace glab {
+
+static int grid1d(int64_t n, int sm_count, int threads = 256) {
+  int64_t b = (n + threads - 1) / threads;
+  const int64_t cap = (int64_t)sm_count * 32;
+  if (b < 1) b = 1;
+  return (int)(b < cap ? b : cap);
+}
+
+static inline size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
+
+static int bits_for(int64_t n) {  // bits needed to hold values in [0, n)
+  int b = 1;
+  while (((int64_t)1 << b) < n) ++b;
+  return b;
+}
+
+// ============================================================================ prolongator assembly
+// Entry (i, j) of W survives in P when j is a coarse point and the weight is not an exact zero
+// (.to_sparse() of the reference drops exact zeros, NaN is kept: VCycle.py:129-137).
+// mode 0: the Python reference as shipped -- coarse rows keep their (NaN) W entries.
+// mode 1: the MATLAB twin -- coarse rows are identity rows (test_direct_interpolation.m:130-132).
+template <typename T>
+__device__ __forceinline__ bool keeps(T w, T cj) { return cj > T(0) && !(w == T(0)); }
+
+template <typename T>
+__global__ void k_interp_count(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ colidx,
+                               const T* __restrict__ w, const T* __restrict__ cflag, int mode,
+                               int64_t n, int32_t* __restrict__ cnt, int32_t* __restrict__ cid) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i <= n;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    if (i == n) {  // sentinel so that the exclusive scans deliver the totals in slot n
+      cnt[n] = 0;
+      cid[n] = 0;
+      continue;
+    }
+    const bool coarse = cflag[i] > T(0);
+    int c = coarse ? 1 : 0;
+    if (!(coarse && mode == 1)) {
+      const int e1 = rowptr[i + 1];
+      for (int e = rowptr[i]; e < e1; ++e) c += keeps(w[e], cflag[colidx[e]]) ? 1 : 0;
+    }
+    cnt[i] = c;
+    cid[i] = coarse ? 1 : 0;
+  }
+}
+
+// Row i of P in ascending coarse-column order: the kept W entries (ascending when the row of A is,
+// as in every coalesced operator) with the identity entry (i, cid[i]) merged in at its place.
+template <typename T>
+__global__ void k_interp_fill(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ colidx,
+                              const T* __restrict__ w, const T* __restrict__ cflag, int mode,
+                              int64_t n, const int32_t* __restrict__ prow,
+                              const int32_t* __restrict__ cid, int64_t* __restrict__ out_row,
+                              int64_t* __restrict__ out_col, T* __restrict__ out_val) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    const bool coarse = cflag[i] > T(0);
+    int64_t o = prow[i];
+    bool placed = !coarse;
+    if (!(coarse && mode == 1)) {
+      const int e1 = rowptr[i + 1];
+      for (int e = rowptr[i]; e < e1; ++e) {
+        const int j = colidx[e];
+        const T we = w[e];
+        if (!keeps(we, cflag[j])) continue;
+        if (!placed && j > i) {
+          out_row[o] = i; out_col[o] = cid[i]; out_val[o] = T(1); ++o;
+          placed = true;
+        }
+        out_row[o] = i; out_col[o] = cid[j]; out_val[o] = we; ++o;
+      }
+    }
+    if (!placed) { out_row[o] = i; out_col[o] = cid[i]; out_val[o] = T(1); }
+  }
+}
+
+template <typename T>
+static int interp_count(const glab_plan* A, const T* w, const T* cflag, int mode, int32_t* prow,
+                        int32_t* cid, int64_t* nnz_p, int64_t* n_coarse, void* stream_) {
+  if (!A || !prow || !cid || !nnz_p || !n_coarse || (mode != 0 && mode != 1)) return GLAB_E_ARG;
+  const int64_t n = A->n_rows;
+  if ((n > 0 && !cflag) || (A->nnz > 0 && !w)) return GLAB_E_ARG;
+  cudaStream_t st = as_stream(stream_);
+  k_interp_count<T><<<grid1d(n + 1, A->sm_count), 256, 0, st>>>(A->rowptr, A->colidx, w, cflag, mode, n,
+                                                                prow, cid);
+  GLAB_CUDA(cudaGetLastError());
+  size_t tb = 0;
+  GLAB_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tb, prow, prow, (int)(n + 1), st));
+  void* tmp = nullptr;
+  GLAB_CUDA(cudaMallocAsync(&tmp, tb ? tb : 16, st));  // a few KB of scan state, stream-ordered
+  cudaError_t e = cub::DeviceScan::ExclusiveSum(tmp, tb, prow, prow, (int)(n + 1), st);
+  if (e == cudaSuccess) e = cub::DeviceScan::ExclusiveSum(tmp, tb, cid, cid, (int)(n + 1), st);
+  int32_t totals[2] = {0, 0};
+  if (e == cudaSuccess) e = cudaMemcpyAsync(&totals[0], prow + n, 4, cudaMemcpyDeviceToHost, st);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(&totals[1], cid + n, 4, cudaMemcpyDeviceToHost, st);
+  cudaFreeAsync(tmp, st);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+  if (e != cudaSuccess) return (int)e;
+  *nnz_p = totals[0];
+  *n_coarse = totals[1];
+  return 0;
+}
+
+template <typename T>
+static int interp_fill(const glab_plan* A, const T* w, const T* cflag, int mode, const int32_t* prow,
+                       const int32_t* cid, int64_t* out_row, int64_t* out_col, T* out_val,
+                       void* stream_) {
+  if (!A || !prow || !cid || (mode != 0 && mode != 1)) return GLAB_E_ARG;
+  const int64_t n = A->n_rows;
+  if (n == 0) return 0;
+  if (!cflag || (A->nnz > 0 && !w) || !out_row || !out_col || !out_val) return GLAB_E_ARG;
+  k_interp_fill<T><<<grid1d(n, A->sm_count), 256, 0, as_stream(stream_)>>>(
+      A->rowptr, A->colidx, w, cflag, mode, n, prow, cid, out_row, out_col, out_val);
+  return (int)cudaGetLastError();
+}
+
+// ============================================================================ SpGEMM (ESC)
+// Workspace layout (caller-owned, one allocation).  hdr[0] = number of distinct (row, col) keys,
+// hdr[1] = which of the two key/value buffers holds the sorted result.
+struct SpgemmWs {
+  size_t hdr, rowoff, keys[2], vals[2], cub, total;
+  size_t cub_bytes;
+};
+
+struct HeadOp {  // p starts a run of equal keys
+  const uint64_t* k;
+  __host__ __device__ __forceinline__ bool operator()(int p) const { return p == 0 || k[p] != k[p - 1]; }
+};
+
+template <typename T>
+static int spgemm_layout(int64_t n_rows_x, int64_t n_products, SpgemmWs* L) {
+  if (n_rows_x < 0 || n_products < 0) return GLAB_E_ARG;
+  if (n_products >= (int64_t)INT32_MAX - 64) return GLAB_E_RANGE;
+  const size_t P = (size_t)n_products + 2;
+  size_t sort_b = 0, sel_b = 0, scan_b = 0;
+  cub::DoubleBuffer<uint64_t> dk(nullptr, nullptr);
+  cub::DoubleBuffer<T> dv(nullptr, nullptr);
+  GLAB_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, sort_b, dk, dv, (int)n_products, 0, 64, (cudaStream_t)0));
+  HeadOp op{nullptr};
+  GLAB_CUDA(cub::DeviceSelect::If(nullptr, sel_b, thrust::counting_iterator<int>(0), (int32_t*)nullptr,
+                                  (int64_t*)nullptr, (int)n_products, op, (cudaStream_t)0));
+  GLAB_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, scan_b, (int64_t*)nullptr, (int64_t*)nullptr,
+                                          (int)(n_rows_x + 1), (cudaStream_t)0));
+  size_t cb = sort_b > sel_b ? sort_b : sel_b;
+  if (scan_b > cb) cb = scan_b;
+  size_t o = 0;
+  L->hdr = o;      o += 256;
+  L->rowoff = o;   o += align256((size_t)(n_rows_x + 2) * 8);
+  L->keys[0] = o;  o += align256(P * 8);
+  L->keys[1] = o;  o += align256(P * 8);
+  L->vals[0] = o;  o += align256(P * sizeof(T));
+  L->vals[1] = o;  o += align256(P * sizeof(T));
+  L->cub = o;      o += align256(cb + 16);
+  L->cub_bytes = cb;
+  L->total = o;
+  return 0;
+}
+
+// products of X row r = sum over its slots (r, j) of nnz(Y row j)
+__global__ void k_spgemm_count(const int32_t* __restrict__ xrp, const int32_t* __restrict__ xci,
+                               const int32_t* __restrict__ yrp, int64_t n, int64_t* __restrict__ cnt,
+                               unsigned long long* __restrict__ total) {
+  unsigned long long local = 0;
+  for (int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; r <= n;
+       r += (int64_t)gridDim.x * blockDim.x) {
+    int64_t c = 0;
+    if (r < n) {
+      const int e1 = xrp[r + 1];
+      for (int e = xrp[r]; e < e1; ++e) {
+        const int j = xci[e];
+        c += yrp[j + 1] - yrp[j];
+      }
+    }
+    if (cnt) cnt[r] = c;
+    local += (unsigned long long)c;
+  }
+  if (total) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) local += __shfl_xor_sync(0xffffffffu, local, o);
+    if ((threadIdx.x & 31) == 0 && local) atomicAdd(total, local);
+  }
+}
+
+// 8 lanes per X row: the lanes walk the row's slots together and spread over each Y row, so a
+// product's position is rowoff[r] + (products of the earlier slots) + (position in the Y row):
+// expansion order == X slot order, then Y slot order.
+template <typename T>
+__global__ void k_spgemm_expand(const int32_t* __restrict__ xrp, const int32_t* __restrict__ xci,
+                                const T* __restrict__ xv, const int32_t* __restrict__ yrp,
+                                const int32_t* __restrict__ yci, const T* __restrict__ yv, int64_t n,
+                                const int64_t* __restrict__ rowoff, int col_bits,
+                                uint64_t* __restrict__ keys, T* __restrict__ vals) {
+  const int lane = threadIdx.x & 7;
+  const int64_t group = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 3;
+  const int64_t ngroups = ((int64_t)gridDim.x * blockDim.x) >> 3;
+  for (int64_t r = group; r < n; r += ngroups) {
+    int64_t o = rowoff[r];
+    const int e1 = xrp[r + 1];
+    for (int e = xrp[r]; e < e1; ++e) {
+      const int j = xci[e];
+      const T a = xv[e];
+      const int y0 = yrp[j], y1 = yrp[j + 1];
+      for (int t = y0 + lane; t < y1; t += 8) {
+        keys[o + (t - y0)] = ((uint64_t)r << col_bits) | (uint64_t)(uint32_t)yci[t];
+        vals[o + (t - y0)] = a * yv[t];
+      }
+      o += y1 - y0;
+    }
+  }
+}
+
+__global__ void k_spgemm_store_hdr(int64_t* hdr, int selector) { hdr[1] = selector; }
+
+template <typename T>
+__global__ void k_spgemm_compress(const int64_t* __restrict__ hdr, const uint64_t* __restrict__ k0,
+                                  const uint64_t* __restrict__ k1, const T* __restrict__ v0,
+                                  const T* __restrict__ v1, int64_t n_products, int64_t nnz_out,
+                                  int col_bits, int64_t* __restrict__ out_row,
+                                  int64_t* __restrict__ out_col, T* __restrict__ out_val) {
+  const int sel = (int)hdr[1];
+  const uint64_t* __restrict__ keys = sel ? k1 : k0;
+  const T* __restrict__ vals = sel ? v1 : v0;
+  // the run starts live in the key buffer the sort left free
+  const int32_t* __restrict__ heads = reinterpret_cast<const int32_t*>(sel ? k0 : k1);
+  const uint64_t cmask = (col_bits >= 64) ? ~0ull : ((1ull << col_bits) - 1);
+  for (int64_t u = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; u < nnz_out;
+       u += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t p0 = heads[u];
+    const int64_t p1 = (u + 1 < nnz_out) ? (int64_t)heads[u + 1] : n_products;
+    T acc = vals[p0];
+    for (int64_t p = p0 + 1; p < p1; ++p) acc = acc + vals[p];
+    const uint64_t key = keys[p0];
+    out_row[u] = (int64_t)(key >> col_bits);
+    out_col[u] = (int64_t)(key & cmask);
+    out_val[u] = acc;
+  }
+}
+
+static int spgemm_check(const glab_plan* X, const glab_plan* Y) {
+  if (!X || !Y) return GLAB_E_ARG;
+  if (X->n_cols != Y->n_rows) return GLAB_E_ARG;
+  if (bits_for(X->n_rows) + bits_for(Y->n_cols) > 63) return GLAB_E_RANGE;
+  return 0;
+}
+
+template <typename T>
+static int spgemm_symbolic(const glab_plan* X, const T* xv, const glab_plan* Y, const T* yv, void* ws,
+                           int64_t ws_bytes, int64_t n_products, int64_t* nnz_out, void* stream_) {
+  int rc = spgemm_check(X, Y);
+  if (rc) return rc;
+  if (!nnz_out || !ws) return GLAB_E_ARG;
+  if ((X->nnz > 0 && !xv) || (Y->nnz > 0 && !yv)) return GLAB_E_ARG;
+  SpgemmWs L;
+  rc = spgemm_layout<T>(X->n_rows, n_products, &L);
+  if (rc) return rc;
+  if (ws_bytes < (int64_t)L.total) return GLAB_E_ARG;
+  cudaStream_t st = as_stream(stream_);
+  char* base = reinterpret_cast<char*>(ws);
+  int64_t* hdr = reinterpret_cast<int64_t*>(base + L.hdr);
+  int64_t* rowoff = reinterpret_cast<int64_t*>(base + L.rowoff);
+  uint64_t* k[2] = {reinterpret_cast<uint64_t*>(base + L.keys[0]), reinterpret_cast<uint64_t*>(base + L.keys[1])};
+  T* v[2] = {reinterpret_cast<T*>(base + L.vals[0]), reinterpret_cast<T*>(base + L.vals[1])};
+  void* ctmp = base + L.cub;
+  size_t cb = L.cub_bytes;
+  GLAB_CUDA(cudaMemsetAsync(hdr, 0, 256, st));
+  if (n_products == 0) {
+    *nnz_out = 0;
+    return 0;
+  }
+  const int64_t n = X->n_rows;
+  k_spgemm_count<<<grid1d(n + 1, X->sm_count), 256, 0, st>>>(X->rowptr, X->colidx, Y->rowptr, n, rowoff, nullptr);
+  GLAB_CUDA(cudaGetLastError());
+  GLAB_CUDA(cub::DeviceScan::ExclusiveSum(ctmp, cb, rowoff, rowoff, (int)(n + 1), st));
+  const int col_bits = bits_for(Y->n_cols);
+  k_spgemm_expand<T><<<grid1d(n * 8, X->sm_count), 256, 0, st>>>(X->rowptr, X->colidx, xv, Y->rowptr, Y->colidx,
+                                                              yv, n, rowoff, col_bits, k[0], v[0]);
+  GLAB_CUDA(cudaGetLastError());
+  cub::DoubleBuffer<uint64_t> dk(k[0], k[1]);
+  cub::DoubleBuffer<T> dv(v[0], v[1]);
+  cb = L.cub_bytes;
+  GLAB_CUDA(cub::DeviceRadixSort::SortPairs(ctmp, cb, dk, dv, (int)n_products, 0,
+                                            col_bits + bits_for(X->n_rows), st));
+  const int sel = dk.selector;
+  if (dv.selector != sel) return GLAB_E_ARG;  // cannot happen: CUB flips both buffers together
+  k_spgemm_store_hdr<<<1, 1, 0, st>>>(hdr, sel);
+  HeadOp op{k[sel]};
+  cb = L.cub_bytes;
+  GLAB_CUDA(cub::DeviceSelect::If(ctmp, cb, thrust::counting_iterator<int>(0),
+                                  reinterpret_cast<int32_t*>(k[sel ^ 1]), hdr, (int)n_products, op, st));
+  int64_t h = 0;
+  GLAB_CUDA(cudaMemcpyAsync(&h, hdr, 8, cudaMemcpyDeviceToHost, st));
+  GLAB_CUDA(cudaStreamSynchronize(st));
+  GLAB_CUDA(cudaGetLastError());
+  *nnz_out = h;
+  return 0;
+}
+
+template <typename T>
+static int spgemm_numeric(const glab_plan* X, const glab_plan* Y, void* ws, int64_t ws_bytes,
+                          int64_t n_products, int64_t nnz_out, int64_t* out_row, int64_t* out_col,
+                          T* out_val, void* stream_) {
+  int rc = spgemm_check(X, Y);
+  if (rc) return rc;
+  if (!ws || nnz_out < 0 || nnz_out > n_products) return GLAB_E_ARG;
+  if (nnz_out == 0) return 0;
+  if (!out_row || !out_col || !out_val) return GLAB_E_ARG;
+  SpgemmWs L;
+  rc = spgemm_layout<T>(X->n_rows, n_products, &L);
+  if (rc) return rc;
+  if (ws_bytes < (int64_t)L.total) return GLAB_E_ARG;
+  char* base = reinterpret_cast<char*>(ws);
+  k_spgemm_compress<T><<<grid1d(nnz_out, X->sm_count), 256, 0, as_stream(stream_)>>>(
+      reinterpret_cast<const int64_t*>(base + L.hdr), reinterpret_cast<const uint64_t*>(base + L.keys[0]),
+      reinterpret_cast<const uint64_t*>(base + L.keys[1]), reinterpret_cast<const T*>(base + L.vals[0]),
+      reinterpret_cast<const T*>(base + L.vals[1]), n_products, nnz_out, bits_for(Y->n_cols), out_row, out_col,
+      out_val);
+  return (int)cudaGetLastError();
+}
+
+// ============================================================================ PMIS C/F splitting
+// state: 0 undecided, 1 coarse, 2 fine.  key_i = (lambda_i + 1) << 32 | mix32(i + seed) with
+// lambda_i = number of rows that strongly depend on i; mix32 is a bijection of uint32, so all keys
+// are distinct and positive: every comparison is an integer comparison, no ties, no rounding.
+__device__ __forceinline__ uint32_t mix32(uint32_t x) {  // murmur3 finaliser (bijective)
+  x ^= x >> 16; x *= 0x85ebca6bu; x ^= x >> 13; x *= 0xc2b2ae35u; x ^= x >> 16;
+  return x;
+}
+
+struct PmisWs {
+  size_t key, maxnbr, lambda, state, counter, total;
+};
+
+static int pmis_layout(int64_t n, PmisWs* L) {
+  if (n < 0) return GLAB_E_ARG;
+  size_t o = 0;
+  L->counter = o; o += 256;
+  L->key = o;     o += align256((size_t)(n + 1) * 8);
+  L->maxnbr = o;  o += align256((size_t)(n + 1) * 8);
+  L->lambda = o;  o += align256((size_t)(n + 1) * 4);
+  L->state = o;   o += align256((size_t)(n + 1) * 4);
+  L->total = o;
+  return 0;
+}
+
+template <typename T>
+__global__ void k_pmis_lambda(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ colidx,
+                              const T* __restrict__ S, int64_t n, uint32_t* __restrict__ lambda) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    const int e1 = rowptr[i + 1];
+    for (int e = rowptr[i]; e < e1; ++e)
+      if (S[e] > T(0) && colidx[e] != i) atomicAdd(lambda + colidx[e], 1u);
+  }
+}
+
+__global__ void k_pmis_keys(const uint32_t* __restrict__ lambda, uint32_t seed, int64_t n,
+                            unsigned long long* __restrict__ key) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n;
+       i += (int64_t)gridDim.x * blockDim.x)
+    key[i] = ((unsigned long long)(lambda[i] + 1u) << 32) | (unsigned long long)mix32((uint32_t)i + seed);
+}
+
+// largest key among the undecided strong neighbours (either direction) of every undecided vertex
+template <typename T>
+__global__ void k_pmis_neighbour_max(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ colidx,
+                                     const T* __restrict__ S, int64_t n, const int32_t* __restrict__ state,
+                                     const unsigned long long* __restrict__ key,
+                                     unsigned long long* __restrict__ maxnbr) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    if (state[i] != 0) continue;
+    const unsigned long long ki = key[i];
+    unsigned long long m = 0;
+    const int e1 = rowptr[i + 1];
+    for (int e = rowptr[i]; e < e1; ++e) {
+      if (!(S[e] > T(0))) continue;
+      const int j = colidx[e];
+      if (j == i || state[j] != 0) continue;
+      const unsigned long long kj = key[j];
+      m = kj > m ? kj : m;
+      atomicMax(maxnbr + j, ki);
+    }
+    if (m) atomicMax(maxnbr + i, m);
+  }
+}
+
+__global__ void k_pmis_select(int64_t n, int32_t* __restrict__ state,
+                              const unsigned long long* __restrict__ key,
+                              unsigned long long* __restrict__ maxnbr) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    if (state[i] == 0 && key[i] > maxnbr[i]) state[i] = 1;
+    maxnbr[i] = 0;
+  }
+}
+
+// undecided rows that strongly depend on a coarse point become fine; counts what is left.
+// Only 0 -> 2 transitions happen here and only "== 1" is tested, so the kernel is order-independent.
+template <typename T>
+__global__ void k_pmis_fine(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ colidx,
+                            const T* __restrict__ S, int64_t n, int32_t* __restrict__ state,
+                            unsigned long long* __restrict__ undecided) {
+  unsigned long long left = 0;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    if (state[i] != 0) continue;
+    bool fine = false;
+    const int e1 = rowptr[i + 1];
+    for (int e = rowptr[i]; e < e1 && !fine; ++e)
+      fine = (S[e] > T(0)) && colidx[e] != i && state[colidx[e]] == 1;
+    if (fine) state[i] = 2; else ++left;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) left += __shfl_xor_sync(0xffffffffu, left, o);
+  if ((threadIdx.x & 31) == 0 && left) atomicAdd(undecided, left);
+}
+
+template <typename T>
+__global__ void k_pmis_flags(const int32_t* __restrict__ state, int64_t n, T* __restrict__ cflag) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n;
+       i += (int64_t)gridDim.x * blockDim.x)
+    cflag[i] = state[i] == 1 ? T(1) : T(0);
+}
+
+template <typename T>
+static int cf_split_pmis(const glab_plan* A, const T* S, uint32_t seed, void* ws, int64_t ws_bytes,
+                         T* cflag, int32_t* rounds_out, void* stream_) {
+  if (!A || !ws) return GLAB_E_ARG;
+  const int64_t n = A->n_rows;
+  if (A->n_cols != n) return GLAB_E_ARG;
+  if ((n > 0 && !cflag) || (A->nnz > 0 && !S)) return GLAB_E_ARG;
+  PmisWs L;
+  int rc = pmis_layout(n, &L);
+  if (rc) return rc;
+  if (ws_bytes < (int64_t)L.total) return GLAB_E_ARG;
+  if (rounds_out) *rounds_out = 0;
+  if (n == 0) return 0;
+  cudaStream_t st = as_stream(stream_);
+  char* base = reinterpret_cast<char*>(ws);
+  unsigned long long* counter = reinterpret_cast<unsigned long long*>(base + L.counter);
+  unsigned long long* key = reinterpret_cast<unsigned long long*>(base + L.key);
+  unsigned long long* maxnbr = reinterpret_cast<unsigned long long*>(base + L.maxnbr);
+  uint32_t* lambda = reinterpret_cast<uint32_t*>(base + L.lambda);
+  int32_t* state = reinterpret_cast<int32_t*>(base + L.state);
+  GLAB_CUDA(cudaMemsetAsync(ws, 0, L.total, st));
+  const int gv = grid1d(n, A->sm_count);
+  if (A->nnz > 0) k_pmis_lambda<T><<<gv, 256, 0, st>>>(A->rowptr, A->colidx, S, n, lambda);
+  k_pmis_keys<<<gv, 256, 0, st>>>(lambda, seed, n, key);
+  int rounds = 0;
+  unsigned long long left = (unsigned long long)n;
+  while (left) {
+    if (++rounds > 100000) return GLAB_E_ARG;  // cannot happen: the largest undecided key wins each round
+    k_pmis_neighbour_max<T><<<gv, 256, 0, st>>>(A->rowptr, A->colidx, S, n, state, key, maxnbr);
+    k_pmis_select<<<gv, 256, 0, st>>>(n, state, key, maxnbr);
+    GLAB_CUDA(cudaMemsetAsync(counter, 0, 8, st));
+    k_pmis_fine<T><<<gv, 256, 0, st>>>(A->rowptr, A->colidx, S, n, state, counter);
+    GLAB_CUDA(cudaMemcpyAsync(&left, counter, 8, cudaMemcpyDeviceToHost, st));
+    GLAB_CUDA(cudaStreamSynchronize(st));
+  }
+  k_pmis_flags<T><<<gv, 256, 0, st>>>(state, n, cflag);
+  GLAB_CUDA(cudaGetLastError());
+  if (rounds_out) *rounds_out = rounds;
+  return 0;
+}
+
+}  // namespace glab
+
+using namespace glab;
+
+extern "C" int glab_interp_count_f32(const glab_plan* A, const float* w, const float* c, int mode, int32_t* prow,
+                                     int32_t* cid, int64_t* nnz_p, int64_t* n_coarse, void* s) {
+  return interp_count<float>(A, w, c, mode, prow, cid, nnz_p, n_coarse, s);
+}
+extern "C" int glab_interp_count_f64(const glab_plan* A, const double* w, const double* c, int mode, int32_t* prow,
+                                     int32_t* cid, int64_t* nnz_p, int64_t* n_coarse, void* s) {
+  return interp_count<double>(A, w, c, mode, prow, cid, nnz_p, n_coarse, s);
+}
+extern "C" int glab_interp_fill_f32(const glab_plan* A, const float* w, const float* c, int mode,
+                                    const int32_t* prow, const int32_t* cid, int64_t* orow, int64_t* ocol,
+                                    float* oval, void* s) {
+  return interp_fill<float>(A, w, c, mode, prow, cid, orow, ocol, oval, s);
+}
+extern "C" int glab_interp_fill_f64(const glab_plan* A, const double* w, const double* c, int mode,
+                                    const int32_t* prow, const int32_t* cid, int64_t* orow, int64_t* ocol,
+                                    double* oval, void* s) {
+  return interp_fill<double>(A, w, c, mode, prow, cid, orow, ocol, oval, s);
+}
+
+extern "C" int glab_spgemm_products(const glab_plan* X, const glab_plan* Y, void* scratch8, int64_t* n_products,
+                                    void* stream_) {
+  int rc = spgemm_check(X, Y);
+  if (rc) return rc;
+  if (!n_products || !scratch8) return GLAB_E_ARG;
+  cudaStream_t st = as_stream(stream_);
+  unsigned long long* total = reinterpret_cast<unsigned long long*>(scratch8);
+  GLAB_CUDA(cudaMemsetAsync(total, 0, 8, st));
+  if (X->n_rows > 0 && X->nnz > 0)
+    k_spgemm_count<<<grid1d(X->n_rows + 1, X->sm_count), 256, 0, st>>>(X->rowptr, X->colidx, Y->rowptr,
+                                                                      X->n_rows, nullptr, total);
+  unsigned long long h = 0;
+  GLAB_CUDA(cudaMemcpyAsync(&h, total, 8, cudaMemcpyDeviceToHost, st));
+  GLAB_CUDA(cudaStreamSynchronize(st));
+  GLAB_CUDA(cudaGetLastError());
+  *n_products = (int64_t)h;
+  return 0;
+}
+
+extern "C" int64_t glab_spgemm_workspace_bytes(int64_t n_rows_x, int64_t n_products, int elem_size) {
+  SpgemmWs L;
+  int rc = (elem_size == 8) ? spgemm_layout<double>(n_rows_x, n_products, &L)
+                            : (elem_size == 4) ? spgemm_layout<float>(n_rows_x, n_products, &L) : GLAB_E_ARG;
+  return rc ? (int64_t)(rc < 0 ? rc : -rc) : (int64_t)L.total;
+}
+
+extern "C" int glab_spgemm_symbolic_f32(const glab_plan* X, const float* xv, const glab_plan* Y, const float* yv,
+                                        void* ws, int64_t ws_bytes, int64_t n_products, int64_t* nnz_out, void* s) {
+  return spgemm_symbolic<float>(X, xv, Y, yv, ws, ws_bytes, n_products, nnz_out, s);
+}
+extern "C" int glab_spgemm_symbolic_f64(const glab_plan* X, const double* xv, const glab_plan* Y, const double* yv,
+                                        void* ws, int64_t ws_bytes, int64_t n_products, int64_t* nnz_out, void* s) {
+  return spgemm_symbolic<double>(X, xv, Y, yv, ws, ws_bytes, n_products, nnz_out, s);
+}
+extern "C" int glab_spgemm_numeric_f32(const glab_plan* X, const glab_plan* Y, void* ws, int64_t ws_bytes,
+                                       int64_t n_products, int64_t nnz_out, int64_t* orow, int64_t* ocol,
+                                       float* oval, void* s) {
+  return spgemm_numeric<float>(X, Y, ws, ws_bytes, n_products, nnz_out, orow, ocol, oval, s);
+}
+extern "C" int glab_spgemm_numeric_f64(const glab_plan* X, const glab_plan* Y, void* ws, int64_t ws_bytes,
+                                       int64_t n_products, int64_t nnz_out, int64_t* orow, int64_t* ocol,
+                                       double* oval, void* s) {
+  return spgemm_numeric<double>(X, Y, ws, ws_bytes, n_products, nnz_out, orow, ocol, oval, s);
+}
+
+extern "C" int64_t glab_cf_split_workspace_bytes(int64_t n) {
+  PmisWs L;
+  int rc = pmis_layout(n, &L);
+  return rc ? (int64_t)rc : (int64_t)L.total;
+}
+extern "C" int glab_cf_split_pmis_f32(const glab_plan* A, const float* S, uint32_t seed, void* ws, int64_t ws_bytes,
+                                      float* cflag, int32_t* rounds, void* s) {
+  return cf_split_pmis<float>(A, S, seed, ws, ws_bytes, cflag, rounds, s);
+}
+extern "C" int glab_cf_split_pmis_f64(const glab_plan* A, const double* S, uint32_t seed, void* ws, int64_t ws_bytes,
+                                      double* cflag, int32_t* rounds, void* s) {
+  return cf_split_pmis<double>(A, S, seed, ws, ws_bytes, cflag, rounds, s);
+}

@@ -373,6 +373,84 @@ int glab_rayleigh_halo_f64(const glab_plan*, const double* vals, const double* b
                            double* y_out, const double* sumsq_in, double* sums_out, void* workspace,
                            const glab_halo_step* halo, void* stream);
 
+/* ------------------------------------------------------------------------------------------
+ * AMG setup on the device: the glue either side of SOCClassicGNN /
+ * DirectInterpGNN in the reference's two-grid cycle.  Setup work, once per operator; the calls
+ * marked "host-synchronous" synchronise `stream` because they return a size to the host.
+ * ------------------------------------------------------------------------------------------ */
+
+/* Prolongator P = [I + W](:, C) as a sparse, (row, col)-sorted int64 COO.  Replaces
+ * VCycle.py:126-137 (torch.eye(n) + W, .to_dense(), column slice, .to_sparse()), which builds a
+ * dense n x n matrix.  `A_off` is the plan of the off-diagonal edges (the edge set DirectInterpGNN
+ * ran on, UtilsGNN.py:69-72) with ascending columns inside each row (any coalesced operator),
+ * w_slots[nnz] the DirectInterpGNN output in CSR slot order, cflag[n] the C/F splitting
+ * (> 0 = coarse).  An entry (i, j) of W is kept when j is coarse and w_ij is not an exact zero
+ * (NaN is kept), exactly what .to_sparse() keeps.  mode 0 = the Python reference as shipped
+ * (a coarse row keeps its W entries, which are NaN when it has no strong coarse neighbour,
+ * DirectInterpGNN.py:150); mode 1 = the MATLAB twin (coarse rows are identity rows,
+ * matlab/test_direct_interpolation.m:130-132).
+ *   count (host-synchronous): p_rowptr[n+1] = row offsets of P, coarse_id[n+1] = coarse column
+ *     number of every vertex (exclusive count of coarse points before it); returns nnz(P), n_coarse.
+ *   fill: writes the nnz(P) entries; row i holds its kept W entries in ascending column order with
+ *     the identity entry (i, coarse_id[i]) = 1 merged in.  nnz(P) must be < 2^31. */
+int glab_interp_count_f32(const glab_plan* A_off, const float* w_slots, const float* cflag, int mode,
+                          int32_t* p_rowptr, int32_t* coarse_id, int64_t* nnz_p, int64_t* n_coarse,
+                          void* stream);
+int glab_interp_count_f64(const glab_plan* A_off, const double* w_slots, const double* cflag, int mode,
+                          int32_t* p_rowptr, int32_t* coarse_id, int64_t* nnz_p, int64_t* n_coarse,
+                          void* stream);
+int glab_interp_fill_f32(const glab_plan* A_off, const float* w_slots, const float* cflag, int mode,
+                         const int32_t* p_rowptr, const int32_t* coarse_id, int64_t* out_row,
+                         int64_t* out_col, float* out_val, void* stream);
+int glab_interp_fill_f64(const glab_plan* A_off, const double* w_slots, const double* cflag, int mode,
+                         const int32_t* p_rowptr, const int32_t* coarse_id, int64_t* out_row,
+                         int64_t* out_col, double* out_val, void* stream);
+
+/* Sparse product Z = X * Y of two plans (expand - sort - compress); called twice for the Galerkin
+ * operator A_c = P^T (A P).  Replaces VCycle.py:209 (`P.t() @ (A @ P)` on torch.sparse tensors).
+ * The output is a (row, col)-sorted int64 COO without duplicates -- the reference's edge layout
+ * (UtilsGNN.py:74-78), so it can be handed to glab_plan_create and to every layer as the next
+ * operator.  Products that meet in one entry are added sequentially in expansion order (X slot
+ * order, then Y slot order): deterministic and independent of the launch geometry.
+ *   products (host-synchronous): number of scalar multiplications sum_{(i,j) in X} nnz(Y_j*);
+ *     scratch8 = 8 bytes of device memory.  Must be < 2^31 - 64 (GLAB_E_RANGE otherwise).
+ *   workspace_bytes: size of the caller-owned device workspace for that many products
+ *     (elem_size 4 or 8); negative = error code.  About (16 + 2 * elem_size) bytes per product.
+ *   symbolic (host-synchronous): expands, sorts, finds the runs; returns nnz(Z).
+ *   numeric: sums the runs and writes the nnz(Z) entries; same X, Y, workspace as symbolic. */
+int glab_spgemm_products(const glab_plan* X, const glab_plan* Y, void* scratch8, int64_t* n_products,
+                         void* stream);
+int64_t glab_spgemm_workspace_bytes(int64_t n_rows_x, int64_t n_products, int elem_size);
+int glab_spgemm_symbolic_f32(const glab_plan* X, const float* x_vals, const glab_plan* Y,
+                             const float* y_vals, void* workspace, int64_t workspace_bytes,
+                             int64_t n_products, int64_t* nnz_out, void* stream);
+int glab_spgemm_symbolic_f64(const glab_plan* X, const double* x_vals, const glab_plan* Y,
+                             const double* y_vals, void* workspace, int64_t workspace_bytes,
+                             int64_t n_products, int64_t* nnz_out, void* stream);
+int glab_spgemm_numeric_f32(const glab_plan* X, const glab_plan* Y, void* workspace,
+                            int64_t workspace_bytes, int64_t n_products, int64_t nnz_out,
+                            int64_t* out_row, int64_t* out_col, float* out_val, void* stream);
+int glab_spgemm_numeric_f64(const glab_plan* X, const glab_plan* Y, void* workspace,
+                            int64_t workspace_bytes, int64_t n_products, int64_t nnz_out,
+                            int64_t* out_row, int64_t* out_col, double* out_val, void* stream);
+
+/* Coarse/fine splitting on the strength graph (PMIS: parallel modified independent set).  Stands
+ * in for the pyamg CLJP call of the reference (VCycle.py:114, DirectInterpGNN.py:194; un-pinned
+ * third-party package, so there is no reference output to match -- parity is against
+ * oracle/cf_split.py, bit for bit).  `A_off` = plan of the off-diagonal edges, S_slots[nnz] = the
+ * SOCClassicGNN output in slot order (strong <=> S > 0, VCycle.py:90).  Vertex keys are integers
+ * ((number of rows that strongly depend on i) + 1) << 32 | mix32(i + seed), all distinct; each
+ * round the undecided vertices whose key beats every undecided strong neighbour (either direction)
+ * become coarse, then undecided rows that strongly depend on a coarse point become fine.  Every
+ * fine point ends with at least one strong coarse neighbour; vertices without strong connections
+ * become coarse.  cflag_out[n] = 1 (coarse) / 0 (fine) in the operator's dtype, the layout of
+ * vertex_attr[:,1] of DirectInterpGNN.  Host-synchronous (one read-back per round). */
+int64_t glab_cf_split_workspace_bytes(int64_t n);
+int glab_cf_split_pmis_f32(const glab_plan* A_off, const float* S_slots, uint32_t seed, void* workspace,
+                           int64_t workspace_bytes, float* cflag_out, int32_t* rounds_out, void* stream);
+int glab_cf_split_pmis_f64(const glab_plan* A_off, const double* S_slots, uint32_t seed, void* workspace,
+                           int64_t workspace_bytes, double* cflag_out, int32_t* rounds_out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

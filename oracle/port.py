@@ -391,3 +391,22 @@ def two_grid_vcycle(edge_index, A_val, b, x, splitting, n_pre=3, n_post=3, theta
                          torch.tensor([coarse_c, coarse_d]))               # :221-223,139-154
     x = x + P @ vc[:, 1].reshape(-1, 1)                                    # :226
     return run_jacobi(n_post, x)                                           # :229-231
+
+
+def prolongator(edge_index_off, w_ij, splitting, n, coarse_rows_identity=False):
+    """VCycle.py:126-137 restated on its own: P = (eye(n) + W)[:, splitting > 0].to_sparse(),
+    through the reference's DENSE n x n intermediate (small n only).  With
+    ``coarse_rows_identity`` the W entries of coarse rows are zeroed first -- the MATLAB twin's
+    rule (matlab/test_direct_interpolation.m:130-132); the Python reference keeps them (NaN when a
+    coarse row has no strong coarse neighbour)."""
+    w = w_ij.clone()
+    if coarse_rows_identity:
+        w[splitting.flatten()[edge_index_off[0]] > 0] = 0
+    W = torch.sparse_coo_tensor(edge_index_off, w, (n, n), dtype=w.dtype)
+    W = (torch.eye(n, dtype=w.dtype) + W).to_dense()                        # :129-131
+    return W[:, splitting.flatten() > 0].to_sparse().coalesce()            # :133-137
+
+
+def galerkin(A, P):
+    """VCycle.py:209 -- Ac = P^T (A P) on torch.sparse COO tensors (CPU)."""
+    return (P.t() @ (A @ P)).coalesce()

@@ -49,7 +49,7 @@ def main():
         times.append(time.perf_counter() - t0)
         norms.append(torch.norm(V.runResidual(A, b, x), dim=0))
     op = V._operator(A)
-    tg = op.hierarchy["two_grid"]
+    tg = V._two_grid(A, None)
     z, zp, zc = ei.shape[1], tg.plan_P.nnz, tg.Ac._nnz()
     work = (3 + 3 + 1) * z + 2 * zp + 4 * zc          # SpMV-bearing steps of one cycle (nnz)
     t = min(times)

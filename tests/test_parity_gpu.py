@@ -352,13 +352,13 @@ def test_c_abi_direct(G, dev):
     assert lib.glab_plan_destroy(plan) == 0
 
 
-@pytest.mark.parametrize("dt", [torch.float32, torch.float64])
-def test_large_operator_properties(G, dev, dt):
-    """Size-independent checks at a size the CPU oracle cannot reach in seconds (2048^2 rows):
+@pytest.mark.parametrize("dt,N", [(torch.float32, 4096), (torch.float64, 2048)])
+def test_large_operator_properties(G, dev, dt, N):
+    """Size-independent checks at sizes the CPU oracle cannot reach in seconds -- fp32 at the FULL
+    size of BASELINE config 2 (4096^2 = 16.7 M rows, 83.9 M nnz), fp64 at 2048^2:
     A*1 equals the analytic row sums exactly, the fused Jacobi sweep equals its definition built
     from the fused residual (bit-exact), linearity, and an independent fp64 torch.sparse CSR
     product agrees within the tolerance."""
-    N = 2048
     n = N * N
     ei, ev = G.UtilsGNN.laplacianfun_torch(N, device=dev)
     ev = ev.to(dt)
@@ -601,3 +601,52 @@ def test_generic_metalayer_with_user_callbacks(G, dev):
     ref = port.residual(torch.cat([b, x], 1), ei, ev)
     assert v.is_cuda and same(v.cpu()[:, 2:3], ref)
     assert same(G.GNNResidual.GNNResidual()(torch.cat([b, x], 1).to(dev), ei.to(dev), ev.to(dev)).cpu(), ref)
+
+
+def test_config4_full_size_masks_bit_exact(G, dev):
+    """BASELINE config 4 at FULL size (anisotropic periodic FEM operator, 4096^2 = 16.7 M rows,
+    134 M off-diagonal edges, fp32).  The operator is a constant stencil and SOC / SA / direct
+    interpolation are row-local, so EVERY row must reproduce -- bit for bit, NaN pattern included
+    -- the row of the same kind (first / interior / last grid line in x and y, parity of x) that
+    the CPU oracle computes on a 24 x 24 torus."""
+    dt = torch.float32
+    Ns, N = 24, 4096
+
+    def setup(M, device):
+        ei, ev = G.generators.constant_diffusion_fem(1.0, 0.01, M, dtype=dt, device=device)
+        n = M * M
+        diag = G.generators.diagonal_of(ei, ev, n)
+        keep = ei[0] != ei[1]
+        return n, ei[:, keep].contiguous(), ev[keep].contiguous(), diag
+
+    # oracle on the small torus
+    ns, eo_s, ao_s, diag_s = setup(Ns, "cpu")
+    S_s = port.soc_classic(0.25, torch.zeros(ns, 1, dtype=dt), eo_s, ao_s)
+    sa_s = port.soc_sa(diag_s, eo_s, ao_s)[:, 1]
+    split_s = torch.zeros(ns, 1, dtype=dt)
+    split_s[0::2] = 1
+    w_s = port.direct_interp(torch.hstack([diag_s, split_s]), eo_s, torch.hstack([ao_s, (S_s.reshape(-1, 1) > 0).to(dt)]))
+    # full size on the GPU through the drop-in layers
+    n, eo, ao, diag = setup(N, dev)
+    assert eo.shape[1] == 8 * n
+    S = G.SOCClassicGNN.SOCClassicGNN(0.25)(torch.zeros(n, 1, dtype=dt, device=dev), eo, ao)
+    sa = G.SOCSAGNN.SOCSAGNN()(diag, eo, ao)[1][:, 1]
+    split = torch.zeros(n, 1, dtype=dt, device=dev)
+    split[0::2] = 1
+    w = G.DirectInterpGNN.DirectInterpGNN()(torch.hstack([diag, split]), eo, torch.hstack([ao, (S.reshape(-1, 1) > 0).to(dt)]))
+    assert int((S > 0).sum().item()) == 6 * n                       # 6 of the 8 neighbours are strong
+    # Row (gx, gy) of the big torus has the same neighbour order (ascending wrapped column index) and
+    # the same C/F flags as the row of the same kind on the small one: first / interior / last in
+    # each direction, with the parity of x (N and Ns are both even).
+    idx = torch.arange(n, device=dev)
+    gx, gy = idx % N, idx // N
+    sx = torch.where(gx == 0, 0, torch.where(gx == N - 1, Ns - 1, 6 + gx % 2))
+    sy = torch.where(gy == 0, 0, torch.where(gy == N - 1, Ns - 1, 5))
+    small = sy * Ns + sx
+    for name, t, t_s in (("S", S, S_s), ("sa", sa, sa_s), ("w", w, w_s)):
+        got = t.view(n, 8)
+        want = t_s.view(ns, 8).to(dev)[small]
+        same_bits = (got == want) | (torch.isnan(got) & torch.isnan(want))
+        assert bool(same_bits.all()), name
+        del want, same_bits
+    assert bool(torch.isnan(w_s).any()) and bool((S_s > 0).any()) and not bool((S_s > 0).all())
