@@ -57,34 +57,95 @@ def committed_traffic():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons DURING the timed region."""
+    """SM clock and throttle reasons sampled DURING the timed regions: an NVML polling thread
+    (every ~4 ms; samples taken between region_begin() / region_end() count as "under load"),
+    with the recipe's `nvidia-smi -lms` loop as the fallback when NVML cannot be opened."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
          "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap,utilization.gpu")
+    REASONS = ((0x8, "hw_slowdown"), (0x40, "hw_thermal_slowdown"), (0x20, "sw_thermal_slowdown"),
+               (0x4, "sw_power_cap"), (0x80, "hw_power_brake_slowdown"))
 
-    def __init__(self, gpu_index):
+    def __init__(self, cuda_index):
+        self.cuda_index = cuda_index
         vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        self.smi_index = cuda_index
         if vis:
             try:
-                gpu_index = int(vis.split(",")[gpu_index])
+                self.smi_index = int(vis.split(",")[cuda_index])
             except (ValueError, IndexError):
                 pass
-        self.idx = gpu_index
-        self.proc = None
-        self.path = None
+        self.proc = self.path = self.thread = self.nvml = None
+        self.samples = []          # (sm_mhz, reasons bitmask, in timed region)
+        self.sm_max = None
+        self.in_region = False
+        self.stop_flag = False
+
+    # ---- NVML thread
+    def _nvml_handle(self):
+        import pynvml
+        pynvml.nvmlInit()
+        self.nvml = pynvml
+        try:
+            uuid = str(torch.cuda.get_device_properties(self.cuda_index).uuid)
+            if not uuid.startswith("GPU-"):
+                uuid = "GPU-" + uuid
+            return pynvml.nvmlDeviceGetHandleByUUID(uuid.encode())
+        except Exception:
+            return pynvml.nvmlDeviceGetHandleByIndex(self.smi_index)
+
+    def _poll(self, handle):
+        nv = self.nvml
+        get_reasons = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or \
+            nv.nvmlDeviceGetCurrentClocksThrottleReasons
+        while not self.stop_flag:
+            try:
+                mhz = nv.nvmlDeviceGetClockInfo(handle, nv.NVML_CLOCK_SM)
+                self.samples.append((float(mhz), int(get_reasons(handle)), self.in_region))
+            except Exception:
+                pass
+            time.sleep(0.004)
 
     def start(self):
+        try:
+            handle = self._nvml_handle()
+            self.sm_max = float(self.nvml.nvmlDeviceGetMaxClockInfo(handle, self.nvml.NVML_CLOCK_SM))
+            self.thread = threading.Thread(target=self._poll, args=(handle,), daemon=True)
+            self.thread.start()
+            return
+        except Exception:
+            self.thread = None
         try:
             fd, self.path = tempfile.mkstemp(suffix=".csv")
             os.close(fd)
             self.proc = subprocess.Popen(
-                ["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                ["nvidia-smi", "-i", str(self.smi_index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
                  "-lms", "50"], stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+            time.sleep(0.5)        # nvidia-smi needs ~0.3 s to start
         except Exception:
             self.proc = None
 
+    def region_begin(self):
+        self.in_region = True
+
+    def region_end(self):
+        self.in_region = False
+
     def stop(self):
-        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0, "samples_under_load": 0}
+        if self.thread is not None:
+            self.stop_flag = True
+            self.thread.join(timeout=2)
+            loaded = [s_ for s_ in self.samples if s_[2]]
+            use = sorted(m for m, _, _ in (loaded or self.samples))
+            mask = 0
+            for _, r, _ in (loaded or self.samples):
+                mask |= r
+            if use:
+                out.update(sm_mhz=use[len(use) // 2], sm_min_mhz=use[0], sm_max_mhz=self.sm_max,
+                           samples=len(self.samples), samples_under_load=len(loaded),
+                           reasons=sorted(name for bit, name in self.REASONS if mask & bit), source="nvml")
+            return out
         if self.proc is None:
             return out
         self.proc.terminate()
@@ -114,7 +175,7 @@ class ClockSampler:
         if sm:
             use = sorted(loaded) if loaded else sorted(sm)
             out.update(sm_mhz=use[len(use) // 2], sm_max_mhz=max(mx), samples=len(sm),
-                       samples_under_load=len(loaded), reasons=sorted(reasons))
+                       samples_under_load=len(loaded), reasons=sorted(reasons), source="nvidia-smi")
         return out
 
 
@@ -257,8 +318,7 @@ def main_gpu(args):
     # ---------------- kernels only (value) + roofline of the dominant kernel
     sampler = ClockSampler(local_rank)
     if rank == 0:
-        sampler.start()      # nvidia-smi needs ~0.3 s to start: begin before the warm-up,
-        time.sleep(0.5)      # samples then cover warm-up + both timed regions
+        sampler.start()      # before the warm-up; region_begin/end mark the two timed regions
     for _ in range(args.warmup):
         prob.step_kernels()
     barrier()
@@ -266,11 +326,13 @@ def main_gpu(args):
     jac_events = []
     launches0 = rt.launch_count
     barrier()
+    sampler.region_begin()
     ev0.record()
     for _ in range(args.steps):
         jac_events.append(prob.step_kernels(time_jacobi=True))
     ev1.record()
     barrier()
+    sampler.region_end()
     launches = rt.launch_count - launches0
     ms_total = ev0.elapsed_time(ev1)
     jac_ms = sum(a.elapsed_time(b) for a, b in jac_events) / (len(jac_events) * N_JACOBI)
@@ -281,6 +343,7 @@ def main_gpu(args):
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
+    sampler.region_begin()
     t_wall0 = time.perf_counter()
     e0.record()
     for _ in range(args.steps):
@@ -288,6 +351,7 @@ def main_gpu(args):
     e1.record()
     barrier()
     e2e_wall = time.perf_counter() - t_wall0
+    sampler.region_end()
     e2e_ms = max(e0.elapsed_time(e1), e2e_wall * 1e3)  # D2H is synchronous: host clock bounds it too
     clocks = sampler.stop() if rank == 0 else None
 

@@ -70,9 +70,10 @@ class HaloStep(ctypes.Structure):
 
 
 _sig("glab_halo_wait", c_int, c_int, POINTER(c_void_p), P, P)
-_sig("glab_spgemm_products", c_int, P, P, P, POINTER(_I64), P)
-_sig("glab_spgemm_workspace_bytes", _I64, _I64, _I64, c_int)
+_sig("glab_spgemm_products", c_int, P, P, P, POINTER(_I64), POINTER(_I64), P)
+_sig("glab_spgemm_workspace_bytes", _I64, _I64, _I64, _I64, c_int)
 _sig("glab_cf_split_workspace_bytes", _I64, _I64)
+_sig("glab_interp_workspace_bytes", _I64, _I64)
 
 for _suf, _ct in (("f32", c_float), ("f64", c_double)):
     _sig("glab_gather_vals_" + _suf, c_int, P, P, _I64, _I64, P, P)
@@ -106,10 +107,10 @@ for _suf, _ct in (("f32", c_float), ("f64", c_double)):
     _sig("glab_soc_sa_" + _suf, c_int, P, P, P, P, P)
     _sig("glab_direct_interp_" + _suf, c_int, P, P, P, P, P, P, P)
     _sig("glab_halo_push_" + _suf, c_int, P, _INT, _INT, POINTER(PushDesc), P, P)
-    _sig("glab_interp_count_" + _suf, c_int, P, P, P, _INT, P, P, POINTER(_I64), POINTER(_I64), P)
+    _sig("glab_interp_count_" + _suf, c_int, P, P, P, _INT, P, _I64, P, P, POINTER(_I64), POINTER(_I64), P)
     _sig("glab_interp_fill_" + _suf, c_int, P, P, P, _INT, P, P, P, P, P, P)
-    _sig("glab_spgemm_symbolic_" + _suf, c_int, P, P, P, P, P, _I64, _I64, POINTER(_I64), P)
-    _sig("glab_spgemm_numeric_" + _suf, c_int, P, P, P, _I64, _I64, _I64, P, P, P, P)
+    _sig("glab_spgemm_symbolic_" + _suf, c_int, P, P, P, P, P, _I64, _I64, _I64, POINTER(_I64), P)
+    _sig("glab_spgemm_numeric_" + _suf, c_int, P, P, P, P, P, _I64, _I64, _I64, _I64, P, P, P, P)
     _sig("glab_cf_split_pmis_" + _suf, c_int, P, P, c_uint32, P, _I64, P, POINTER(_I32), P)
 
 

@@ -541,8 +541,13 @@ def interp_assemble(plan_off, w_slots, cflag, mode=0):
     prow = torch.empty(n + 1, dtype=torch.int32, device=dev)
     cid = torch.empty(n + 1, dtype=torch.int32, device=dev)
     nnz_p, n_coarse = ctypes.c_int64(), ctypes.c_int64()
-    _call("interp_count", dt, dev, plan_off.handle, ptr(w_slots), ptr(cflag), int(mode), ptr(prow), ptr(cid),
-          ctypes.byref(nnz_p), ctypes.byref(n_coarse), stream_ptr())
+    with torch.cuda.device(dev):
+        ws_bytes = int(lib.glab_interp_workspace_bytes(n))
+    if ws_bytes < 0:
+        check(ws_bytes, "glab_interp_workspace_bytes")
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+    _call("interp_count", dt, dev, plan_off.handle, ptr(w_slots), ptr(cflag), int(mode), ptr(ws), ws_bytes, ptr(prow),
+          ptr(cid), ctypes.byref(nnz_p), ctypes.byref(n_coarse), stream_ptr())
     ei = torch.empty((2, nnz_p.value), dtype=torch.int64, device=dev)
     vals = torch.empty(nnz_p.value, dtype=dt, device=dev)
     if nnz_p.value:
@@ -552,30 +557,35 @@ def interp_assemble(plan_off, w_slots, cflag, mode=0):
 
 
 def spgemm(plan_x, vals_x, plan_y, vals_y):
-    """Z = X * Y (expand - sort - compress on the device): returns (edge_index int64 [2, nnz_Z]
-    sorted by (row, col) without duplicates, values [nnz_Z]) -- the reference's COO layout."""
+    """Z = X * Y on the device (row-local accumulation, or expand - sort - compress for dense-ish
+    rows): returns (edge_index int64 [2, nnz_Z] sorted by (row, col) without duplicates, values
+    [nnz_Z]) -- the reference's COO layout.  `spgemm.last` describes the most recent call (setup
+    diagnostics: product count, workspace size, path taken)."""
     global launch_count
     dev, dt = plan_x.device, vals_x.dtype
     if vals_y.dtype != dt:
         raise GlabError("spgemm: operand dtypes differ (%s, %s)" % (dt, vals_y.dtype))
-    scratch = torch.zeros(1, dtype=torch.int64, device=dev)
-    n_prod = ctypes.c_int64()
+    scratch = torch.zeros(2, dtype=torch.int64, device=dev)
+    n_prod, max_row = ctypes.c_int64(), ctypes.c_int64()
     with torch.cuda.device(dev):
         launch_count += 1
         check(lib.glab_spgemm_products(plan_x.handle, plan_y.handle, ptr(scratch), ctypes.byref(n_prod),
-                                       stream_ptr()), "glab_spgemm_products")
-        ws_bytes = int(lib.glab_spgemm_workspace_bytes(plan_x.n_rows, n_prod.value, vals_x.element_size()))
+                                       ctypes.byref(max_row), stream_ptr()), "glab_spgemm_products")
+        ws_bytes = int(lib.glab_spgemm_workspace_bytes(plan_x.n_rows, n_prod.value, max_row.value,
+                                                       vals_x.element_size()))
     if ws_bytes < 0:
         check(ws_bytes, "glab_spgemm_workspace_bytes")
     ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
     nnz = ctypes.c_int64()
     _call("spgemm_symbolic", dt, dev, plan_x.handle, ptr(vals_x), plan_y.handle, ptr(vals_y), ptr(ws), ws_bytes,
-          n_prod.value, ctypes.byref(nnz), stream_ptr())
+          n_prod.value, max_row.value, ctypes.byref(nnz), stream_ptr())
     ei = torch.empty((2, nnz.value), dtype=torch.int64, device=dev)
     vals = torch.empty(nnz.value, dtype=dt, device=dev)
     if nnz.value:
-        _call("spgemm_numeric", dt, dev, plan_x.handle, plan_y.handle, ptr(ws), ws_bytes, n_prod.value, nnz.value,
-              ptr(ei[0]), ptr(ei[1]), ptr(vals), stream_ptr())
+        _call("spgemm_numeric", dt, dev, plan_x.handle, ptr(vals_x), plan_y.handle, ptr(vals_y), ptr(ws), ws_bytes,
+              n_prod.value, max_row.value, nnz.value, ptr(ei[0]), ptr(ei[1]), ptr(vals), stream_ptr())
+    spgemm.last = {"products": n_prod.value, "max_row_products": max_row.value, "workspace_bytes": ws_bytes,
+                   "path": {1: "row-local", 2: "esc"}.get(int(ws[:32].view(torch.int64)[3].item()), "empty")}
     return ei, vals
 
 

@@ -4,16 +4,17 @@
 //   glab_interp_*    prolongator P = [I + W](:, C) assembled SPARSE, sorted COO, from the per-edge
 //                    weights of DirectInterpGNN.  Replaces VCycle.py:126-137 (dense eye(n) + W,
 //                    column slice, .to_sparse()).
-//   glab_spgemm_*    C = X * Y for two CSR plans (expand - sort - compress), used twice for the
-//                    Galerkin operator A_c = P^T (A P).  Replaces VCycle.py:209 (torch.sparse @).
+//   glab_spgemm_*    C = X * Y for two CSR plans (row-local accumulation in shared memory, or
+//                    expand - sort - compress for dense-ish rows), used twice for the Galerkin
+//                    operator A_c = P^T (A P).  Replaces VCycle.py:209 (torch.sparse @).
 //   glab_cf_split_*  PMIS coarse/fine splitting on the strength graph with integer keys
 //                    (deterministic, order-independent).  Stands in for pyamg's CLJP call at
 //                    VCycle.py:114 / DirectInterpGNN.py:194 (un-pinned third-party, absent).
 //
 // All of this is SETUP work (once per operator), HBM-bound integer/key traffic; the radix sort and
-// the scans are CUB device primitives, everything else is hand-written.  Duplicates produced by the
-// expansion are summed SEQUENTIALLY in expansion order (X slot order, then Y slot order; the radix
-// sort is stable), so the result is deterministic and independent of the launch geometry.
+// the scans are CUB device primitives, everything else is hand-written.  Products that meet in one
+// entry are summed SEQUENTIALLY in expansion order (X slot order, then Y slot order) on both SpGEMM
+// paths, so the result is deterministic and independent of the path and of the launch geometry.
 #include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_scan.cuh>
 #include <cub/device/device_select.cuh>
@@ -97,28 +98,36 @@ __global__ void k_interp_fill(const int32_t* __restrict__ rowptr, const int32_t*
   }
 }
 
+static int64_t interp_workspace_bytes(int64_t n) {
+  if (n < 0) return GLAB_E_ARG;
+  size_t tb = 0;
+  cudaError_t e = cub::DeviceScan::ExclusiveSum(nullptr, tb, (int32_t*)nullptr, (int32_t*)nullptr, (int)(n + 1),
+                                                (cudaStream_t)0);
+  if (e != cudaSuccess) return -(int64_t)e;
+  return (int64_t)align256(tb + 16);
+}
+
 template <typename T>
-static int interp_count(const glab_plan* A, const T* w, const T* cflag, int mode, int32_t* prow,
-                        int32_t* cid, int64_t* nnz_p, int64_t* n_coarse, void* stream_) {
-  if (!A || !prow || !cid || !nnz_p || !n_coarse || (mode != 0 && mode != 1)) return GLAB_E_ARG;
+static int interp_count(const glab_plan* A, const T* w, const T* cflag, int mode, void* ws, int64_t ws_bytes,
+                        int32_t* prow, int32_t* cid, int64_t* nnz_p, int64_t* n_coarse, void* stream_) {
+  if (!A || !prow || !cid || !nnz_p || !n_coarse || !ws || (mode != 0 && mode != 1)) return GLAB_E_ARG;
   const int64_t n = A->n_rows;
   if ((n > 0 && !cflag) || (A->nnz > 0 && !w)) return GLAB_E_ARG;
+  const int64_t need = interp_workspace_bytes(n);
+  if (need < 0) return (int)-need;
+  if (ws_bytes < need) return GLAB_E_ARG;
   cudaStream_t st = as_stream(stream_);
   k_interp_count<T><<<grid1d(n + 1, A->sm_count), 256, 0, st>>>(A->rowptr, A->colidx, w, cflag, mode, n,
                                                                 prow, cid);
   GLAB_CUDA(cudaGetLastError());
-  size_t tb = 0;
-  GLAB_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tb, prow, prow, (int)(n + 1), st));
-  void* tmp = nullptr;
-  GLAB_CUDA(cudaMallocAsync(&tmp, tb ? tb : 16, st));  // a few KB of scan state, stream-ordered
-  cudaError_t e = cub::DeviceScan::ExclusiveSum(tmp, tb, prow, prow, (int)(n + 1), st);
-  if (e == cudaSuccess) e = cub::DeviceScan::ExclusiveSum(tmp, tb, cid, cid, (int)(n + 1), st);
+  size_t tb = (size_t)ws_bytes;
+  GLAB_CUDA(cub::DeviceScan::ExclusiveSum(ws, tb, prow, prow, (int)(n + 1), st));
+  tb = (size_t)ws_bytes;
+  GLAB_CUDA(cub::DeviceScan::ExclusiveSum(ws, tb, cid, cid, (int)(n + 1), st));
   int32_t totals[2] = {0, 0};
-  if (e == cudaSuccess) e = cudaMemcpyAsync(&totals[0], prow + n, 4, cudaMemcpyDeviceToHost, st);
-  if (e == cudaSuccess) e = cudaMemcpyAsync(&totals[1], cid + n, 4, cudaMemcpyDeviceToHost, st);
-  cudaFreeAsync(tmp, st);
-  if (e == cudaSuccess) e = cudaStreamSynchronize(st);
-  if (e != cudaSuccess) return (int)e;
+  GLAB_CUDA(cudaMemcpyAsync(&totals[0], prow + n, 4, cudaMemcpyDeviceToHost, st));
+  GLAB_CUDA(cudaMemcpyAsync(&totals[1], cid + n, 4, cudaMemcpyDeviceToHost, st));
+  GLAB_CUDA(cudaStreamSynchronize(st));
   *nnz_p = totals[0];
   *n_coarse = totals[1];
   return 0;
@@ -137,12 +146,26 @@ static int interp_fill(const glab_plan* A, const T* w, const T* cflag, int mode,
   return (int)cudaGetLastError();
 }
 
-// ============================================================================ SpGEMM (ESC)
-// Workspace layout (caller-owned, one allocation).  hdr[0] = number of distinct (row, col) keys,
-// hdr[1] = which of the two key/value buffers holds the sorted result.
+// ============================================================================ SpGEMM
+// Z = X * Y.  Two paths that produce bit-identical results (each entry's products are added one
+// at a time in expansion order: X slot order, then Y slot order, first product not added to 0):
+//
+//   row-local  one thread per output row keeps the row's distinct columns sorted in a private
+//              shared-memory strip (insert / accumulate), once to count (symbolic) and once to
+//              fill (numeric).  Every input and output byte crosses HBM once; used whenever no
+//              row has more than kRowCap distinct columns (all stencil / Galerkin operators).
+//   ESC        expand - stable radix sort - compress through a caller workspace of ~24 B per
+//              product; the general fallback (dense-ish rows).
+//
+// Workspace header: hdr[0] = number of distinct (row, col) keys (ESC), hdr[1] = sorted buffer
+// selector (ESC), hdr[2] = row-local overflow flag, hdr[3] = path taken (1 = row-local, 2 = ESC).
+constexpr int kRowCap = 64;       // distinct columns per output row on the row-local path
+constexpr int kRowThreads = 128;  // rows (threads) per CTA on the row-local path
+
 struct SpgemmWs {
   size_t hdr, rowoff, keys[2], vals[2], cub, total;
   size_t cub_bytes;
+  bool esc;  // the workspace is large enough for the ESC path
 };
 
 struct HeadOp {  // p starts a run of equal keys
@@ -150,22 +173,29 @@ struct HeadOp {  // p starts a run of equal keys
   __host__ __device__ __forceinline__ bool operator()(int p) const { return p == 0 || k[p] != k[p - 1]; }
 };
 
+// A row with at most kRowCap products cannot have more than kRowCap distinct columns: then the
+// row-local path is guaranteed and only the header + the row-offset array are needed.
 template <typename T>
-static int spgemm_layout(int64_t n_rows_x, int64_t n_products, SpgemmWs* L) {
-  if (n_rows_x < 0 || n_products < 0) return GLAB_E_ARG;
+static int spgemm_layout(int64_t n_rows_x, int64_t n_products, int64_t max_row_products, SpgemmWs* L) {
+  if (n_rows_x < 0 || n_products < 0 || max_row_products < 0) return GLAB_E_ARG;
   if (n_products >= (int64_t)INT32_MAX - 64) return GLAB_E_RANGE;
-  const size_t P = (size_t)n_products + 2;
-  size_t sort_b = 0, sel_b = 0, scan_b = 0;
-  cub::DoubleBuffer<uint64_t> dk(nullptr, nullptr);
-  cub::DoubleBuffer<T> dv(nullptr, nullptr);
-  GLAB_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, sort_b, dk, dv, (int)n_products, 0, 64, (cudaStream_t)0));
-  HeadOp op{nullptr};
-  GLAB_CUDA(cub::DeviceSelect::If(nullptr, sel_b, thrust::counting_iterator<int>(0), (int32_t*)nullptr,
-                                  (int64_t*)nullptr, (int)n_products, op, (cudaStream_t)0));
+  L->esc = max_row_products > kRowCap;
+  size_t scan_b = 0;
   GLAB_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, scan_b, (int64_t*)nullptr, (int64_t*)nullptr,
                                           (int)(n_rows_x + 1), (cudaStream_t)0));
-  size_t cb = sort_b > sel_b ? sort_b : sel_b;
-  if (scan_b > cb) cb = scan_b;
+  size_t cb = scan_b;
+  const size_t P = L->esc ? (size_t)n_products + 2 : 0;
+  if (L->esc) {
+    size_t sort_b = 0, sel_b = 0;
+    cub::DoubleBuffer<uint64_t> dk(nullptr, nullptr);
+    cub::DoubleBuffer<T> dv(nullptr, nullptr);
+    GLAB_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, sort_b, dk, dv, (int)n_products, 0, 64, (cudaStream_t)0));
+    HeadOp op{nullptr};
+    GLAB_CUDA(cub::DeviceSelect::If(nullptr, sel_b, thrust::counting_iterator<int>(0), (int32_t*)nullptr,
+                                    (int64_t*)nullptr, (int)n_products, op, (cudaStream_t)0));
+    if (sort_b > cb) cb = sort_b;
+    if (sel_b > cb) cb = sel_b;
+  }
   size_t o = 0;
   L->hdr = o;      o += 256;
   L->rowoff = o;   o += align256((size_t)(n_rows_x + 2) * 8);
@@ -183,7 +213,7 @@ static int spgemm_layout(int64_t n_rows_x, int64_t n_products, SpgemmWs* L) {
 __global__ void k_spgemm_count(const int32_t* __restrict__ xrp, const int32_t* __restrict__ xci,
                                const int32_t* __restrict__ yrp, int64_t n, int64_t* __restrict__ cnt,
                                unsigned long long* __restrict__ total) {
-  unsigned long long local = 0;
+  unsigned long long local = 0, biggest = 0;
   for (int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; r <= n;
        r += (int64_t)gridDim.x * blockDim.x) {
     int64_t c = 0;
@@ -196,14 +226,101 @@ __global__ void k_spgemm_count(const int32_t* __restrict__ xrp, const int32_t* _
     }
     if (cnt) cnt[r] = c;
     local += (unsigned long long)c;
+    biggest = (unsigned long long)c > biggest ? (unsigned long long)c : biggest;
   }
-  if (total) {
+  if (total) {  // total[0] = sum, total[1] = max over rows
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) local += __shfl_xor_sync(0xffffffffu, local, o);
-    if ((threadIdx.x & 31) == 0 && local) atomicAdd(total, local);
+    for (int o = 16; o > 0; o >>= 1) {
+      local += __shfl_xor_sync(0xffffffffu, local, o);
+      const unsigned long long other = __shfl_xor_sync(0xffffffffu, biggest, o);
+      biggest = other > biggest ? other : biggest;
+    }
+    if ((threadIdx.x & 31) == 0 && local) {
+      atomicAdd(total, local);
+      atomicMax(total + 1, biggest);
+    }
   }
 }
 
+// ---- row-local path ---------------------------------------------------------------------------
+// Thread `tid` owns strip element s at cols[s * kRowThreads + tid] (conflict-free when the threads
+// of a warp touch the same s).  Columns arrive mostly ascending, so the insertion point is searched
+// from the top.  NUMERIC = false only counts the distinct columns of each row.
+template <typename T, bool NUMERIC>
+__global__ void __launch_bounds__(kRowThreads)
+k_spgemm_rows(const int32_t* __restrict__ xrp, const int32_t* __restrict__ xci, const T* __restrict__ xv,
+              const int32_t* __restrict__ yrp, const int32_t* __restrict__ yci, const T* __restrict__ yv,
+              int64_t n, int32_t* __restrict__ rowcnt, const int32_t* __restrict__ zrp,
+              int64_t* __restrict__ out_row, int64_t* __restrict__ out_col, T* __restrict__ out_val,
+              int64_t* __restrict__ hdr) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  int32_t* cols = reinterpret_cast<int32_t*>(smem_raw);                                  // [kRowCap][kRowThreads]
+  T* vals = reinterpret_cast<T*>(smem_raw + (size_t)kRowCap * kRowThreads * sizeof(int32_t));  // same shape
+  const int tid = threadIdx.x;
+  for (int64_t r = blockIdx.x * (int64_t)kRowThreads + tid; r <= n; r += (int64_t)gridDim.x * kRowThreads) {
+    if (r == n) {
+      if (!NUMERIC) rowcnt[n] = 0;  // sentinel: the exclusive scan leaves nnz(Z) here
+      continue;
+    }
+    int cnt = 0;
+    bool over = false;
+    const int e1 = xrp[r + 1];
+    for (int e = xrp[r]; e < e1 && !over; ++e) {
+      const int j = xci[e];
+      T a = T(0);
+      if (NUMERIC) a = xv[e];
+      const int y1 = yrp[j + 1];
+      for (int t = yrp[j]; t < y1; ++t) {
+        const int c = yci[t];
+        int pos = cnt;
+        while (pos > 0 && cols[(pos - 1) * kRowThreads + tid] >= c) --pos;
+        if (pos < cnt && cols[pos * kRowThreads + tid] == c) {
+          if (NUMERIC) vals[pos * kRowThreads + tid] = vals[pos * kRowThreads + tid] + a * yv[t];
+          continue;
+        }
+        if (cnt == kRowCap) {
+          over = true;
+          break;
+        }
+        for (int s = cnt; s > pos; --s) {
+          cols[s * kRowThreads + tid] = cols[(s - 1) * kRowThreads + tid];
+          if (NUMERIC) vals[s * kRowThreads + tid] = vals[(s - 1) * kRowThreads + tid];
+        }
+        cols[pos * kRowThreads + tid] = c;
+        if (NUMERIC) vals[pos * kRowThreads + tid] = a * yv[t];
+        ++cnt;
+      }
+    }
+    if (!NUMERIC) {
+      rowcnt[r] = cnt;
+      if (over) atomicOr(reinterpret_cast<unsigned long long*>(hdr + 2), 1ull);
+    } else {
+      int64_t o = zrp[r];
+      for (int s = 0; s < cnt; ++s, ++o) {
+        out_row[o] = r;
+        out_col[o] = cols[s * kRowThreads + tid];
+        out_val[o] = vals[s * kRowThreads + tid];
+      }
+    }
+  }
+}
+
+template <typename T, bool NUMERIC>
+static int spgemm_rows_launch(const glab_plan* X, const T* xv, const glab_plan* Y, const T* yv, int32_t* rowcnt,
+                              int64_t* out_row, int64_t* out_col, T* out_val, int64_t* hdr, cudaStream_t st) {
+  const size_t smem = (size_t)kRowCap * kRowThreads * (sizeof(int32_t) + (NUMERIC ? sizeof(T) : 0));
+  auto kern = k_spgemm_rows<T, NUMERIC>;
+  GLAB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const int64_t n = X->n_rows;
+  int64_t blocks = (n + 1 + kRowThreads - 1) / kRowThreads;
+  const int64_t cap = (int64_t)X->sm_count * 16;
+  if (blocks > cap) blocks = cap;
+  kern<<<(unsigned)blocks, kRowThreads, smem, st>>>(X->rowptr, X->colidx, xv, Y->rowptr, Y->colidx, yv, n, rowcnt,
+                                                     rowcnt, out_row, out_col, out_val, hdr);
+  return (int)cudaGetLastError();
+}
+
+// ---- ESC path ---------------------------------------------------------------------------------
 // 8 lanes per X row: the lanes walk the row's slots together and spread over each Y row, so a
 // product's position is rowoff[r] + (products of the earlier slots) + (position in the Y row):
 // expansion order == X slot order, then Y slot order.
@@ -232,7 +349,7 @@ __global__ void k_spgemm_expand(const int32_t* __restrict__ xrp, const int32_t* 
   }
 }
 
-__global__ void k_spgemm_store_hdr(int64_t* hdr, int selector) { hdr[1] = selector; }
+__global__ void k_spgemm_store_hdr(int64_t* hdr, int slot, int64_t value) { hdr[slot] = value; }
 
 template <typename T>
 __global__ void k_spgemm_compress(const int64_t* __restrict__ hdr, const uint64_t* __restrict__ k0,
@@ -268,21 +385,21 @@ static int spgemm_check(const glab_plan* X, const glab_plan* Y) {
 
 template <typename T>
 static int spgemm_symbolic(const glab_plan* X, const T* xv, const glab_plan* Y, const T* yv, void* ws,
-                           int64_t ws_bytes, int64_t n_products, int64_t* nnz_out, void* stream_) {
+                           int64_t ws_bytes, int64_t n_products, int64_t max_row_products, int64_t* nnz_out,
+                           void* stream_) {
   int rc = spgemm_check(X, Y);
   if (rc) return rc;
   if (!nnz_out || !ws) return GLAB_E_ARG;
   if ((X->nnz > 0 && !xv) || (Y->nnz > 0 && !yv)) return GLAB_E_ARG;
   SpgemmWs L;
-  rc = spgemm_layout<T>(X->n_rows, n_products, &L);
+  rc = spgemm_layout<T>(X->n_rows, n_products, max_row_products, &L);
   if (rc) return rc;
   if (ws_bytes < (int64_t)L.total) return GLAB_E_ARG;
   cudaStream_t st = as_stream(stream_);
   char* base = reinterpret_cast<char*>(ws);
   int64_t* hdr = reinterpret_cast<int64_t*>(base + L.hdr);
   int64_t* rowoff = reinterpret_cast<int64_t*>(base + L.rowoff);
-  uint64_t* k[2] = {reinterpret_cast<uint64_t*>(base + L.keys[0]), reinterpret_cast<uint64_t*>(base + L.keys[1])};
-  T* v[2] = {reinterpret_cast<T*>(base + L.vals[0]), reinterpret_cast<T*>(base + L.vals[1])};
+  int32_t* rowcnt = reinterpret_cast<int32_t*>(base + L.rowoff);  // row-local path: int32 view
   void* ctmp = base + L.cub;
   size_t cb = L.cub_bytes;
   GLAB_CUDA(cudaMemsetAsync(hdr, 0, 256, st));
@@ -291,8 +408,28 @@ static int spgemm_symbolic(const glab_plan* X, const T* xv, const glab_plan* Y, 
     return 0;
   }
   const int64_t n = X->n_rows;
+  // ---- row-local attempt: count the distinct columns of every row
+  rc = spgemm_rows_launch<T, false>(X, xv, Y, yv, rowcnt, nullptr, nullptr, nullptr, hdr, st);
+  if (rc) return rc;
+  GLAB_CUDA(cub::DeviceScan::ExclusiveSum(ctmp, cb, rowcnt, rowcnt, (int)(n + 1), st));
+  int32_t total = 0;
+  int64_t overflow = 0;
+  GLAB_CUDA(cudaMemcpyAsync(&total, rowcnt + n, 4, cudaMemcpyDeviceToHost, st));
+  GLAB_CUDA(cudaMemcpyAsync(&overflow, hdr + 2, 8, cudaMemcpyDeviceToHost, st));
+  GLAB_CUDA(cudaStreamSynchronize(st));
+  if (!overflow) {
+    k_spgemm_store_hdr<<<1, 1, 0, st>>>(hdr, 3, 1);
+    GLAB_CUDA(cudaGetLastError());
+    *nnz_out = total;
+    return 0;
+  }
+  if (!L.esc) return GLAB_E_ARG;  // cannot happen: <= kRowCap products per row cannot overflow
+  // ---- ESC fallback
+  uint64_t* k[2] = {reinterpret_cast<uint64_t*>(base + L.keys[0]), reinterpret_cast<uint64_t*>(base + L.keys[1])};
+  T* v[2] = {reinterpret_cast<T*>(base + L.vals[0]), reinterpret_cast<T*>(base + L.vals[1])};
   k_spgemm_count<<<grid1d(n + 1, X->sm_count), 256, 0, st>>>(X->rowptr, X->colidx, Y->rowptr, n, rowoff, nullptr);
   GLAB_CUDA(cudaGetLastError());
+  cb = L.cub_bytes;
   GLAB_CUDA(cub::DeviceScan::ExclusiveSum(ctmp, cb, rowoff, rowoff, (int)(n + 1), st));
   const int col_bits = bits_for(Y->n_cols);
   k_spgemm_expand<T><<<grid1d(n * 8, X->sm_count), 256, 0, st>>>(X->rowptr, X->colidx, xv, Y->rowptr, Y->colidx,
@@ -305,7 +442,8 @@ static int spgemm_symbolic(const glab_plan* X, const T* xv, const glab_plan* Y, 
                                             col_bits + bits_for(X->n_rows), st));
   const int sel = dk.selector;
   if (dv.selector != sel) return GLAB_E_ARG;  // cannot happen: CUB flips both buffers together
-  k_spgemm_store_hdr<<<1, 1, 0, st>>>(hdr, sel);
+  k_spgemm_store_hdr<<<1, 1, 0, st>>>(hdr, 1, sel);
+  k_spgemm_store_hdr<<<1, 1, 0, st>>>(hdr, 3, 2);
   HeadOp op{k[sel]};
   cb = L.cub_bytes;
   GLAB_CUDA(cub::DeviceSelect::If(ctmp, cb, thrust::counting_iterator<int>(0),
@@ -319,24 +457,32 @@ static int spgemm_symbolic(const glab_plan* X, const T* xv, const glab_plan* Y, 
 }
 
 template <typename T>
-static int spgemm_numeric(const glab_plan* X, const glab_plan* Y, void* ws, int64_t ws_bytes,
-                          int64_t n_products, int64_t nnz_out, int64_t* out_row, int64_t* out_col,
-                          T* out_val, void* stream_) {
+static int spgemm_numeric(const glab_plan* X, const T* xv, const glab_plan* Y, const T* yv, void* ws,
+                          int64_t ws_bytes, int64_t n_products, int64_t max_row_products, int64_t nnz_out,
+                          int64_t* out_row, int64_t* out_col, T* out_val, void* stream_) {
   int rc = spgemm_check(X, Y);
   if (rc) return rc;
   if (!ws || nnz_out < 0 || nnz_out > n_products) return GLAB_E_ARG;
   if (nnz_out == 0) return 0;
-  if (!out_row || !out_col || !out_val) return GLAB_E_ARG;
+  if (!out_row || !out_col || !out_val || !xv || !yv) return GLAB_E_ARG;
   SpgemmWs L;
-  rc = spgemm_layout<T>(X->n_rows, n_products, &L);
+  rc = spgemm_layout<T>(X->n_rows, n_products, max_row_products, &L);
   if (rc) return rc;
   if (ws_bytes < (int64_t)L.total) return GLAB_E_ARG;
+  cudaStream_t st = as_stream(stream_);
   char* base = reinterpret_cast<char*>(ws);
-  k_spgemm_compress<T><<<grid1d(nnz_out, X->sm_count), 256, 0, as_stream(stream_)>>>(
-      reinterpret_cast<const int64_t*>(base + L.hdr), reinterpret_cast<const uint64_t*>(base + L.keys[0]),
-      reinterpret_cast<const uint64_t*>(base + L.keys[1]), reinterpret_cast<const T*>(base + L.vals[0]),
-      reinterpret_cast<const T*>(base + L.vals[1]), n_products, nnz_out, bits_for(Y->n_cols), out_row, out_col,
-      out_val);
+  int64_t* hdr = reinterpret_cast<int64_t*>(base + L.hdr);
+  int64_t path = 0;  // which path the symbolic phase took (it left the row offsets / sorted runs)
+  GLAB_CUDA(cudaMemcpyAsync(&path, hdr + 3, 8, cudaMemcpyDeviceToHost, st));
+  GLAB_CUDA(cudaStreamSynchronize(st));
+  if (path == 1)
+    return spgemm_rows_launch<T, true>(X, xv, Y, yv, reinterpret_cast<int32_t*>(base + L.rowoff), out_row, out_col,
+                                       out_val, hdr, st);
+  if (path != 2 || !L.esc) return GLAB_E_ARG;  // symbolic phase did not run on this workspace
+  k_spgemm_compress<T><<<grid1d(nnz_out, X->sm_count), 256, 0, st>>>(
+      hdr, reinterpret_cast<const uint64_t*>(base + L.keys[0]), reinterpret_cast<const uint64_t*>(base + L.keys[1]),
+      reinterpret_cast<const T*>(base + L.vals[0]), reinterpret_cast<const T*>(base + L.vals[1]), n_products, nnz_out,
+      bits_for(Y->n_cols), out_row, out_col, out_val);
   return (int)cudaGetLastError();
 }
 
@@ -490,13 +636,16 @@ static int cf_split_pmis(const glab_plan* A, const T* S, uint32_t seed, void* ws
 
 using namespace glab;
 
-extern "C" int glab_interp_count_f32(const glab_plan* A, const float* w, const float* c, int mode, int32_t* prow,
-                                     int32_t* cid, int64_t* nnz_p, int64_t* n_coarse, void* s) {
-  return interp_count<float>(A, w, c, mode, prow, cid, nnz_p, n_coarse, s);
+extern "C" int64_t glab_interp_workspace_bytes(int64_t n) { return interp_workspace_bytes(n); }
+extern "C" int glab_interp_count_f32(const glab_plan* A, const float* w, const float* c, int mode, void* ws,
+                                     int64_t ws_bytes, int32_t* prow, int32_t* cid, int64_t* nnz_p,
+                                     int64_t* n_coarse, void* s) {
+  return interp_count<float>(A, w, c, mode, ws, ws_bytes, prow, cid, nnz_p, n_coarse, s);
 }
-extern "C" int glab_interp_count_f64(const glab_plan* A, const double* w, const double* c, int mode, int32_t* prow,
-                                     int32_t* cid, int64_t* nnz_p, int64_t* n_coarse, void* s) {
-  return interp_count<double>(A, w, c, mode, prow, cid, nnz_p, n_coarse, s);
+extern "C" int glab_interp_count_f64(const glab_plan* A, const double* w, const double* c, int mode, void* ws,
+                                     int64_t ws_bytes, int32_t* prow, int32_t* cid, int64_t* nnz_p,
+                                     int64_t* n_coarse, void* s) {
+  return interp_count<double>(A, w, c, mode, ws, ws_bytes, prow, cid, nnz_p, n_coarse, s);
 }
 extern "C" int glab_interp_fill_f32(const glab_plan* A, const float* w, const float* c, int mode,
                                     const int32_t* prow, const int32_t* cid, int64_t* orow, int64_t* ocol,
@@ -509,49 +658,55 @@ extern "C" int glab_interp_fill_f64(const glab_plan* A, const double* w, const d
   return interp_fill<double>(A, w, c, mode, prow, cid, orow, ocol, oval, s);
 }
 
-extern "C" int glab_spgemm_products(const glab_plan* X, const glab_plan* Y, void* scratch8, int64_t* n_products,
-                                    void* stream_) {
+extern "C" int glab_spgemm_products(const glab_plan* X, const glab_plan* Y, void* scratch16, int64_t* n_products,
+                                    int64_t* max_row_products, void* stream_) {
   int rc = spgemm_check(X, Y);
   if (rc) return rc;
-  if (!n_products || !scratch8) return GLAB_E_ARG;
+  if (!n_products || !max_row_products || !scratch16) return GLAB_E_ARG;
   cudaStream_t st = as_stream(stream_);
-  unsigned long long* total = reinterpret_cast<unsigned long long*>(scratch8);
-  GLAB_CUDA(cudaMemsetAsync(total, 0, 8, st));
+  unsigned long long* total = reinterpret_cast<unsigned long long*>(scratch16);
+  GLAB_CUDA(cudaMemsetAsync(total, 0, 16, st));
   if (X->n_rows > 0 && X->nnz > 0)
     k_spgemm_count<<<grid1d(X->n_rows + 1, X->sm_count), 256, 0, st>>>(X->rowptr, X->colidx, Y->rowptr,
                                                                       X->n_rows, nullptr, total);
-  unsigned long long h = 0;
-  GLAB_CUDA(cudaMemcpyAsync(&h, total, 8, cudaMemcpyDeviceToHost, st));
+  unsigned long long h[2] = {0, 0};
+  GLAB_CUDA(cudaMemcpyAsync(h, total, 16, cudaMemcpyDeviceToHost, st));
   GLAB_CUDA(cudaStreamSynchronize(st));
   GLAB_CUDA(cudaGetLastError());
-  *n_products = (int64_t)h;
+  *n_products = (int64_t)h[0];
+  *max_row_products = (int64_t)h[1];
   return 0;
 }
 
-extern "C" int64_t glab_spgemm_workspace_bytes(int64_t n_rows_x, int64_t n_products, int elem_size) {
+extern "C" int64_t glab_spgemm_workspace_bytes(int64_t n_rows_x, int64_t n_products, int64_t max_row_products,
+                                               int elem_size) {
   SpgemmWs L;
-  int rc = (elem_size == 8) ? spgemm_layout<double>(n_rows_x, n_products, &L)
-                            : (elem_size == 4) ? spgemm_layout<float>(n_rows_x, n_products, &L) : GLAB_E_ARG;
+  int rc = (elem_size == 8)   ? spgemm_layout<double>(n_rows_x, n_products, max_row_products, &L)
+           : (elem_size == 4) ? spgemm_layout<float>(n_rows_x, n_products, max_row_products, &L)
+                              : GLAB_E_ARG;
   return rc ? (int64_t)(rc < 0 ? rc : -rc) : (int64_t)L.total;
 }
 
 extern "C" int glab_spgemm_symbolic_f32(const glab_plan* X, const float* xv, const glab_plan* Y, const float* yv,
-                                        void* ws, int64_t ws_bytes, int64_t n_products, int64_t* nnz_out, void* s) {
-  return spgemm_symbolic<float>(X, xv, Y, yv, ws, ws_bytes, n_products, nnz_out, s);
+                                        void* ws, int64_t ws_bytes, int64_t n_products, int64_t max_row_products,
+                                        int64_t* nnz_out, void* s) {
+  return spgemm_symbolic<float>(X, xv, Y, yv, ws, ws_bytes, n_products, max_row_products, nnz_out, s);
 }
 extern "C" int glab_spgemm_symbolic_f64(const glab_plan* X, const double* xv, const glab_plan* Y, const double* yv,
-                                        void* ws, int64_t ws_bytes, int64_t n_products, int64_t* nnz_out, void* s) {
-  return spgemm_symbolic<double>(X, xv, Y, yv, ws, ws_bytes, n_products, nnz_out, s);
+                                        void* ws, int64_t ws_bytes, int64_t n_products, int64_t max_row_products,
+                                        int64_t* nnz_out, void* s) {
+  return spgemm_symbolic<double>(X, xv, Y, yv, ws, ws_bytes, n_products, max_row_products, nnz_out, s);
 }
-extern "C" int glab_spgemm_numeric_f32(const glab_plan* X, const glab_plan* Y, void* ws, int64_t ws_bytes,
-                                       int64_t n_products, int64_t nnz_out, int64_t* orow, int64_t* ocol,
-                                       float* oval, void* s) {
-  return spgemm_numeric<float>(X, Y, ws, ws_bytes, n_products, nnz_out, orow, ocol, oval, s);
+extern "C" int glab_spgemm_numeric_f32(const glab_plan* X, const float* xv, const glab_plan* Y, const float* yv,
+                                       void* ws, int64_t ws_bytes, int64_t n_products, int64_t max_row_products,
+                                       int64_t nnz_out, int64_t* orow, int64_t* ocol, float* oval, void* s) {
+  return spgemm_numeric<float>(X, xv, Y, yv, ws, ws_bytes, n_products, max_row_products, nnz_out, orow, ocol, oval, s);
 }
-extern "C" int glab_spgemm_numeric_f64(const glab_plan* X, const glab_plan* Y, void* ws, int64_t ws_bytes,
-                                       int64_t n_products, int64_t nnz_out, int64_t* orow, int64_t* ocol,
-                                       double* oval, void* s) {
-  return spgemm_numeric<double>(X, Y, ws, ws_bytes, n_products, nnz_out, orow, ocol, oval, s);
+extern "C" int glab_spgemm_numeric_f64(const glab_plan* X, const double* xv, const glab_plan* Y, const double* yv,
+                                       void* ws, int64_t ws_bytes, int64_t n_products, int64_t max_row_products,
+                                       int64_t nnz_out, int64_t* orow, int64_t* ocol, double* oval, void* s) {
+  return spgemm_numeric<double>(X, xv, Y, yv, ws, ws_bytes, n_products, max_row_products, nnz_out, orow, ocol, oval,
+                                s);
 }
 
 extern "C" int64_t glab_cf_split_workspace_bytes(int64_t n) {

@@ -389,16 +389,19 @@ int glab_rayleigh_halo_f64(const glab_plan*, const double* vals, const double* b
  * (a coarse row keeps its W entries, which are NaN when it has no strong coarse neighbour,
  * DirectInterpGNN.py:150); mode 1 = the MATLAB twin (coarse rows are identity rows,
  * matlab/test_direct_interpolation.m:130-132).
+ *   workspace_bytes: size of the caller-owned scratch for count (scan state, < 1 MB); negative =
+ *     error code.
  *   count (host-synchronous): p_rowptr[n+1] = row offsets of P, coarse_id[n+1] = coarse column
  *     number of every vertex (exclusive count of coarse points before it); returns nnz(P), n_coarse.
  *   fill: writes the nnz(P) entries; row i holds its kept W entries in ascending column order with
  *     the identity entry (i, coarse_id[i]) = 1 merged in.  nnz(P) must be < 2^31. */
+int64_t glab_interp_workspace_bytes(int64_t n);
 int glab_interp_count_f32(const glab_plan* A_off, const float* w_slots, const float* cflag, int mode,
-                          int32_t* p_rowptr, int32_t* coarse_id, int64_t* nnz_p, int64_t* n_coarse,
-                          void* stream);
+                          void* workspace, int64_t workspace_bytes, int32_t* p_rowptr,
+                          int32_t* coarse_id, int64_t* nnz_p, int64_t* n_coarse, void* stream);
 int glab_interp_count_f64(const glab_plan* A_off, const double* w_slots, const double* cflag, int mode,
-                          int32_t* p_rowptr, int32_t* coarse_id, int64_t* nnz_p, int64_t* n_coarse,
-                          void* stream);
+                          void* workspace, int64_t workspace_bytes, int32_t* p_rowptr,
+                          int32_t* coarse_id, int64_t* nnz_p, int64_t* n_coarse, void* stream);
 int glab_interp_fill_f32(const glab_plan* A_off, const float* w_slots, const float* cflag, int mode,
                          const int32_t* p_rowptr, const int32_t* coarse_id, int64_t* out_row,
                          int64_t* out_col, float* out_val, void* stream);
@@ -406,32 +409,45 @@ int glab_interp_fill_f64(const glab_plan* A_off, const double* w_slots, const do
                          const int32_t* p_rowptr, const int32_t* coarse_id, int64_t* out_row,
                          int64_t* out_col, double* out_val, void* stream);
 
-/* Sparse product Z = X * Y of two plans (expand - sort - compress); called twice for the Galerkin
- * operator A_c = P^T (A P).  Replaces VCycle.py:209 (`P.t() @ (A @ P)` on torch.sparse tensors).
- * The output is a (row, col)-sorted int64 COO without duplicates -- the reference's edge layout
+/* Sparse product Z = X * Y of two plans; called twice for the Galerkin operator A_c = P^T (A P).
+ * Replaces VCycle.py:209 (`P.t() @ (A @ P)` on torch.sparse tensors).  The output is a
+ * (row, col)-sorted int64 COO without duplicates -- the reference's edge layout
  * (UtilsGNN.py:74-78), so it can be handed to glab_plan_create and to every layer as the next
  * operator.  Products that meet in one entry are added sequentially in expansion order (X slot
- * order, then Y slot order): deterministic and independent of the launch geometry.
- *   products (host-synchronous): number of scalar multiplications sum_{(i,j) in X} nnz(Y_j*);
- *     scratch8 = 8 bytes of device memory.  Must be < 2^31 - 64 (GLAB_E_RANGE otherwise).
- *   workspace_bytes: size of the caller-owned device workspace for that many products
- *     (elem_size 4 or 8); negative = error code.  About (16 + 2 * elem_size) bytes per product.
- *   symbolic (host-synchronous): expands, sorts, finds the runs; returns nnz(Z).
- *   numeric: sums the runs and writes the nnz(Z) entries; same X, Y, workspace as symbolic. */
-int glab_spgemm_products(const glab_plan* X, const glab_plan* Y, void* scratch8, int64_t* n_products,
-                         void* stream);
-int64_t glab_spgemm_workspace_bytes(int64_t n_rows_x, int64_t n_products, int elem_size);
+ * order, then Y slot order): deterministic and independent of the launch geometry and of the
+ * path taken.  Two paths: "row-local" (one thread per output row keeps the row's distinct columns
+ * sorted in shared memory; taken when no row has more than 64 distinct columns, i.e. for every
+ * stencil / Galerkin operator; every byte crosses HBM once) and "ESC" (expand - stable radix
+ * sort - compress through the workspace; the fallback for dense-ish rows).
+ *   products (host-synchronous): number of scalar multiplications sum_{(i,j) in X} nnz(Y_j*) and
+ *     the largest such count of a single row; scratch16 = 16 bytes of device memory.
+ *     n_products must be < 2^31 - 64 (GLAB_E_RANGE otherwise).
+ *   workspace_bytes: size of the caller-owned device workspace (elem_size 4 or 8); negative =
+ *     error code.  8 bytes per X row when max_row_products <= 64 (row-local path guaranteed),
+ *     else about (16 + 2 * elem_size) bytes per product.
+ *   symbolic (host-synchronous): returns nnz(Z) and leaves the row offsets / sorted runs in the
+ *     workspace.
+ *   numeric (host-synchronous): writes the nnz(Z) entries; same X, Y, values, workspace and counts
+ *     as symbolic. */
+int glab_spgemm_products(const glab_plan* X, const glab_plan* Y, void* scratch16, int64_t* n_products,
+                         int64_t* max_row_products, void* stream);
+int64_t glab_spgemm_workspace_bytes(int64_t n_rows_x, int64_t n_products, int64_t max_row_products,
+                                    int elem_size);
 int glab_spgemm_symbolic_f32(const glab_plan* X, const float* x_vals, const glab_plan* Y,
                              const float* y_vals, void* workspace, int64_t workspace_bytes,
-                             int64_t n_products, int64_t* nnz_out, void* stream);
+                             int64_t n_products, int64_t max_row_products, int64_t* nnz_out,
+                             void* stream);
 int glab_spgemm_symbolic_f64(const glab_plan* X, const double* x_vals, const glab_plan* Y,
                              const double* y_vals, void* workspace, int64_t workspace_bytes,
-                             int64_t n_products, int64_t* nnz_out, void* stream);
-int glab_spgemm_numeric_f32(const glab_plan* X, const glab_plan* Y, void* workspace,
-                            int64_t workspace_bytes, int64_t n_products, int64_t nnz_out,
+                             int64_t n_products, int64_t max_row_products, int64_t* nnz_out,
+                             void* stream);
+int glab_spgemm_numeric_f32(const glab_plan* X, const float* x_vals, const glab_plan* Y,
+                            const float* y_vals, void* workspace, int64_t workspace_bytes,
+                            int64_t n_products, int64_t max_row_products, int64_t nnz_out,
                             int64_t* out_row, int64_t* out_col, float* out_val, void* stream);
-int glab_spgemm_numeric_f64(const glab_plan* X, const glab_plan* Y, void* workspace,
-                            int64_t workspace_bytes, int64_t n_products, int64_t nnz_out,
+int glab_spgemm_numeric_f64(const glab_plan* X, const double* x_vals, const glab_plan* Y,
+                            const double* y_vals, void* workspace, int64_t workspace_bytes,
+                            int64_t n_products, int64_t max_row_products, int64_t nnz_out,
                             int64_t* out_row, int64_t* out_col, double* out_val, void* stream);
 
 /* Coarse/fine splitting on the strength graph (PMIS: parallel modified independent set).  Stands

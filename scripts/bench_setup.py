@@ -75,10 +75,10 @@ def main():
     t, (plan_PT, vals_PT) = timed(transpose, args.reps)
     res["transpose_plan_ms"] = t
     t, (ap_i, ap_v) = timed(lambda: rt.spgemm(plan_A, vals_A, plan_P, pv), args.reps)
-    res["spgemm_AP_ms"], res["nnz_AP"] = t, int(ap_v.numel())
+    res["spgemm_AP_ms"], res["nnz_AP"], res["spgemm_AP_info"] = t, int(ap_v.numel()), dict(rt.spgemm.last)
     plan_AP = rt.Plan.from_coo(ap_i, n, nc)
     t, (ac_i, ac_v) = timed(lambda: rt.spgemm(plan_PT, vals_PT, plan_AP, ap_v), args.reps)
-    res["spgemm_PtAP_ms"], res["nnz_Ac"] = t, int(ac_v.numel())
+    res["spgemm_PtAP_ms"], res["nnz_Ac"], res["spgemm_PtAP_info"] = t, int(ac_v.numel()), dict(rt.spgemm.last)
     res["galerkin_ms"] = res["spgemm_AP_ms"] + res["spgemm_PtAP_ms"]
     res["setup_total_ms"] = sum(res[k] for k in ("soc_classic_ms", "direct_interp_ms", "prolongator_assembly_ms",
                                                  "transpose_plan_ms", "galerkin_ms")) + (

@@ -2,9 +2,10 @@
 assembly, the SpGEMM behind the Galerkin operator and the PMIS coarse/fine splitting, each against
 its CPU oracle on the same inputs.
 
-Bars: sparsity patterns, C/F flags and the prolongator values bit-exact; SpGEMM values bit-exact
-against a sequential restatement of its documented summation order and <= 1e-5 / 1e-12 against
-torch.sparse on the CPU (the reference's VCycle.py:209 path, whose summation order differs).
+Bars: sparsity patterns, C/F flags and the prolongator values bit-exact; SpGEMM values (both the
+row-local and the expand-sort-compress path) bit-exact against a sequential restatement of the
+documented summation order and <= 1e-5 / 1e-12 against torch.sparse on the CPU (the reference's
+VCycle.py:209 path, whose summation order differs).
 """
 import numpy as np
 import pytest
@@ -99,13 +100,15 @@ def _sequential_product(Xm, Xd, Ym, Yd):
 @pytest.mark.parametrize("dt", [torch.float32, torch.float64])
 def test_spgemm_bit_exact_and_vs_torch_sparse(G, dev, dt):
     rt = G.runtime
+    paths = set()
     for (m, k, n, dx, dy, seed) in ((40, 30, 50, 0.15, 0.2, 1), (200, 200, 200, 0.03, 0.03, 2), (7, 1, 9, 0.9, 0.9, 3),
-                                    (64, 80, 3, 0.1, 0.5, 4)):
+                                    (64, 80, 3, 0.1, 0.5, 4), (40, 30, 300, 0.5, 0.5, 5), (300, 70, 64, 0.2, 0.9, 6)):
         xi, xv, Xm, Xd = _random_sparse(m, k, dx, dt, seed, empty_rows=(0, m - 1))
-        yi, yv, Ym, Yd = _random_sparse(k, n, dy, dt, seed + 100, empty_rows=(k // 2,))
+        yi, yv, Ym, Yd = _random_sparse(k, n, dy, dt, seed + 100, empty_rows=(k // 2,) if k > 1 else ())
         px = rt.Plan.from_coo(xi.to(dev), m, k)
         py = rt.Plan.from_coo(yi.to(dev), k, n)
         zi, zv = rt.spgemm(px, xv.to(dev), py, yv.to(dev))
+        paths.add(rt.spgemm.last["path"])
         seen, acc = _sequential_product(Xm, Xd, Ym, Yd)
         ref_idx = seen.nonzero().t().contiguous()
         assert torch.equal(zi.cpu(), ref_idx)                              # pattern + (row, col) order
@@ -113,6 +116,7 @@ def test_spgemm_bit_exact_and_vs_torch_sparse(G, dev, dt):
         ts = (torch.sparse_coo_tensor(xi, xv, (m, k)) @ torch.sparse_coo_tensor(yi, yv, (k, n))).to_dense()
         mine = torch.sparse_coo_tensor(zi.cpu(), zv.cpu(), (m, n)).to_dense()
         assert relerr(mine, ts) <= TOL[dt]
+    assert {"row-local", "esc"} <= paths, paths        # both paths ran (and agree with the same emulation)
     # empty operands
     pe = rt.Plan.from_coo(torch.zeros(2, 0, dtype=torch.int64, device=dev), 5, 4)
     py = rt.Plan.from_coo(torch.tensor([[0, 3], [1, 2]], device=dev), 4, 6)
@@ -133,7 +137,8 @@ def test_spgemm_bit_exact_and_vs_torch_sparse(G, dev, dt):
     # argument errors come back as codes
     import ctypes
     n_prod = ctypes.c_int64()
-    assert G.lib.glab_spgemm_products(py.handle, py.handle, None, ctypes.byref(n_prod), None) == -1   # 6 != 4
+    assert G.lib.glab_spgemm_products(py.handle, py.handle, None, ctypes.byref(n_prod), ctypes.byref(n_prod),
+                                      None) == -1                          # inner dimensions 6 != 4
 
 
 @pytest.mark.parametrize("dt", [torch.float32, torch.float64])
