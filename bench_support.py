@@ -31,7 +31,9 @@ class SingleGpuSmoother:
         self.n_local = self.n = n
         self.nnz_local = self.nnz_global = self.plan.nnz
         self.setup_info = {"generate_ms": (t1 - t0) * 1e3, "plan_build_ms": (t2 - t1) * 1e3,
-                           "plan_identity_perm": self.plan.identity, "max_row_nnz": self.plan.max_row_nnz}
+                           "plan_identity_perm": self.plan.identity, "max_row_nnz": self.plan.max_row_nnz,
+                           "index_bytes_streamed": self.plan.index_bytes}
+        self.index_bytes = self.plan.index_bytes
         torch.manual_seed(24601)
         self.b_host = torch.rand(n, 1).pin_memory()
         self.x_host = torch.rand(n, 1).pin_memory()

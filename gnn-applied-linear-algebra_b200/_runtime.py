@@ -92,6 +92,9 @@ class Plan:
               "glab_plan_info")
         self.n_rows, self.n_cols, self.nnz = n_rows.value, n_cols.value, nnz.value
         self.max_row_nnz, self.identity = mx.value, bool(ident.value)
+        iw = ctypes.c_int32()
+        check(lib.glab_plan_index_width(self._h, ctypes.byref(iw)), "glab_plan_index_width")
+        self.index_bytes = iw.value      # 2: 16-bit row-relative column indices are streamed, 4: int32
 
     @property
     def handle(self):

@@ -487,10 +487,21 @@ static int launch_pipe_halo(const glab_plan* p, const T* vals, const T* x, const
 
 // TMA pipeline launch.  Returns kNoPipe if the operator does not fit the pipeline (caller falls
 // back to the generic chunked kernel), 0 on success, or an error code.
+template <typename T, int K, int U, class Epi, bool IDX16>
+static int launch_pipe_impl(const glab_plan* p, const T* vals, const T* x, const Epi& epi, int64_t row_begin,
+                            int64_t row_end, void* stream);
+
 template <typename T, int K, int U, class Epi>
 static int launch_pipe_u(const glab_plan* p, const T* vals, const T* x, const Epi& epi, int64_t row_begin,
                          int64_t row_end, void* stream, const glab_halo_step* h) {
   if (h) return launch_pipe_halo<T, K, U>(p, vals, x, epi, stream, h);
+  if (p->coldelta) return launch_pipe_impl<T, K, U, Epi, true>(p, vals, x, epi, row_begin, row_end, stream);
+  return launch_pipe_impl<T, K, U, Epi, false>(p, vals, x, epi, row_begin, row_end, stream);
+}
+
+template <typename T, int K, int U, class Epi, bool IDX16>
+static int launch_pipe_impl(const glab_plan* p, const T* vals, const T* x, const Epi& epi, int64_t row_begin,
+                            int64_t row_end, void* stream) {
   if (!tuning().pipe) return kNoPipe;
   // 16-byte granule preconditions of the bulk copies (see k_row_pipe)
   if ((reinterpret_cast<uintptr_t>(p->rowptr) & 15) || ((row_begin * 4) & 15)) return kNoPipe;
@@ -503,14 +514,14 @@ static int launch_pipe_u(const glab_plan* p, const T* vals, const T* x, const Ep
   PipeLayout L;
   int off = 0;
   L.off_row = off; off += round_up((kThreads + 1) * 4 + 32, 128);
-  L.off_col = off; off += round_up((int)slots * 4 + 32, 128);
+  L.off_col = off; off += round_up((int)slots * (IDX16 ? 2 : 4) + 32, 128);
   L.off_val = off; off += round_up((int)slots * (int)sizeof(T) + 32, 128);
   for (int i = 0; i < kMaxStreams; ++i) {
     L.off_stream[i] = off;
     if (i < Epi::kStreams) off += round_up(kThreads * epi.stream_width(i) * (int)sizeof(T) + 32, 128);
   }
   L.stage_bytes = off;
-  auto kern = k_row_pipe<T, K, U, Epi, false>;
+  auto kern = k_row_pipe<T, K, U, Epi, false, IDX16>;
   static int max_smem_dev[kMaxDevices] = {};  // per instantiation and device: 227 KB minus static smem
   int& max_smem = max_smem_dev[p->device % kMaxDevices];
   if (!max_smem) {
@@ -542,7 +553,7 @@ static int launch_pipe_u(const glab_plan* p, const T* vals, const T* x, const Ep
   if (grid > kMaxReduceBlocks) grid = kMaxReduceBlocks;
   if (grid > ntiles) grid = ntiles;
   if (grid < 1) grid = 1;
-  TileArgs<T> a{p->rowptr, p->colidx, vals, (int)row_begin, (int)row_end, (int)slots};
+  TileArgs<T> a{p->rowptr, p->colidx, vals, (int)row_begin, (int)row_end, (int)slots, IDX16 ? p->coldelta : nullptr};
   return launch_pdl(kern, grid, kPipeThreads, smem, as_stream(stream), tuning().pdl != 0, a, x, epi, ntiles, L,
                     NoHalo{});
 }

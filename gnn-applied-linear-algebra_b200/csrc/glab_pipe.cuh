@@ -141,10 +141,15 @@ __device__ __forceinline__ void load_vec_cg(T (&dst)[K], const T* p) {
 // (only the colidx / vals slices, which start at an arbitrary CSR slot, carry a lead offset).
 // U = gathers kept in flight per thread per pass; rows of exactly U entries (every interior row
 // of a U-point stencil) take an unpredicated straight-line path.
-template <typename T, int K, int U, class Epi, bool HALO>
+// IDX16: the column indices are streamed as 2-byte offsets from the row (a.coldelta; banded
+// operators, single-GPU plans only) instead of 4-byte absolute indices -- 2 B less HBM traffic
+// per nonzero, the only per-nonzero bytes besides the value itself.
+template <typename T, int K, int U, class Epi, bool HALO, bool IDX16 = false>
 __global__ void __launch_bounds__(kPipeThreads, (K * sizeof(T) <= 8) ? 4 : 2)
 k_row_pipe(TileArgs<T> a, const T* __restrict__ x, Epi epi, int ntiles, PipeLayout L,
            typename std::conditional<HALO, HaloCtl, NoHalo>::type h) {
+  static_assert(!(HALO && IDX16), "halo plans renumber their columns: no relative 16-bit indices");
+  using ColT = typename std::conditional<IDX16, int16_t, int32_t>::type;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw);
   uint64_t* empty = full + L.stages;
@@ -264,7 +269,8 @@ k_row_pipe(TileArgs<T> a, const T* __restrict__ x, Epi epi, int ntiles, PipeLayo
         const uint32_t nb_r = (uint32_t)(((r1 - r0 + 1) * 4 + 15) & ~15);
         uint32_t total = nb_r;
         if (e1 > e0) {
-          align16(a.colidx + e0, (e1 - e0) * 4, src_c, nb_c);
+          if constexpr (IDX16) align16(a.coldelta + e0, (e1 - e0) * 2, src_c, nb_c);
+          else align16(a.colidx + e0, (e1 - e0) * 4, src_c, nb_c);
           align16(a.vals + e0, (e1 - e0) * (int)sizeof(T), src_v, nb_v);
           total += nb_c + nb_v;
         }
@@ -307,7 +313,9 @@ k_row_pipe(TileArgs<T> a, const T* __restrict__ x, Epi epi, int ntiles, PipeLayo
       if (r < r1) {
         const int e0 = srow[0];
         const int rs = srow[tid], re = srow[tid + 1];
-        const int32_t* scol = reinterpret_cast<const int32_t*>(sb + L.off_col) + lead_elems(a.colidx + e0, 4) - e0;
+        const ColT* scol = reinterpret_cast<const ColT*>(sb + L.off_col) - e0 +
+                           (IDX16 ? lead_elems(a.coldelta + e0, 2) : lead_elems(a.colidx + e0, 4));
+        const int cbase = IDX16 ? r : 0;  // relative indices are offsets from the row
         const T* sval = reinterpret_cast<const T*>(sb + L.off_val) + lead_elems(a.vals + e0, sizeof(T)) - e0;
         T acc[K];
 #pragma unroll
@@ -316,7 +324,7 @@ k_row_pipe(TileArgs<T> a, const T* __restrict__ x, Epi epi, int ntiles, PipeLayo
           // rows that read the halo tail: L2-coherent gathers (the tail was written by peers)
           for (int j = rs; j < re; ++j) {
             T xv[K];
-            load_vec_cg<T, K>(xv, x + (size_t)scol[j] * K);
+            load_vec_cg<T, K>(xv, x + (size_t)(cbase + (int)scol[j]) * K);
             const T v = sval[j];
 #pragma unroll
             for (int c = 0; c < K; ++c) acc[c] = acc[c] + v * xv[c];
@@ -326,7 +334,7 @@ k_row_pipe(TileArgs<T> a, const T* __restrict__ x, Epi epi, int ntiles, PipeLayo
           T xv[U][K];
 #pragma unroll
           for (int u = 0; u < U; ++u) {
-            const int col = scol[rs + u];
+            const int col = cbase + (int)scol[rs + u];
             vv[u] = sval[rs + u];
             load_vec<T, K>(xv[u], x + (size_t)col * K);
           }
@@ -342,7 +350,7 @@ k_row_pipe(TileArgs<T> a, const T* __restrict__ x, Epi epi, int ntiles, PipeLayo
 #pragma unroll
             for (int u = 0; u < U; ++u) {
               if (base + u < re) {
-                const int col = scol[base + u];
+                const int col = cbase + (int)scol[base + u];
                 vv[u] = sval[base + u];
                 load_vec<T, K>(xv[u], x + (size_t)col * K);
               }

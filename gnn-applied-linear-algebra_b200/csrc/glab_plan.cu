@@ -10,6 +10,7 @@
 // Slow path (arbitrary edge order): stable LSD radix sort of (row, edge id) with CUB -- setup
 // only, never on a layer step -- then the same boundary pass.
 #include <cub/device/device_radix_sort.cuh>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include "glab_common.cuh"
@@ -71,6 +72,22 @@ __global__ void k_max_row(const int32_t* __restrict__ rowptr, int64_t n_rows, in
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, o));
   if ((threadIdx.x & 31) == 0 && m > 0) atomicMax(out, m);
+}
+
+// delta[slot] = col - row as int16; flags |= 4 when some delta does not fit
+__global__ void k_col_delta(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ colidx,
+                            int64_t n_rows, int16_t* __restrict__ delta, int* flags) {
+  int f = 0;
+  for (int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; r < n_rows;
+       r += (int64_t)gridDim.x * blockDim.x) {
+    const int e1 = rowptr[r + 1];
+    for (int e = rowptr[r]; e < e1; ++e) {
+      const int64_t d = (int64_t)colidx[e] - r;
+      if (d < -32767 || d > 32767) f = 4;
+      delta[e] = (int16_t)d;
+    }
+  }
+  if (f) atomicOr(flags, f);
 }
 
 __global__ void k_validate_csr(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col,
@@ -182,6 +199,7 @@ static void plan_free(glab_plan* p) {
   if (p->rowptr) cudaFree(p->rowptr);
   if (p->colidx) cudaFree(p->colidx);
   if (p->perm) cudaFree(p->perm);
+  if (p->coldelta) cudaFree(p->coldelta);
   if (p->owned_vals) cudaFree(p->owned_vals);
   delete p;
 }
@@ -199,6 +217,7 @@ static int plan_alloc(int64_t n_rows, int64_t n_cols, int64_t nnz, glab_plan** o
   p->rowptr = nullptr;
   p->colidx = nullptr;
   p->perm = nullptr;
+  p->coldelta = nullptr;
   p->max_row_nnz = 0;
   p->owned_vals = nullptr;
   p->owned_vals_bytes = 0;
@@ -213,6 +232,34 @@ static int plan_alloc(int64_t n_rows, int64_t n_cols, int64_t nnz, glab_plan** o
     return e == cudaErrorMemoryAllocation ? GLAB_E_NOMEM : (int)e;
   }
   *out = p;
+  return 0;
+}
+
+// 2-byte relative column indices for banded operators (every |col - row| <= 32767): the pipeline
+// kernels then stream 2 B instead of 4 B of index per nonzero.  GLAB_IDX16=0 disables it.  Leaves
+// p->coldelta NULL when the operator is not banded enough (or on allocation failure: optional).
+static int plan_build_coldelta(glab_plan* p, int* d_flags, cudaStream_t st) {
+  const char* env = getenv("GLAB_IDX16");
+  if (env && atoi(env) == 0) return 0;
+  if (p->nnz == 0 || p->n_rows == 0) return 0;
+  int16_t* d = nullptr;
+  if (cudaMalloc(&d, (size_t)(p->nnz + 16) * sizeof(int16_t)) != cudaSuccess) {
+    cudaGetLastError();
+    return 0;
+  }
+  cudaError_t e = cudaMemsetAsync(d_flags, 0, sizeof(int), st);
+  if (e == cudaSuccess) {
+    k_col_delta<<<grid_for(p->n_rows, p->sm_count), 256, 0, st>>>(p->rowptr, p->colidx, p->n_rows, d, d_flags);
+    e = cudaGetLastError();
+  }
+  int h = 0;
+  if (e == cudaSuccess) e = cudaMemcpyAsync(&h, d_flags, sizeof(int), cudaMemcpyDeviceToHost, st);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+  if (e != cudaSuccess || (h & 4)) {
+    cudaFree(d);
+    return e == cudaSuccess ? 0 : (int)e;
+  }
+  p->coldelta = d;
   return 0;
 }
 
@@ -299,6 +346,7 @@ extern "C" int glab_plan_create(int64_t n_rows, int64_t n_cols, int64_t nnz, con
   if ((e = cudaStreamSynchronize(st)) != cudaSuccess) return fail((int)e);
   if ((e = cudaGetLastError()) != cudaSuccess) return fail((int)e);
   p->max_row_nnz = h_flags[1];
+  if (int rcd = plan_build_coldelta(p, d_flags, st)) return fail(rcd);
   cudaFree(d_flags);
   if (keys_in) cudaFree(keys_in);
   if (keys_out) cudaFree(keys_out);
@@ -339,6 +387,7 @@ extern "C" int glab_plan_create_csr(int64_t n_rows, int64_t n_cols, int64_t nnz,
   if ((e = cudaGetLastError()) != cudaSuccess) return fail((int)e);
   if (h_flags[0]) return fail(GLAB_E_RANGE);
   p->max_row_nnz = h_flags[1];
+  if (int rcd = plan_build_coldelta(p, d_flags, st)) return fail(rcd);
   cudaFree(d_flags);
   *out = p;
   return 0;
@@ -357,6 +406,12 @@ extern "C" int glab_plan_info(const glab_plan* p, int64_t* n_rows, int64_t* n_co
   if (nnz) *nnz = p->nnz;
   if (max_row_nnz) *max_row_nnz = p->max_row_nnz;
   if (identity_perm) *identity_perm = p->perm ? 0 : 1;
+  return 0;
+}
+
+extern "C" int glab_plan_index_width(const glab_plan* p, int32_t* bytes) {
+  if (!p || !bytes) return GLAB_E_ARG;
+  *bytes = p->coldelta ? 2 : 4;
   return 0;
 }
 

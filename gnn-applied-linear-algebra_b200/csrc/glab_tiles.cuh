@@ -22,6 +22,7 @@ template <typename T> struct TileArgs {
   const T* __restrict__ vals;
   int row_begin, row_end;
   int cap;  // staging capacity in CSR slots (multiple of 32)
+  const int16_t* __restrict__ coldelta;  // col - row per slot (pipeline kernels with IDX16), else NULL
 };
 
 __host__ __device__ inline size_t round16(size_t x) { return (x + 15) & ~(size_t)15; }

@@ -76,6 +76,11 @@ int glab_plan_info(const glab_plan* plan, int64_t* n_rows, int64_t* n_cols, int6
                    int32_t* max_row_nnz, int32_t* identity_perm);
 int glab_plan_csr(const glab_plan* plan, const int32_t** rowptr, const int32_t** colidx,
                   const int32_t** perm);
+/* Bytes of column index the single-GPU pipeline kernels stream per nonzero: 2 when the plan also
+ * holds 16-bit row-relative indices (built automatically when every |col - row| <= 32767, i.e.
+ * for banded operators such as the 2-D stencils up to a 32767-wide grid line; the environment
+ * variable GLAB_IDX16=0 at plan creation disables it), else 4.  Results do not depend on it. */
+int glab_plan_index_width(const glab_plan* plan, int32_t* bytes);
 /* L2 residency for operators that fit the 126 MB L2 (e.g. one rank's block of a row-partitioned
  * operator): adopt copies the CSR-ordered values into plan-owned storage directly behind colidx
  * (*vals_out points at the copy; use it instead of the caller's array), l2_persist then marks

@@ -650,3 +650,164 @@ def test_config4_full_size_masks_bit_exact(G, dev):
         assert bool(same_bits.all()), name
         del want, same_bits
     assert bool(torch.isnan(w_s).any()) and bool((S_s > 0).any()) and not bool((S_s > 0).all())
+
+
+def _grid_stencil_apply(x, c0, ce, cn, cc):
+    """9-point constant stencil with zero (eliminated Dirichlet) boundary on an [N, N] grid,
+    written with shifted slices -- independent of every CSR code path."""
+    y = c0 * x
+    y[:, 1:] += ce * x[:, :-1]
+    y[:, :-1] += ce * x[:, 1:]
+    y[1:, :] += cn * x[:-1, :]
+    y[:-1, :] += cn * x[1:, :]
+    y[1:, 1:] += cc * x[:-1, :-1]
+    y[1:, :-1] += cc * x[:-1, 1:]
+    y[:-1, 1:] += cc * x[1:, :-1]
+    y[:-1, :-1] += cc * x[1:, 1:]
+    return y
+
+
+def _grid_power_method(b0_grid, iters, c):
+    b = b0_grid.double()
+    for _ in range(iters):
+        b = _grid_stencil_apply(b, *c)
+        nrm = b.norm()
+        b = b / nrm
+    ab = _grid_stencil_apply(b, *c)
+    return ((b * ab).sum() / (b * b).sum()).item(), nrm.item(), b
+
+
+def test_config3_full_size_power_method(G, dev):
+    """BASELINE config 3 at FULL size on one GPU: PowerMethodGNN(100) on the 8192 x 8192 heat-equation
+    FEM operator (67.1 M rows, 603.9 M nnz, fp32) against an independent fp64 power iteration that
+    applies the closed-form stencil (centre 8/3, the eight neighbours -1/3) with shifted
+    grid slices.  That reference is first checked against the CPU oracle at a size the oracle holds."""
+    c = (8.0 / 3.0, -1.0 / 3.0, -1.0 / 3.0, -1.0 / 3.0)
+    # the grid reference == the oracle (fp64, small)
+    Ns = 48
+    ei, ev = G.generators.heat_fem_2d((Ns + 1, Ns + 1), (1.0, 1.0), torch.float64)
+    torch.manual_seed(24601)
+    b0 = torch.rand(Ns * Ns, 1, dtype=torch.float64)
+    g_ref = port.power_method(30, torch.cat([b0, torch.zeros_like(b0)], 1), ei, torch.cat([ev, torch.zeros_like(ev)], 1),
+                              torch.zeros(3, dtype=torch.float64))[2]
+    lam_s, nrm_s, _ = _grid_power_method(b0.view(Ns, Ns), 30, c)
+    assert abs(lam_s - g_ref[2].item()) <= 1e-12 * abs(lam_s) and abs(nrm_s - g_ref[0].item()) <= 1e-12 * nrm_s
+    # full size
+    N, iters = 8192, 100
+    n = N * N
+    ei, ev = G.generators.heat_fem_2d((N + 1, N + 1), (1.0, 1.0), torch.float32, dev)
+    assert ei.shape[1] == (3 * N - 2) ** 2
+    b0 = torch.rand(n, 1, generator=torch.Generator().manual_seed(24601)).to(dev)
+    va = torch.cat([b0, torch.zeros_like(b0)], 1)
+    ea = torch.cat([ev, torch.zeros_like(ev)], 1)
+    v, e, g = G.PowerMethodGNN.PowerMethodGNN(iters)(va, ei, ea, torch.zeros(3, device=dev), None)
+    assert v.shape == (n, 2) and e.shape == (ei.shape[1], 2) and g.shape == (3,)
+    del e, ea
+    lam_ref, nrm_ref, b_ref = _grid_power_method(b0.view(N, N), iters, c)
+    assert abs(g[2].item() - lam_ref) <= 1e-5 * abs(lam_ref), (g[2].item(), lam_ref)
+    assert abs(g[0].item() - nrm_ref) <= 1e-5 * abs(nrm_ref), (g[0].item(), nrm_ref)
+    assert lam_ref < 4.0                                        # unconverged estimate below lambda_max -> 4
+    # the iterate itself (normalised vector after the last step)
+    assert relerr(v[:, 0].view(N, N), b_ref) <= 1e-5
+
+
+def test_config5_full_size_vcycle_multi_rhs(G, dev):
+    """BASELINE config 5 at FULL size on one GPU: two-grid V-cycle (VCycle.py:193-237) on the
+    8192 x 8192 Laplacian (67.1 M rows) with 8 right-hand-side columns, fp32.  Size-independent
+    properties: every column's residual norm decreases cycle by cycle, and column 3 of the batched
+    run equals the same cycle run with that column alone, bit for bit (the k = 8 kernels and the
+    k = 1 kernels accumulate in the same order)."""
+    V = G.VCycle
+    N, k = 8192, 8
+    n = N * N
+    ei, ev = G.UtilsGNN.laplacianfun_torch(N, device=dev)
+    A = torch.sparse_coo_tensor(ei, ev.flatten().float(), (n, n))
+    del ei, ev
+    gen = torch.Generator().manual_seed(24601)
+    b = torch.rand(n, k, generator=gen).to(dev)
+    x = torch.zeros(n, k, device=dev)
+    x1 = torch.zeros(n, 1, device=dev)
+    b1 = b[:, 3:4].contiguous()
+    norms = [torch.norm(V.runResidual(A, b, x), dim=0)]
+    for _ in range(2):
+        x = V.runVCycle(A, b, x, 3, 3, 5, True)
+        x1 = V.runVCycle(A, b1, x1, 3, 3, 5, True)
+        norms.append(torch.norm(V.runResidual(A, b, x), dim=0))
+        assert torch.equal(x[:, 3:4], x1)
+    for a_, b_ in zip(norms, norms[1:]):
+        assert bool((b_ < a_).all()), norms
+    tg = V._two_grid(A, None)
+    assert tg.P.shape == (n, n // 2) and tg.Ac.shape == (n // 2, n // 2)
+
+
+@pytest.mark.parametrize("dt", [torch.float32, torch.float64])
+def test_index16_and_index32_plans_agree(G, dev, dt, monkeypatch):
+    """Banded operators get 16-bit row-relative column indices in their plan (2 B instead of 4 B of
+    index traffic per nonzero in the pipeline kernels).  Every fused step must give bit-identical
+    results with and without them (GLAB_IDX16=0 at plan creation), non-banded operators must stay
+    on int32, and the band limit |col - row| <= 32767 is respected exactly."""
+    rt = G.runtime
+    torch.manual_seed(7)
+    for kind, N in (("laplace", 70), ("heat", 45)):
+        if kind == "laplace":
+            ei, ev = G.UtilsGNN.laplacianfun_torch(N, device=dev)
+        else:
+            ei, ev = G.generators.heat_fem_2d((N + 1, N + 1), (1.0, 2.0), torch.float64, dev)
+        ev = ev.to(dt).contiguous()
+        n = int(ei.max().item()) + 1
+        monkeypatch.setenv("GLAB_IDX16", "1")
+        p16 = rt.Plan.from_coo(ei, n)
+        monkeypatch.setenv("GLAB_IDX16", "0")
+        p32 = rt.Plan.from_coo(ei, n)
+        monkeypatch.delenv("GLAB_IDX16")
+        assert p16.index_bytes == 2 and p32.index_bytes == 4
+        vals = ev.view(-1)
+        diag = G.generators.diagonal_of(ei, ev, n).reshape(-1).contiguous()
+        w = torch.tensor([0.7], dtype=dt, device=dev)
+        sc = torch.tensor([0.3, -0.25, 0.11], dtype=dt, device=dev)
+        for k in (1, 2, 8):
+            x, b = torch.rand(n, k, dtype=dt, device=dev), torch.rand(n, k, dtype=dt, device=dev)
+            outs = []
+            for plan in (p16, p32):
+                y = rt.spmm(plan, vals, x)
+                r = rt.residual(plan, vals, x, b)
+                xj = rt.jacobi(plan, vals, diag, b, x, torch.empty_like(x), w)
+                xo, rr, pp = torch.empty_like(x), torch.empty_like(x), torch.empty_like(x)
+                rt.cheby_first(plan, vals, b, x, xo, rr, pp, sc[0:1])
+                p2 = torch.empty_like(x)
+                rt.cheby_next(plan, vals, pp, p2, rr, xo, sc[0:1], sc[1:2], sc[2:3])
+                half = (n // 2) // 256 * 256          # row ranges (16-byte aligned starts stay on the pipeline)
+                y2 = torch.full_like(y, float("nan"))
+                rt.spmm(plan, vals, x, y2, rows=(0, half))
+                rt.spmm(plan, vals, x, y2, rows=(half, n))
+                outs.append((y, r, xj, xo, rr, p2, y2))
+            for a_, b_ in zip(*outs):
+                assert torch.equal(a_, b_)
+            assert torch.equal(outs[0][0], outs[0][6])
+    # power-method scalars through the reducing epilogues
+    ei, ev = G.UtilsGNN.laplacianfun_torch(33, device=dev)
+    ev = ev.to(dt)
+    x = torch.rand(33 * 33, 1, dtype=dt, device=dev)
+    va, ea = torch.cat([x, torch.zeros_like(x)], 1), torch.cat([ev, torch.zeros_like(ev)], 1)
+    g16 = G.PowerMethodGNN.PowerMethodGNN(7)(va, ei, ea, torch.zeros(3, dtype=dt), None)[2]
+    monkeypatch.setenv("GLAB_IDX16", "0")
+    rt.clear_caches()
+    g32 = G.PowerMethodGNN.PowerMethodGNN(7)(va, ei.clone(), ea, torch.zeros(3, dtype=dt), None)[2]
+    monkeypatch.delenv("GLAB_IDX16")
+    rt.clear_caches()
+    assert torch.equal(g16, g32)
+    # band limit and non-banded operators
+    n = 70000
+    d = torch.arange(n, device=dev)
+    for off, want in ((32767, 2), (32768, 4)):
+        rows = torch.cat([d, d[:n - off], d[off:]])
+        cols = torch.cat([d, d[:n - off] + off, d[off:] - off])
+        order = torch.argsort(rows * n + cols)
+        ei = torch.stack([rows[order], cols[order]])
+        plan = rt.Plan.from_coo(ei, n)
+        assert plan.index_bytes == want, (off, plan.index_bytes)
+        v = torch.rand(ei.shape[1], dtype=dt, device=dev)
+        x = torch.rand(n, 1, dtype=dt, device=dev)
+        y = rt.spmm(plan, v, x)
+        A = torch.sparse_coo_tensor(ei, v.double(), (n, n)).to_sparse_csr()
+        assert relerr(y, A @ x.double()) <= TOL[dt]
