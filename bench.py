@@ -370,7 +370,7 @@ def main_gpu(args):
     achieved = bytes_jac / (jac_ms * 1e-3) / 1e9
     traffic = committed_traffic()
     idx_bytes = getattr(prob, "index_bytes", 4)
-    moved_jac = bytes_jac - (4 - idx_bytes) * prob.nnz_local   # what the kernel actually streams
+    moved_jac = int(bytes_jac - (4 - idx_bytes) * prob.nnz_local)   # what the kernel actually streams
     line = {
         "metric": "fused SpMV-layer nnz/s", "value": value, "unit": "nnz/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
@@ -383,10 +383,13 @@ def main_gpu(args):
                      "moved_gbs": moved_jac / (jac_ms * 1e-3) / 1e9, "moved_frac": moved_jac / (jac_ms * 1e-3) / 1e9 / peak,
                      "note": ("algorithmic bytes use SURVEY 8d's 4-byte column indices; with index_bytes_streamed = 2 the "
                               "kernel streams 16-bit row-relative indices, so it moves fewer bytes than the algorithmic "
-                              "count and `frac` can exceed 1; `moved_frac` is the fraction of peak actually moved"),
+                              "count and `frac` can exceed 1; `moved_frac` is the fraction of peak actually moved "
+                              "(row blocks of a partitioned operator: fractional = share of 256-row tiles on 16-bit "
+                              "indices; the tiles that read the halo tail stay on int32)"),
                      "gnnz_per_s": prob.nnz_local / (jac_ms * 1e-3) / 1e9,
                      "traffic": None if not traffic else traffic.get(
-                         "jacobi_dram_bytes_per_launch_idx16" if idx_bytes == 2 else "jacobi_dram_bytes_per_launch"),
+                         "jacobi_dram_bytes_per_launch_idx16" if idx_bytes == 2 else "jacobi_dram_bytes_per_launch")
+                     if world == 1 else None,
                      "traffic_source": None if not traffic else traffic.get(
                          "source_idx16" if idx_bytes == 2 else "source")},
         "e2e": {"value": e2e_value, "unit": "nnz/s", "ms_per_step": e2e_ms / args.steps,

@@ -147,7 +147,10 @@ class PartitionedSmoother:
         self.nnz_global = int(z.item())
         self.setup_info = {"generate_ms": (t1 - t0) * 1e3, "plan_build_ms": (t2 - t1) * 1e3, "engine": engine,
                            "rows_local": nl, "halo_rows": self.halo.n_halo, "interior": [self.op.lo, self.op.hi],
-                           "cuda_graph": bool(use_graph)}
+                           "cuda_graph": bool(use_graph),
+                           "index16_tiles": [self.op.plan.index16_tiles, self.op.plan.tiles]}
+        # effective bytes of column index streamed per nonzero (tiles with 16-bit indices stream 2)
+        self.index_bytes = 4 - 2.0 * self.op.plan.index16_tiles / max(self.op.plan.tiles, 1)
         g = torch.Generator().manual_seed(24601 + rank)
         self.b_host = torch.rand(nl, 1, generator=g).pin_memory()
         self.x_host = torch.rand(nl, 1, generator=g).pin_memory()

@@ -46,6 +46,7 @@ _sig("glab_plan_destroy", c_int, P)
 _sig("glab_plan_info", c_int, P, POINTER(_I64), POINTER(_I64), POINTER(_I64), POINTER(_I32), POINTER(_I32))
 _sig("glab_plan_csr", c_int, P, POINTER(P), POINTER(P), POINTER(P))
 _sig("glab_plan_index_width", c_int, P, POINTER(_I32))
+_sig("glab_plan_index16_tiles", c_int, P, POINTER(_I64), POINTER(_I64))
 _sig("glab_plan_adopt_vals_f32", c_int, P, P, POINTER(P), P)
 _sig("glab_plan_adopt_vals_f64", c_int, P, P, POINTER(P), P)
 _sig("glab_plan_l2_persist", c_int, P, c_int, P)

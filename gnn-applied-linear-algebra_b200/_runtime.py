@@ -94,7 +94,10 @@ class Plan:
         self.max_row_nnz, self.identity = mx.value, bool(ident.value)
         iw = ctypes.c_int32()
         check(lib.glab_plan_index_width(self._h, ctypes.byref(iw)), "glab_plan_index_width")
-        self.index_bytes = iw.value      # 2: 16-bit row-relative column indices are streamed, 4: int32
+        self.index_bytes = iw.value      # 2: every tile streams 16-bit row-relative column indices, 4: not all
+        t16, tt = ctypes.c_int64(), ctypes.c_int64()
+        check(lib.glab_plan_index16_tiles(self._h, ctypes.byref(t16), ctypes.byref(tt)), "glab_plan_index16_tiles")
+        self.index16_tiles, self.tiles = t16.value, tt.value
 
     @property
     def handle(self):

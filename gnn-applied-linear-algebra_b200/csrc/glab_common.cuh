@@ -13,7 +13,9 @@
 // The CSR structure of one operator (or one row block of it) resident in HBM.
 //   rowptr [n_rows+1] int32, colidx [nnz] int32 (+16 B pad), perm [nnz] int32 or NULL.
 // coldelta [nnz] int16 (+16 B pad) or NULL: 2-byte column indices relative to the row, streamed
-// by the single-GPU pipeline kernels instead of colidx (halves the index traffic).
+// by the pipeline kernels instead of colidx (halves the index traffic) for every 256-row tile
+// whose flag in tile16 is set -- all tiles of a banded operator; all but the wrap-around / halo
+// tiles of a periodic or row-partitioned one.
 // perm[slot] = index of the caller's edge that landed in CSR slot `slot`; NULL when the
 // caller's COO was already row-sorted (all reference generators emit it that way), in which
 // case CSR slot order == edge order and per-edge arrays are used zero-copy.
@@ -24,7 +26,9 @@ struct glab_plan {
   int32_t* rowptr;
   int32_t* colidx;
   int32_t* perm;
-  int16_t* coldelta;       // colidx[slot] - row as int16 when every |col - row| <= 32767 (banded operators), else NULL
+  int16_t* coldelta;       // colidx[slot] - row as int16 (valid in the row tiles flagged in tile16), or NULL
+  uint8_t* tile16;         // [ceil(n_rows/256)]: 1 = every |col - row| of the tile's rows fits int16
+  int64_t tiles16, tiles_total;
   int32_t max_row_nnz;
   void* owned_vals;        // optional plan-owned copy of the values (glab_plan_adopt_vals_*), else NULL
   size_t owned_vals_bytes;

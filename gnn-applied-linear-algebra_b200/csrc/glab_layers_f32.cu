@@ -1,0 +1,3 @@
+// fp32 entry points of the fused layer steps (see glab_layers_impl.cuh).
+#define GLAB_LAYERS_F32
+#include "glab_layers_impl.cuh"

@@ -1,4 +1,4 @@
-// glab_layers.cu -- fused SpMV-bearing layer steps (MatVec, residual, Jacobi, Chebyshev,
+// glab_layers_impl.cuh -- fused SpMV-bearing layer steps (MatVec, residual, Jacobi, Chebyshev,
 // power method, Rayleigh quotient, x^T W x) on the row-tile machinery of glab_tiles.cuh.
 // Each extern "C" entry is ONE kernel launch that replaces one or more reference GN blocks
 // (gathers + edge update + scatter + vertex update); citations are in include/glab.h.
@@ -379,6 +379,24 @@ static int launch_pdl(Kern kern, int grid, int block, size_t smem, cudaStream_t 
 static inline int round_up(int x, int m) { return (x + m - 1) / m * m; }
 template <typename T, int K, int U, class Epi>
 static int launch_pipe_halo(const glab_plan*, const T*, const T*, const Epi&, void*, const glab_halo_step*);
+template <typename T, int K, int U, class Epi, int IDX>
+static int launch_pipe_impl(const glab_plan* p, const T* vals, const T* x, const Epi& epi, int64_t row_begin,
+                            int64_t row_end, void* stream);
+template <typename T, int K, int U, class Epi, int IDX>
+static int launch_pipe_halo_impl(const glab_plan*, const T*, const T*, const Epi&, void*, const glab_halo_step*);
+
+// How the column indices are streamed (k_row_pipe's IDX): 1 = 16-bit row-relative everywhere,
+// 2 = per tile (tile16 flags; needs 256-aligned tiles), 0 = int32.
+// The 16-bit index paths are compiled for fp32 and for the fp64 5-point kernel; the other fp64
+// instantiations sit at their register cap and would spill, so they keep int32 indices.
+template <typename T, int K, int U> constexpr bool idx16_ok() { return sizeof(T) == 4 || (K == 1 && U == 5); }
+
+static inline int index_mode(const glab_plan* p, int64_t row_begin) {
+  if (!p->coldelta || !p->tile16) return 0;
+  if (p->tiles16 == p->tiles_total) return 1;
+  return (row_begin % kThreads == 0) ? 2 : 0;
+}
+
 template <typename T, int K, int U, class Epi>
 static int launch_pipe_u(const glab_plan*, const T*, const T*, const Epi&, int64_t, int64_t, void*,
                          const glab_halo_step*);
@@ -421,6 +439,16 @@ static bool make_pipe_layout(const glab_plan* p, const Epi& epi, PipeLayout& L, 
 template <typename T, int K, int U, class Epi>
 static int launch_pipe_halo(const glab_plan* p, const T* vals, const T* x, const Epi& epi, void* stream,
                             const glab_halo_step* hs) {
+  // interior tiles of a row block have local, in-band columns: they stream 16-bit indices (IDX 2)
+  if constexpr (idx16_ok<T, K, U>()) {
+    if (index_mode(p, 0) != 0) return launch_pipe_halo_impl<T, K, U, Epi, 2>(p, vals, x, epi, stream, hs);
+  }
+  return launch_pipe_halo_impl<T, K, U, Epi, 0>(p, vals, x, epi, stream, hs);
+}
+
+template <typename T, int K, int U, class Epi, int IDX>
+static int launch_pipe_halo_impl(const glab_plan* p, const T* vals, const T* x, const Epi& epi, void* stream,
+                                 const glab_halo_step* hs) {
   if (hs->n_wait < 0 || hs->n_wait > GLAB_MAX_PEERS || hs->n_push < 0 || hs->n_push > GLAB_MAX_PEERS)
     return GLAB_E_ARG;
   if ((hs->n_wait > 0 && (!hs->wait_flags || !hs->wait_target)) || (hs->n_push > 0 && (!hs->push || !hs->push_src)) ||
@@ -437,7 +465,7 @@ static int launch_pipe_halo(const glab_plan* p, const T* vals, const T* x, const
   PipeLayout L;
   int64_t slots;
   if (!make_pipe_layout<T>(p, epi, L, slots)) return GLAB_E_ARG;
-  auto kern = k_row_pipe<T, K, U, Epi, true>;
+  auto kern = k_row_pipe<T, K, U, Epi, true, IDX>;
   static int max_smem_dev[kMaxDevices] = {};
   int& max_smem = max_smem_dev[p->device % kMaxDevices];
   if (!max_smem) {
@@ -481,25 +509,29 @@ static int launch_pipe_halo(const glab_plan* p, const T* vals, const T* x, const
   if (grid > kMaxReduceBlocks) grid = kMaxReduceBlocks;
   if (grid > ntiles + 1) grid = ntiles + 1;
   if (grid < 1) grid = 1;
-  TileArgs<T> a{p->rowptr, p->colidx, vals, 0, (int)n, (int)slots};
+  TileArgs<T> a{p->rowptr, p->colidx, vals, 0, (int)n, (int)slots, IDX ? p->coldelta : nullptr,
+                IDX == 2 ? p->tile16 : nullptr};
   return launch_pdl(kern, grid, kPipeThreads, smem, as_stream(stream), tuning().pdl != 0, a, x, epi, ntiles, L, h);
 }
 
 // TMA pipeline launch.  Returns kNoPipe if the operator does not fit the pipeline (caller falls
 // back to the generic chunked kernel), 0 on success, or an error code.
-template <typename T, int K, int U, class Epi, bool IDX16>
-static int launch_pipe_impl(const glab_plan* p, const T* vals, const T* x, const Epi& epi, int64_t row_begin,
-                            int64_t row_end, void* stream);
 
 template <typename T, int K, int U, class Epi>
 static int launch_pipe_u(const glab_plan* p, const T* vals, const T* x, const Epi& epi, int64_t row_begin,
                          int64_t row_end, void* stream, const glab_halo_step* h) {
   if (h) return launch_pipe_halo<T, K, U>(p, vals, x, epi, stream, h);
-  if (p->coldelta) return launch_pipe_impl<T, K, U, Epi, true>(p, vals, x, epi, row_begin, row_end, stream);
-  return launch_pipe_impl<T, K, U, Epi, false>(p, vals, x, epi, row_begin, row_end, stream);
+  if constexpr (idx16_ok<T, K, U>()) {
+    switch (index_mode(p, row_begin)) {
+      case 1: return launch_pipe_impl<T, K, U, Epi, 1>(p, vals, x, epi, row_begin, row_end, stream);
+      case 2: return launch_pipe_impl<T, K, U, Epi, 2>(p, vals, x, epi, row_begin, row_end, stream);
+      default: break;
+    }
+  }
+  return launch_pipe_impl<T, K, U, Epi, 0>(p, vals, x, epi, row_begin, row_end, stream);
 }
 
-template <typename T, int K, int U, class Epi, bool IDX16>
+template <typename T, int K, int U, class Epi, int IDX>
 static int launch_pipe_impl(const glab_plan* p, const T* vals, const T* x, const Epi& epi, int64_t row_begin,
                             int64_t row_end, void* stream) {
   if (!tuning().pipe) return kNoPipe;
@@ -514,14 +546,14 @@ static int launch_pipe_impl(const glab_plan* p, const T* vals, const T* x, const
   PipeLayout L;
   int off = 0;
   L.off_row = off; off += round_up((kThreads + 1) * 4 + 32, 128);
-  L.off_col = off; off += round_up((int)slots * (IDX16 ? 2 : 4) + 32, 128);
+  L.off_col = off; off += round_up((int)slots * (IDX == 1 ? 2 : 4) + 32, 128);
   L.off_val = off; off += round_up((int)slots * (int)sizeof(T) + 32, 128);
   for (int i = 0; i < kMaxStreams; ++i) {
     L.off_stream[i] = off;
     if (i < Epi::kStreams) off += round_up(kThreads * epi.stream_width(i) * (int)sizeof(T) + 32, 128);
   }
   L.stage_bytes = off;
-  auto kern = k_row_pipe<T, K, U, Epi, false, IDX16>;
+  auto kern = k_row_pipe<T, K, U, Epi, false, IDX>;
   static int max_smem_dev[kMaxDevices] = {};  // per instantiation and device: 227 KB minus static smem
   int& max_smem = max_smem_dev[p->device % kMaxDevices];
   if (!max_smem) {
@@ -553,7 +585,8 @@ static int launch_pipe_impl(const glab_plan* p, const T* vals, const T* x, const
   if (grid > kMaxReduceBlocks) grid = kMaxReduceBlocks;
   if (grid > ntiles) grid = ntiles;
   if (grid < 1) grid = 1;
-  TileArgs<T> a{p->rowptr, p->colidx, vals, (int)row_begin, (int)row_end, (int)slots, IDX16 ? p->coldelta : nullptr};
+  TileArgs<T> a{p->rowptr, p->colidx, vals, (int)row_begin, (int)row_end, (int)slots,
+                IDX ? p->coldelta : nullptr, IDX == 2 ? p->tile16 : nullptr};
   return launch_pdl(kern, grid, kPipeThreads, smem, as_stream(stream), tuning().pdl != 0, a, x, epi, ntiles, L,
                     NoHalo{});
 }
@@ -703,7 +736,9 @@ static int xtax(const glab_plan* p, const T* vals, const T* x, double* sums_out,
 
 using namespace glab;
 
+#ifdef GLAB_LAYERS_F32
 extern "C" int64_t glab_reduce_workspace_bytes(void) { return 64 + (int64_t)kMaxReduceBlocks * 2 * 8; }
+#endif
 
 #define GLAB_INST(SUF, T)                                                                          \
   extern "C" int glab_spmm_##SUF(const glab_plan* p, const T* v, const T* x, int k, T* y,          \
@@ -790,7 +825,13 @@ extern "C" int64_t glab_reduce_workspace_bytes(void) { return 64 + (int64_t)kMax
     return rayleigh<T>(p, v, bi, bo, yo, si, so, ws, 0, p->n_rows, s, h);                          \
   }
 
+// One translation unit per value type (glab_layers_f32.cu / glab_layers_f64.cu) so that the
+// ~700 pipeline-kernel instantiations compile in parallel.
+#ifdef GLAB_LAYERS_F32
 GLAB_INST(f32, float)
-GLAB_INST(f64, double)
 GLAB_HALO_INST(f32, float)
+#endif
+#ifdef GLAB_LAYERS_F64
+GLAB_INST(f64, double)
 GLAB_HALO_INST(f64, double)
+#endif

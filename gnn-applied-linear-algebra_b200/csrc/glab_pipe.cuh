@@ -141,15 +141,16 @@ __device__ __forceinline__ void load_vec_cg(T (&dst)[K], const T* p) {
 // (only the colidx / vals slices, which start at an arbitrary CSR slot, carry a lead offset).
 // U = gathers kept in flight per thread per pass; rows of exactly U entries (every interior row
 // of a U-point stencil) take an unpredicated straight-line path.
-// IDX16: the column indices are streamed as 2-byte offsets from the row (a.coldelta; banded
-// operators, single-GPU plans only) instead of 4-byte absolute indices -- 2 B less HBM traffic
-// per nonzero, the only per-nonzero bytes besides the value itself.
-template <typename T, int K, int U, class Epi, bool HALO, bool IDX16 = false>
+// IDX: how the column indices are streamed.  0 = 4-byte absolute indices (a.colidx).  1 = 2-byte
+// offsets from the row (a.coldelta) in every tile: banded operators, single-GPU plans -- 2 B less
+// HBM traffic per nonzero, the only per-nonzero bytes besides the value itself.  2 = per 256-row
+// tile, a.tile16 says which of the two arrays the tile uses (periodic wrap-around rows, the halo
+// columns of a row block: all other tiles still stream 2-byte indices).
+template <typename T, int K, int U, class Epi, bool HALO, int IDX = 0>
 __global__ void __launch_bounds__(kPipeThreads, (K * sizeof(T) <= 8) ? 4 : 2)
 k_row_pipe(TileArgs<T> a, const T* __restrict__ x, Epi epi, int ntiles, PipeLayout L,
            typename std::conditional<HALO, HaloCtl, NoHalo>::type h) {
-  static_assert(!(HALO && IDX16), "halo plans renumber their columns: no relative 16-bit indices");
-  using ColT = typename std::conditional<IDX16, int16_t, int32_t>::type;
+  static_assert(!(HALO && IDX == 1), "row blocks with halo columns are never banded in every tile");
   extern __shared__ __align__(128) unsigned char smem_raw[];
   uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw);
   uint64_t* empty = full + L.stages;
@@ -227,11 +228,13 @@ k_row_pipe(TileArgs<T> a, const T* __restrict__ x, Epi epi, int ntiles, PipeLayo
     } else {
       int lt = cta;
       int e0n = 0, e1n = 0;
+      bool t16n = (IDX == 1);
       bool bnd = false, waited = false;
       if (lt < ntiles) {
         const int r0 = a.row_begin + phys(lt, bnd) * kThreads;
         e0n = __ldg(a.rowptr + r0);
         e1n = __ldg(a.rowptr + min(r0 + kThreads, a.row_end));
+        if constexpr (IDX == 2) t16n = __ldg(a.tile16 + r0 / kThreads) != 0;
       }
       pdl_wait();  // rowptr is constant; everything copied below may come from the previous kernel
       epi.init(st);
@@ -241,12 +244,14 @@ k_row_pipe(TileArgs<T> a, const T* __restrict__ x, Epi epi, int ntiles, PipeLayo
         const int r0 = a.row_begin + phys(lt, bnd) * kThreads;
         const int r1 = min(r0 + kThreads, a.row_end);
         const int e0 = e0n, e1 = e1n;
+        const bool t16 = t16n;
         const int nt = lt + ncta;
         if (nt < ntiles) {  // prefetch the next tile's extents while this stage drains
           bool b2;
           const int q0 = a.row_begin + phys(nt, b2) * kThreads;
           e0n = __ldg(a.rowptr + q0);
           e1n = __ldg(a.rowptr + min(q0 + kThreads, a.row_end));
+          if constexpr (IDX == 2) t16n = __ldg(a.tile16 + q0 / kThreads) != 0;
         }
         if constexpr (HALO) {
           if (bnd && !waited) {  // neighbours' halo rows must have landed before consumers gather them
@@ -269,7 +274,7 @@ k_row_pipe(TileArgs<T> a, const T* __restrict__ x, Epi epi, int ntiles, PipeLayo
         const uint32_t nb_r = (uint32_t)(((r1 - r0 + 1) * 4 + 15) & ~15);
         uint32_t total = nb_r;
         if (e1 > e0) {
-          if constexpr (IDX16) align16(a.coldelta + e0, (e1 - e0) * 2, src_c, nb_c);
+          if (IDX != 0 && t16) align16(a.coldelta + e0, (e1 - e0) * 2, src_c, nb_c);
           else align16(a.colidx + e0, (e1 - e0) * 4, src_c, nb_c);
           align16(a.vals + e0, (e1 - e0) * (int)sizeof(T), src_v, nb_v);
           total += nb_c + nb_v;
@@ -309,13 +314,19 @@ k_row_pipe(TileArgs<T> a, const T* __restrict__ x, Epi epi, int ntiles, PipeLayo
       const int r = r0 + tid;
       unsigned char* sb = stage0 + (size_t)s * L.stage_bytes;
       const int32_t* srow = reinterpret_cast<const int32_t*>(sb + L.off_row);
+      bool t16 = (IDX == 1);
+      if constexpr (IDX == 2) t16 = __ldg(a.tile16 + r0 / kThreads) != 0;  // block-uniform
       mbar_wait(full + s, phase);
       if (r < r1) {
         const int e0 = srow[0];
         const int rs = srow[tid], re = srow[tid + 1];
-        const ColT* scol = reinterpret_cast<const ColT*>(sb + L.off_col) - e0 +
-                           (IDX16 ? lead_elems(a.coldelta + e0, 2) : lead_elems(a.colidx + e0, 4));
-        const int cbase = IDX16 ? r : 0;  // relative indices are offsets from the row
+        // slot j's column: 2-byte offset from this row or 4-byte absolute index
+        const unsigned char* cbuf = sb + L.off_col;
+        const int cofs = ((IDX != 0 && t16) ? lead_elems(a.coldelta + e0, 2) : lead_elems(a.colidx + e0, 4)) - e0;
+        auto col_at = [&](int j) -> int {
+          if (IDX != 0 && t16) return r + (int)reinterpret_cast<const int16_t*>(cbuf)[j + cofs];
+          return reinterpret_cast<const int32_t*>(cbuf)[j + cofs];
+        };
         const T* sval = reinterpret_cast<const T*>(sb + L.off_val) + lead_elems(a.vals + e0, sizeof(T)) - e0;
         T acc[K];
 #pragma unroll
@@ -324,7 +335,7 @@ k_row_pipe(TileArgs<T> a, const T* __restrict__ x, Epi epi, int ntiles, PipeLayo
           // rows that read the halo tail: L2-coherent gathers (the tail was written by peers)
           for (int j = rs; j < re; ++j) {
             T xv[K];
-            load_vec_cg<T, K>(xv, x + (size_t)(cbase + (int)scol[j]) * K);
+            load_vec_cg<T, K>(xv, x + (size_t)col_at(j) * K);
             const T v = sval[j];
 #pragma unroll
             for (int c = 0; c < K; ++c) acc[c] = acc[c] + v * xv[c];
@@ -334,7 +345,7 @@ k_row_pipe(TileArgs<T> a, const T* __restrict__ x, Epi epi, int ntiles, PipeLayo
           T xv[U][K];
 #pragma unroll
           for (int u = 0; u < U; ++u) {
-            const int col = cbase + (int)scol[rs + u];
+            const int col = col_at(rs + u);
             vv[u] = sval[rs + u];
             load_vec<T, K>(xv[u], x + (size_t)col * K);
           }
@@ -350,7 +361,7 @@ k_row_pipe(TileArgs<T> a, const T* __restrict__ x, Epi epi, int ntiles, PipeLayo
 #pragma unroll
             for (int u = 0; u < U; ++u) {
               if (base + u < re) {
-                const int col = cbase + (int)scol[base + u];
+                const int col = col_at(base + u);
                 vv[u] = sval[base + u];
                 load_vec<T, K>(xv[u], x + (size_t)col * K);
               }

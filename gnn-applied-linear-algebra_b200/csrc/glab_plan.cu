@@ -74,20 +74,20 @@ __global__ void k_max_row(const int32_t* __restrict__ rowptr, int64_t n_rows, in
   if ((threadIdx.x & 31) == 0 && m > 0) atomicMax(out, m);
 }
 
-// delta[slot] = col - row as int16; flags |= 4 when some delta does not fit
+// delta[slot] = col - row as int16; a row with a delta that does not fit clears its tile's flag
 __global__ void k_col_delta(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ colidx,
-                            int64_t n_rows, int16_t* __restrict__ delta, int* flags) {
-  int f = 0;
+                            int64_t n_rows, int16_t* __restrict__ delta, uint8_t* __restrict__ tile16) {
   for (int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; r < n_rows;
        r += (int64_t)gridDim.x * blockDim.x) {
+    bool bad = false;
     const int e1 = rowptr[r + 1];
     for (int e = rowptr[r]; e < e1; ++e) {
       const int64_t d = (int64_t)colidx[e] - r;
-      if (d < -32767 || d > 32767) f = 4;
+      bad |= (d < -32767 || d > 32767);
       delta[e] = (int16_t)d;
     }
+    if (bad) tile16[r / kThreads] = 0;
   }
-  if (f) atomicOr(flags, f);
 }
 
 __global__ void k_validate_csr(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col,
@@ -200,6 +200,7 @@ static void plan_free(glab_plan* p) {
   if (p->colidx) cudaFree(p->colidx);
   if (p->perm) cudaFree(p->perm);
   if (p->coldelta) cudaFree(p->coldelta);
+  if (p->tile16) cudaFree(p->tile16);
   if (p->owned_vals) cudaFree(p->owned_vals);
   delete p;
 }
@@ -218,6 +219,8 @@ static int plan_alloc(int64_t n_rows, int64_t n_cols, int64_t nnz, glab_plan** o
   p->colidx = nullptr;
   p->perm = nullptr;
   p->coldelta = nullptr;
+  p->tile16 = nullptr;
+  p->tiles16 = p->tiles_total = 0;
   p->max_row_nnz = 0;
   p->owned_vals = nullptr;
   p->owned_vals_bytes = 0;
@@ -235,31 +238,47 @@ static int plan_alloc(int64_t n_rows, int64_t n_cols, int64_t nnz, glab_plan** o
   return 0;
 }
 
-// 2-byte relative column indices for banded operators (every |col - row| <= 32767): the pipeline
-// kernels then stream 2 B instead of 4 B of index per nonzero.  GLAB_IDX16=0 disables it.  Leaves
-// p->coldelta NULL when the operator is not banded enough (or on allocation failure: optional).
-static int plan_build_coldelta(glab_plan* p, int* d_flags, cudaStream_t st) {
+// 2-byte row-relative column indices: the pipeline kernels stream 2 B instead of 4 B of index per
+// nonzero in every 256-row tile whose deltas all fit int16.  GLAB_IDX16 = 0 disables it, 1 keeps it
+// only for plans where EVERY tile qualifies (banded operators), 2 (default) also keeps mixed plans
+// (periodic wrap-around rows, halo columns of a row block) when at least half of the tiles qualify.
+// Optional: on allocation failure the plan simply stays on int32.
+static int plan_build_coldelta(glab_plan* p, cudaStream_t st) {
   const char* env = getenv("GLAB_IDX16");
-  if (env && atoi(env) == 0) return 0;
-  if (p->nnz == 0 || p->n_rows == 0) return 0;
+  const int mode = env ? atoi(env) : 2;
+  if (mode <= 0 || p->nnz == 0 || p->n_rows == 0) return 0;
+  const int64_t ntiles = (p->n_rows + kThreads - 1) / kThreads;
   int16_t* d = nullptr;
-  if (cudaMalloc(&d, (size_t)(p->nnz + 16) * sizeof(int16_t)) != cudaSuccess) {
+  uint8_t* f = nullptr;
+  if (cudaMalloc(&d, (size_t)(p->nnz + 16) * sizeof(int16_t)) != cudaSuccess ||
+      cudaMalloc(&f, (size_t)ntiles + 16) != cudaSuccess) {
+    if (d) cudaFree(d);
     cudaGetLastError();
     return 0;
   }
-  cudaError_t e = cudaMemsetAsync(d_flags, 0, sizeof(int), st);
+  uint8_t* h = new (std::nothrow) uint8_t[(size_t)ntiles];
+  cudaError_t e = h ? cudaMemsetAsync(f, 1, (size_t)ntiles, st) : cudaErrorMemoryAllocation;
   if (e == cudaSuccess) {
-    k_col_delta<<<grid_for(p->n_rows, p->sm_count), 256, 0, st>>>(p->rowptr, p->colidx, p->n_rows, d, d_flags);
+    k_col_delta<<<grid_for(p->n_rows, p->sm_count), 256, 0, st>>>(p->rowptr, p->colidx, p->n_rows, d, f);
     e = cudaGetLastError();
   }
-  int h = 0;
-  if (e == cudaSuccess) e = cudaMemcpyAsync(&h, d_flags, sizeof(int), cudaMemcpyDeviceToHost, st);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(h, f, (size_t)ntiles, cudaMemcpyDeviceToHost, st);
   if (e == cudaSuccess) e = cudaStreamSynchronize(st);
-  if (e != cudaSuccess || (h & 4)) {
+  int64_t good = 0;
+  if (e == cudaSuccess)
+    for (int64_t t = 0; t < ntiles; ++t) good += h[t] ? 1 : 0;
+  delete[] h;
+  const bool keep = e == cudaSuccess && (good == ntiles || (mode >= 2 && 2 * good >= ntiles && good > 0));
+  if (!keep) {
     cudaFree(d);
-    return e == cudaSuccess ? 0 : (int)e;
+    cudaFree(f);
+    cudaGetLastError();
+    return (e == cudaSuccess || e == cudaErrorMemoryAllocation) ? 0 : (int)e;
   }
   p->coldelta = d;
+  p->tile16 = f;
+  p->tiles16 = good;
+  p->tiles_total = ntiles;
   return 0;
 }
 
@@ -346,7 +365,7 @@ extern "C" int glab_plan_create(int64_t n_rows, int64_t n_cols, int64_t nnz, con
   if ((e = cudaStreamSynchronize(st)) != cudaSuccess) return fail((int)e);
   if ((e = cudaGetLastError()) != cudaSuccess) return fail((int)e);
   p->max_row_nnz = h_flags[1];
-  if (int rcd = plan_build_coldelta(p, d_flags, st)) return fail(rcd);
+  if (int rcd = plan_build_coldelta(p, st)) return fail(rcd);
   cudaFree(d_flags);
   if (keys_in) cudaFree(keys_in);
   if (keys_out) cudaFree(keys_out);
@@ -387,7 +406,7 @@ extern "C" int glab_plan_create_csr(int64_t n_rows, int64_t n_cols, int64_t nnz,
   if ((e = cudaGetLastError()) != cudaSuccess) return fail((int)e);
   if (h_flags[0]) return fail(GLAB_E_RANGE);
   p->max_row_nnz = h_flags[1];
-  if (int rcd = plan_build_coldelta(p, d_flags, st)) return fail(rcd);
+  if (int rcd = plan_build_coldelta(p, st)) return fail(rcd);
   cudaFree(d_flags);
   *out = p;
   return 0;
@@ -411,7 +430,14 @@ extern "C" int glab_plan_info(const glab_plan* p, int64_t* n_rows, int64_t* n_co
 
 extern "C" int glab_plan_index_width(const glab_plan* p, int32_t* bytes) {
   if (!p || !bytes) return GLAB_E_ARG;
-  *bytes = p->coldelta ? 2 : 4;
+  *bytes = (p->coldelta && p->tiles16 == p->tiles_total) ? 2 : 4;
+  return 0;
+}
+
+extern "C" int glab_plan_index16_tiles(const glab_plan* p, int64_t* tiles16, int64_t* tiles_total) {
+  if (!p || !tiles16 || !tiles_total) return GLAB_E_ARG;
+  *tiles16 = p->coldelta ? p->tiles16 : 0;
+  *tiles_total = (p->n_rows + kThreads - 1) / kThreads;
   return 0;
 }
 

@@ -22,7 +22,8 @@ template <typename T> struct TileArgs {
   const T* __restrict__ vals;
   int row_begin, row_end;
   int cap;  // staging capacity in CSR slots (multiple of 32)
-  const int16_t* __restrict__ coldelta;  // col - row per slot (pipeline kernels with IDX16), else NULL
+  const int16_t* __restrict__ coldelta;  // col - row per slot (pipeline kernels with IDX != 0), else NULL
+  const uint8_t* __restrict__ tile16;    // per 256-row tile: 1 = stream coldelta (IDX == 2), else NULL
 };
 
 __host__ __device__ inline size_t round16(size_t x) { return (x + 15) & ~(size_t)15; }

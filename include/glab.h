@@ -76,11 +76,17 @@ int glab_plan_info(const glab_plan* plan, int64_t* n_rows, int64_t* n_cols, int6
                    int32_t* max_row_nnz, int32_t* identity_perm);
 int glab_plan_csr(const glab_plan* plan, const int32_t** rowptr, const int32_t** colidx,
                   const int32_t** perm);
-/* Bytes of column index the single-GPU pipeline kernels stream per nonzero: 2 when the plan also
- * holds 16-bit row-relative indices (built automatically when every |col - row| <= 32767, i.e.
- * for banded operators such as the 2-D stencils up to a 32767-wide grid line; the environment
- * variable GLAB_IDX16=0 at plan creation disables it), else 4.  Results do not depend on it. */
+/* 16-bit row-relative column indices.  Besides int32 colidx a plan holds coldelta[slot] =
+ * col - row as int16 for every 256-row tile whose rows all satisfy |col - row| <= 32767, and the
+ * pipeline kernels stream those 2 bytes instead of the 4-byte index in such tiles: all tiles of a
+ * banded operator (the 2-D stencils up to a 32767-wide grid line), all but the wrap-around tiles
+ * of a periodic one, all but the tiles that read the halo tail of a row block.  Built at plan
+ * creation; environment variable GLAB_IDX16 = 0 disables it, 1 keeps it only when every tile
+ * qualifies, 2 (default) also when at least half of the tiles do.  Results never depend on it.
+ * index_width: 2 when every tile streams 16-bit indices, else 4.  index16_tiles: how many of the
+ * plan's 256-row tiles do. */
 int glab_plan_index_width(const glab_plan* plan, int32_t* bytes);
+int glab_plan_index16_tiles(const glab_plan* plan, int64_t* tiles16, int64_t* tiles_total);
 /* L2 residency for operators that fit the 126 MB L2 (e.g. one rank's block of a row-partitioned
  * operator): adopt copies the CSR-ordered values into plan-owned storage directly behind colidx
  * (*vals_out points at the copy; use it instead of the caller's array), l2_persist then marks

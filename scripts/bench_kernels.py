@@ -34,10 +34,19 @@ def timeit(fn, reps=20, warm=3):
     return a.elapsed_time(b) / reps
 
 
-def report(name, op, ms, nbytes, z, extra=None):
+INDEX_BYTES = 4   # bytes of column index the pipeline kernels stream per nonzero for the current plan
+
+
+def report(name, op, ms, nbytes, z, extra=None, streams_index=True):
+    """alg_MB / GBps / frac_of_measured_peak use SURVEY 8d's algorithmic bytes (4-byte column indices);
+    moved_frac subtracts the index bytes the kernel does not stream when the plan holds 16-bit
+    row-relative indices."""
     d = {"kernel": name, "operator": op, "ms": round(ms, 4), "alg_MB": round(nbytes / 1e6, 1),
          "GBps": round(nbytes / ms / 1e6, 1), "frac_of_measured_peak": round(nbytes / ms / 1e6 / PEAK, 3),
          "Gnnz_per_s": round(z / ms / 1e6, 1)}
+    if streams_index:
+        moved = nbytes - (4 - INDEX_BYTES) * z
+        d.update(index_bytes=INDEX_BYTES, moved_frac=round(moved / ms / 1e6 / PEAK, 3))
     if extra:
         d.update(extra)
     print(json.dumps(d), flush=True)
@@ -53,7 +62,9 @@ def layer_kernels(op_name, ei, ev, dt, ks=(1,)):
     vals = rt.get_vals(plan, ev)
     z, s = plan.nnz, ev.element_size()
     base = z * (4 + s) + 4 * (n + 1)
-    report("plan_create (COO int64 -> CSR int32)", op_name, t_plan, z * 16 + z * 4 + 4 * n, z)
+    global INDEX_BYTES
+    INDEX_BYTES = plan.index_bytes
+    report("plan_create (COO int64 -> CSR int32)", op_name, t_plan, z * 16 + z * 4 + 4 * n, z, streams_index=False)
     ws = torch.zeros(4, dtype=torch.float64, device=dev)
     for k in ks:
         x = torch.rand(n, k, dtype=dt, device=dev)
@@ -79,7 +90,8 @@ def layer_kernels(op_name, ei, ev, dt, ks=(1,)):
                    base + 3 * n * s, z)
             out = torch.empty(z, 2, dtype=dt, device=dev)
             report("edge_messages (optional output)" + tag, op_name,
-                   timeit(lambda: rt.edge_messages(plan, vals, x, out, 1), reps=5), z * (4 + 2 * s) + n * s, z)
+                   timeit(lambda: rt.edge_messages(plan, vals, x, out, 1), reps=5), z * (4 + 2 * s) + n * s, z,
+                   streams_index=False)
             del out
         del x, b, y, y2, r
     return plan
@@ -95,6 +107,8 @@ def amg_kernels(op_name, ei, ev, dt):
     vals = rt.get_vals(plan, ao)
     z, s = plan.nnz, ev.element_size()
     tag = " " + str(dt)[6:]
+    global INDEX_BYTES
+    INDEX_BYTES = 4                     # the per-edge-output kernels stream int32 column indices
     report("soc_classic" + tag, op_name, timeit(lambda: rt.soc_classic(plan, vals, 0.25)), 2 * z * s + 4 * (n + 1), z)
     report("soc_sa" + tag, op_name, timeit(lambda: rt.soc_sa(plan, vals, diag)), z * (4 + 2 * s) + 4 * (n + 1) + n * s, z)
     S = (rt.soc_classic(plan, vals, 0.25) > 0).to(dt)

@@ -28,7 +28,9 @@ def main():
     from glab_b200 import dist as gd
     rt = G.runtime
     ok = True
-    for dt, N, gen in ((torch.float32, 96, "lap"), (torch.float64, 64, "heat")):
+    # N = 512: row blocks of > 32767 rows, so the plans are MIXED (tiles that read the halo tail
+    # stream int32 column indices, interior tiles 16-bit row-relative ones)
+    for dt, N, gen in ((torch.float32, 96, "lap"), (torch.float64, 64, "heat"), (torch.float32, 512, "lap")):
         n = N * N
         if gen == "lap":
             ei, ev = G.generators.laplacian_2d(N, torch.float64, dev)
@@ -59,6 +61,7 @@ def main():
             r0, r1 = part.bounds(rank)
             lei, lev, halo = gd.partition_coo(ei, ev, part, rank)
             op = gd.DistOperator(lei, lev.contiguous(), halo, k=1, engine=engine)
+            t16 = (op.plan.index16_tiles, op.plan.tiles)
             op.load("v0", x0[r0:r1])
             cur = op.jacobi(5, diag[r0:r1].contiguous(), b[r0:r1].contiguous(), w, "v0")
             jac = op.vec[cur][:halo.n_local]
@@ -71,9 +74,9 @@ def main():
             tol = 1e-5 if dt == torch.float32 else 1e-12
             e3 = abs(lam[0].item() - g_ref[2].item()) <= tol * abs(g_ref[2].item())
             torch.cuda.synchronize()
-            print("rank %d %s N=%d engine=%s halo=%d interior=[%d,%d): jacobi %s cheby %s power %s (%.9g vs %.9g)" %
-                  (rank, str(dt)[6:], N, engine, halo.n_halo, op.lo, op.hi, e1, e2, e3, lam[0].item(), g_ref[2].item()),
-                  flush=True)
+            print("rank %d %s N=%d engine=%s halo=%d interior=[%d,%d) idx16 tiles %d/%d: jacobi %s cheby %s power %s "
+                  "(%.9g vs %.9g)" % (rank, str(dt)[6:], N, engine, halo.n_halo, op.lo, op.hi, t16[0], t16[1], e1, e2, e3,
+                                      lam[0].item(), g_ref[2].item()), flush=True)
             ok = ok and e1 and e2 and e3
             op.close()
             dist.barrier()

@@ -428,14 +428,16 @@ def test_vcycle_multi_rhs_and_large_grid(G, dev):
     assert all(b_ < a_ for a_, b_ in zip(norms, norms[1:])), norms
 
 
-@pytest.mark.parametrize("N,align", [(80, 256), (20, 16)])
+@pytest.mark.parametrize("N,align", [(80, 256), (20, 16), (420, 256)])
 @pytest.mark.parametrize("dt", [torch.float32, torch.float64])
 def test_fused_halo_step_two_ranks_emulated_on_one_gpu(G, dev, dt, N, align):
     """The multi-GPU data path (glab_halo_push, the fused glab_jacobi_halo / glab_cheby_*_halo
     kernels with in-kernel acquire + communication CTA) exercised on ONE GPU: two row blocks of
     the operator live in the same process and their kernels run one after the other on one
     stream, each storing its boundary rows into the other block's halo tail exactly as it would
-    through an NVLink peer mapping.  Results must equal the unpartitioned sweeps bit for bit."""
+    through an NVLink peer mapping.  Results must equal the unpartitioned sweeps bit for bit.
+    N = 420: blocks of 88 K rows, so rank 1's plan is MIXED -- the tile that reads the halo tail
+    (column offsets beyond int16) streams int32 indices, every other tile 16-bit ones."""
     from glab_b200 import dist as gd
     from glab_b200._lib import HaloStep, PushDesc
     rt = G.runtime
@@ -473,6 +475,9 @@ def test_fused_halo_step_two_ranks_emulated_on_one_gpu(G, dev, dt, N, align):
         vec = [torch.zeros(h.n_local + h.n_halo, 1, dtype=dt, device=dev) for _ in range(2)]
         flags = torch.zeros(64, dtype=torch.int32, device=dev)     # 16-byte spaced words
         ops.append(dict(plan=p, vals=rt.get_vals(p, v), halo=h, vec=vec, flags=flags, lo=lo, hi=hi, keep=lei))
+    if N == 420:
+        assert ops[0]["plan"].index16_tiles == ops[0]["plan"].tiles
+        assert 0 < ops[1]["plan"].index16_tiles < ops[1]["plan"].tiles
     for r in range(world):
         r0, r1 = part.bounds(r)
         ops[r]["vec"][0][:r1 - r0].copy_(x0[r0:r1])
@@ -784,6 +789,37 @@ def test_index16_and_index32_plans_agree(G, dev, dt, monkeypatch):
             for a_, b_ in zip(*outs):
                 assert torch.equal(a_, b_)
             assert torch.equal(outs[0][0], outs[0][6])
+    # MIXED plans: the periodic operator's wrap-around rows (first / last grid line) do not fit int16
+    Np = 256
+    n = Np * Np
+    ei, ev = G.generators.constant_diffusion_fem(1.0, 0.01, Np, dtype=dt, device=dev)
+    ev = ev.contiguous()
+    monkeypatch.setenv("GLAB_IDX16", "2")
+    pm = rt.Plan.from_coo(ei, n)
+    monkeypatch.setenv("GLAB_IDX16", "1")
+    p1 = rt.Plan.from_coo(ei, n)
+    monkeypatch.setenv("GLAB_IDX16", "0")
+    p0 = rt.Plan.from_coo(ei, n)
+    monkeypatch.delenv("GLAB_IDX16")
+    assert pm.tiles == 256 and pm.index16_tiles == 254 and pm.index_bytes == 4
+    assert p1.index16_tiles == 0 and p0.index16_tiles == 0
+    vals = ev.view(-1)
+    diag = G.generators.diagonal_of(ei, ev, n).reshape(-1).contiguous()
+    for k in (1, 4):
+        x, b = torch.rand(n, k, dtype=dt, device=dev), torch.rand(n, k, dtype=dt, device=dev)
+        res = []
+        for plan in (pm, p0):
+            xj = rt.jacobi(plan, vals, diag, b, x, torch.empty_like(x), w)
+            y = torch.full_like(x, float("nan"))
+            rt.spmm(plan, vals, x, y, rows=(0, 1024))
+            rt.spmm(plan, vals, x, y, rows=(1024, n))
+            y3 = torch.full_like(x, float("nan"))
+            rt.spmm(plan, vals, x, y3, rows=(0, 1000))          # unaligned split: falls back to int32 / generic kernel
+            rt.spmm(plan, vals, x, y3, rows=(1000, n))
+            res.append((xj, y, y3))
+        for a_, b_ in zip(*res):
+            assert torch.equal(a_, b_)
+        assert torch.equal(res[0][1], res[0][2])
     # power-method scalars through the reducing epilogues
     ei, ev = G.UtilsGNN.laplacianfun_torch(33, device=dev)
     ev = ev.to(dt)
