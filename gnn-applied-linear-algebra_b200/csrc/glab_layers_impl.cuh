@@ -441,7 +441,8 @@ static int launch_pipe_halo(const glab_plan* p, const T* vals, const T* x, const
                             const glab_halo_step* hs) {
   // interior tiles of a row block have local, in-band columns: they stream 16-bit indices (IDX 2)
   if constexpr (idx16_ok<T, K, U>()) {
-    if (index_mode(p, 0) != 0) return launch_pipe_halo_impl<T, K, U, Epi, 2>(p, vals, x, epi, stream, hs);
+    if (p->idx16_halo && index_mode(p, 0) != 0)
+      return launch_pipe_halo_impl<T, K, U, Epi, 2>(p, vals, x, epi, stream, hs);
   }
   return launch_pipe_halo_impl<T, K, U, Epi, 0>(p, vals, x, epi, stream, hs);
 }

@@ -21,6 +21,10 @@ namespace glab {
 
 constexpr int kPipeThreads = kThreads + 32;  // 8 consumer warps + 1 producer warp
 constexpr int kMaxStreams = 3;               // row-aligned epilogue input vectors staged by TMA
+// Byte offset, inside a stage's rowptr region, of the word in which the producer tells the consumers
+// whether the tile streams 16-bit indices (IDX == 2).  The rowptr slice occupies at most
+// (kThreads + 1) * 4 bytes rounded up to 16 = 1040 of the region's 1152 bytes.
+constexpr int kTileFlagOff = ((kThreads + 1) * 4 + 15) & ~15;
 
 struct PipeLayout {
   int stages;
@@ -287,6 +291,8 @@ k_row_pipe(TileArgs<T> a, const T* __restrict__ x, Epi epi, int ntiles, PipeLayo
             total += nb_s[i];
           }
         }
+        // ordinary shared store; the arrive below releases it to the consumers' acquire on `full`
+        if constexpr (IDX == 2) *reinterpret_cast<volatile int*>(sb + L.off_row + kTileFlagOff) = t16 ? 1 : 0;
         mbar_expect_tx(full + s, total);
         bulk_g2s(sb + L.off_row, a.rowptr + r0, nb_r, full + s);
         if (nb_c) {
@@ -315,8 +321,9 @@ k_row_pipe(TileArgs<T> a, const T* __restrict__ x, Epi epi, int ntiles, PipeLayo
       unsigned char* sb = stage0 + (size_t)s * L.stage_bytes;
       const int32_t* srow = reinterpret_cast<const int32_t*>(sb + L.off_row);
       bool t16 = (IDX == 1);
-      if constexpr (IDX == 2) t16 = __ldg(a.tile16 + r0 / kThreads) != 0;  // block-uniform
       mbar_wait(full + s, phase);
+      if constexpr (IDX == 2)  // block-uniform; written by the producer, no global latency here
+        t16 = *reinterpret_cast<const volatile int*>(sb + L.off_row + kTileFlagOff) != 0;
       if (r < r1) {
         const int e0 = srow[0];
         const int rs = srow[tid], re = srow[tid + 1];

@@ -221,6 +221,7 @@ static int plan_alloc(int64_t n_rows, int64_t n_cols, int64_t nnz, glab_plan** o
   p->coldelta = nullptr;
   p->tile16 = nullptr;
   p->tiles16 = p->tiles_total = 0;
+  p->idx16_halo = 0;
   p->max_row_nnz = 0;
   p->owned_vals = nullptr;
   p->owned_vals_bytes = 0;
@@ -241,7 +242,9 @@ static int plan_alloc(int64_t n_rows, int64_t n_cols, int64_t nnz, glab_plan** o
 // 2-byte row-relative column indices: the pipeline kernels stream 2 B instead of 4 B of index per
 // nonzero in every 256-row tile whose deltas all fit int16.  GLAB_IDX16 = 0 disables it, 1 keeps it
 // only for plans where EVERY tile qualifies (banded operators), 2 (default) also keeps mixed plans
-// (periodic wrap-around rows, halo columns of a row block) when at least half of the tiles qualify.
+// (periodic wrap-around rows, halo columns of a row block) when at least half of the tiles qualify,
+// 3 additionally lets the fused multi-GPU halo kernels use it (interior tiles of a row block; measured
+// neutral at 2 GPUs -- 0.0797 vs 0.0803 ms per sweep -- so it is not the default).
 // Optional: on allocation failure the plan simply stays on int32.
 static int plan_build_coldelta(glab_plan* p, cudaStream_t st) {
   const char* env = getenv("GLAB_IDX16");
@@ -279,6 +282,7 @@ static int plan_build_coldelta(glab_plan* p, cudaStream_t st) {
   p->tile16 = f;
   p->tiles16 = good;
   p->tiles_total = ntiles;
+  p->idx16_halo = mode >= 3 ? 1 : 0;
   return 0;
 }
 

@@ -82,7 +82,8 @@ int glab_plan_csr(const glab_plan* plan, const int32_t** rowptr, const int32_t**
  * banded operator (the 2-D stencils up to a 32767-wide grid line), all but the wrap-around tiles
  * of a periodic one, all but the tiles that read the halo tail of a row block.  Built at plan
  * creation; environment variable GLAB_IDX16 = 0 disables it, 1 keeps it only when every tile
- * qualifies, 2 (default) also when at least half of the tiles do.  Results never depend on it.
+ * qualifies, 2 (default) also when at least half of the tiles do, 3 additionally lets the fused
+ * multi-GPU halo kernels use it (measured neutral, hence not the default).  Results never depend on it.
  * index_width: 2 when every tile streams 16-bit indices, else 4.  index16_tiles: how many of the
  * plan's 256-row tiles do. */
 int glab_plan_index_width(const glab_plan* plan, int32_t* bytes);
