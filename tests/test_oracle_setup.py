@@ -76,3 +76,29 @@ def test_prolongator_and_galerkin_helpers_match_the_pinned_cycle():
     fine = split == 0
     assert torch.equal(P1[fine], Pd[fine])
     assert torch.equal(P1[~fine], torch.eye(n)[~fine][:, ~fine])
+
+
+def _golden_setup():
+    import os
+    from conftest import ROOT
+    return torch.load(os.path.join(ROOT, "tests", "golden", "reference_setup.pt"), weights_only=False)
+
+
+def test_oracle_setup_helpers_match_the_reference_golden():
+    """oracle port (SOC flags, prolongator, Galerkin operator) == the intermediates the UNMODIFIED
+    reference produced (tests/golden/make_golden_setup.py), bit for bit."""
+    for c in _golden_setup()["cases"]:
+        N = c["N"]
+        n, ei, ev, eo, ao, S = _laplace_strength(N)
+        assert torch.equal(S.reshape(-1, 1) > 0, c["S"])
+        split = torch.zeros(n)
+        split[0::2] = 1
+        dv = -4.0 * torch.ones(n, 1)
+        wij = port.direct_interp(torch.hstack([dv, split.view(-1, 1)]), eo, torch.hstack([ao, c["S"]]))
+        P = port.prolongator(eo, wij, split, n)
+        assert tuple(P.shape) == c["P_shape"]
+        assert torch.equal(P.indices(), c["P_indices"]) and torch.equal(P.values(), c["P_values"])
+        A = torch.sparse_coo_tensor(ei, ev.flatten(), (n, n))
+        Ac = port.galerkin(A, P)
+        assert tuple(Ac.shape) == c["Ac_shape"]
+        assert torch.equal(Ac.indices(), c["Ac_indices"]) and torch.equal(Ac.values(), c["Ac_values"])

@@ -250,3 +250,25 @@ def test_setup_at_scale_properties(G, dev):
     fwd = ci[0] * nc + ci[1]
     bwd = torch.sort(ci[1] * nc + ci[0]).values
     assert torch.equal(fwd, bwd)
+
+
+def test_setup_against_reference_golden(G, dev):
+    """runSOC / runDirectInterp / the Galerkin operator of the cached hierarchy against the
+    intermediates of the UNMODIFIED reference two-grid cycle (tests/golden/reference_setup.pt):
+    strength flags and the prolongator bit for bit, P^T A P with the identical pattern and values
+    within the fp32 tolerance (the reference's torch.sparse product sums in a different order)."""
+    import os
+    from conftest import ROOT
+    V = G.VCycle
+    for c in torch.load(os.path.join(ROOT, "tests", "golden", "reference_setup.pt"), weights_only=False)["cases"]:
+        N = c["N"]
+        ei, ev = G.UtilsGNN.laplacianfun_torch(N)
+        A = torch.sparse_coo_tensor(ei, ev.flatten(), dtype=torch.float)
+        S = V.runSOC(A)
+        assert torch.equal(S, c["S"])
+        P = V.runDirectInterp(A, S, N)
+        assert tuple(P.shape) == c["P_shape"]
+        assert torch.equal(P.indices(), c["P_indices"]) and same(P.values(), c["P_values"])
+        Ac = V._two_grid(A, None).Ac.cpu()
+        assert tuple(Ac.shape) == c["Ac_shape"] and torch.equal(Ac.indices(), c["Ac_indices"])
+        assert relerr(Ac.values(), c["Ac_values"]) <= 1e-5
