@@ -75,3 +75,32 @@ def test_plan_cache_validity_rules(G):
     for i in range(4):               # LRU capacity
         C.put(torch.zeros(3 + i), i)
     assert len(C.d) <= 2
+
+
+def test_ctypes_signatures_match_header_arity(G):
+    """Every prototype of include/glab.h is bound in _lib.py with the same number of arguments and a
+    compatible return type (int / int64_t / const char*): catches ABI drift between the header, the
+    library and the host package without running anything on a GPU."""
+    import ctypes as C
+    src = open(os.path.join(ROOT, "include", "glab.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    protos = re.findall(r"\b(int64_t|int|const char\*)\s+(glab_[a-z0-9_]+)\s*\(([^;{]*?)\)\s*;", src, flags=re.S)
+    assert len(protos) >= 90
+    ret = {"int": C.c_int, "int64_t": C.c_int64, "const char*": C.c_char_p}
+    for rtype, name, params in protos:
+        params = params.strip()
+        arity = 0 if params in ("", "void") else params.count(",") + 1
+        fn = getattr(G.lib, name)
+        assert fn.argtypes is not None, name
+        assert len(fn.argtypes) == arity, (name, len(fn.argtypes), arity)
+        assert fn.restype is ret[rtype], (name, fn.restype, rtype)
+
+
+def test_header_is_plain_c(tmp_path):
+    """include/glab.h must compile as C99 on its own (the boundary is a C ABI, not C++)."""
+    import subprocess
+    src = tmp_path / "use_glab.c"
+    src.write_text('#include "glab.h"\nint main(void) { return glab_version() == GLAB_VERSION ? 0 : 1; }\n')
+    out = subprocess.run(["gcc", "-std=c99", "-Wall", "-Werror", "-pedantic", "-fsyntax-only", "-I",
+                          os.path.join(ROOT, "include"), str(src)], capture_output=True, text=True)
+    assert out.returncode == 0, out.stderr
