@@ -1,4 +1,5 @@
 """Workload drivers used by bench.py (kept apart so bench.py stays a readable contract)."""
+import os
 import time
 
 import torch
@@ -149,8 +150,13 @@ class PartitionedSmoother:
                            "rows_local": nl, "halo_rows": self.halo.n_halo, "interior": [self.op.lo, self.op.hi],
                            "cuda_graph": bool(use_graph),
                            "index16_tiles": [self.op.plan.index16_tiles, self.op.plan.tiles]}
-        # effective bytes of column index streamed per nonzero (tiles with 16-bit indices stream 2)
-        self.index_bytes = 4 - 2.0 * self.op.plan.index16_tiles / max(self.op.plan.tiles, 1)
+        # effective bytes of column index streamed per nonzero: the fused halo kernels (engine "peer") stay on
+        # int32 unless GLAB_IDX16=3; the other engines launch the plain kernels, which stream 2 bytes in the
+        # tiles flagged for 16-bit indices
+        halo16 = os.environ.get("GLAB_IDX16", "2") == "3"
+        frac16 = self.op.plan.index16_tiles / max(self.op.plan.tiles, 1)
+        self.index_bytes = 4 - 2.0 * frac16 if (halo16 or engine != "peer") else 4.0
+        self.setup_info["halo_kernels_use_index16"] = bool(halo16 and engine == "peer")
         g = torch.Generator().manual_seed(24601 + rank)
         self.b_host = torch.rand(nl, 1, generator=g).pin_memory()
         self.x_host = torch.rand(nl, 1, generator=g).pin_memory()
