@@ -8,7 +8,8 @@ from ._io import Placement, float_dtype
 class JacobiGNN(torch.nn.Module):
     """JacobiGNN.py:125-148.  vertex_attr=[A_ii, b, x], edge_attr=[A_ij, c_ij] (edges INCLUDE
     the diagonal), g=[w].  Each sweep is one launch of glab_jacobi (gather + multiply +
-    row sum + update fused); sweeps ping-pong between two x buffers.
+    row sum + update fused); sweeps ping-pong between two x buffers, and forward() runs all n_iters
+    sweeps in one launch of the multi-sweep kernel (glab_jacobi_sweeps_*).
     Extension: vertex_attr = [A_ii | b (k cols) | x (k cols)] smooths k right-hand sides."""
 
     def _setup(self, vertex_attr, edgeij_pair, edge_attr, g):
@@ -33,8 +34,6 @@ class JacobiGNN(torch.nn.Module):
 
     def forward(self, n_iters, vertex_attr, edgeij_pair, edge_attr, g, batch=None):
         io, dt, plan, vals, va, diag, b, x, w = self._setup(vertex_attr, edgeij_pair, edge_attr, g)
-        other = torch.empty_like(x)
-        for _ in range(n_iters):
-            rt.jacobi(plan, vals, diag, b, x, other, w)
-            x, other = other, x
+        # all sweeps in one launch of the multi-sweep kernel (x is a private copy from unpack)
+        x = rt.jacobi_sweeps(plan, vals, diag, b, x, torch.empty_like(x), w, n_iters)
         return io.down(x.reshape(x.shape[0], -1))

@@ -194,12 +194,9 @@ def _two_grid(A, splitting, coarse_rows="reference"):
 
 
 def _jacobi_inplace(plan, vals, diag, b, x, scratch, w_dev, n_iters):
-    """n_iters fused sweeps; returns the buffer that holds the result (x or scratch)."""
-    cur, other = x, scratch
-    for _ in range(n_iters):
-        rt.jacobi(plan, vals, diag, b, cur, other, w_dev)
-        cur, other = other, cur
-    return cur
+    """n_iters fused sweeps in one multi-sweep launch; returns the buffer that holds the result
+    (x or scratch)."""
+    return rt.jacobi_sweeps(plan, vals, diag, b, x, scratch, w_dev, n_iters)
 
 
 def runVCycle(A, b, x, n_presmooth, n_postsmooth, n_coarsesolve, use_jacobi=True, splitting=None):

@@ -68,7 +68,7 @@ class HaloStep(ctypes.Structure):
     _fields_ = [("interior_begin", c_int64), ("interior_end", c_int64), ("n_wait", c_int32),
                 ("wait_flags", POINTER(c_void_p)), ("wait_target", c_void_p), ("n_push", c_int32),
                 ("push", POINTER(PushDesc)), ("pushed_counter", c_void_p), ("push_src", c_void_p),
-                ("done_counter", c_void_p)]
+                ("done_counter", c_void_p), ("status", c_void_p), ("timeout_ms", c_int64)]
 
 
 _sig("glab_halo_wait", c_int, c_int, POINTER(c_void_p), P, P)
@@ -95,6 +95,8 @@ for _suf, _ct in (("f32", c_float), ("f64", c_double)):
     _sig("glab_spmm_halo_" + _suf, c_int, P, P, P, _INT, P, _H, P)
     _sig("glab_residual_halo_" + _suf, c_int, P, P, P, P, _INT, P, _H, P)
     _sig("glab_jacobi_halo_" + _suf, c_int, P, P, P, P, P, P, P, _INT, _H, P)
+    _sig("glab_jacobi_sweeps_" + _suf, c_int, P, P, P, P, P, P, P, _INT, _INT, P)
+    _sig("glab_jacobi_sweeps_halo_" + _suf, c_int, P, P, P, P, P, P, P, _INT, _INT, _H, _H, P)
     _sig("glab_cheby_first_halo_" + _suf, c_int, P, P, P, P, P, P, P, P, _INT, _H, P)
     _sig("glab_cheby_next_halo_" + _suf, c_int, P, P, P, P, P, P, P, P, P, _INT, _H, P)
     _sig("glab_power_step_halo_" + _suf, c_int, P, P, P, P, P, P, P, _H, P)

@@ -353,6 +353,23 @@ def jacobi(plan, vals, diag, b, x_in, x_out, omega_dev, rows=None, halo=None):
     return x_out
 
 
+def jacobi_sweeps(plan, vals, diag, b, xa, xb, omega_dev, n_sweeps, halo=None):
+    """n_sweeps weighted-Jacobi sweeps ping-ponging xa -> xb -> xa ... in ONE launch of the multi-sweep
+    kernel (glab_jacobi_sweeps_*; the library falls back to one fused launch per sweep for operators
+    that kernel cannot take).  Returns the buffer that holds the result.  halo = (step gathering xa and
+    producing xb, step gathering xb and producing xa) on a row-partitioned operator."""
+    k = _k_of(xa)
+    if n_sweeps <= 0:
+        return xa
+    if halo is not None:
+        _call("jacobi_sweeps_halo", xa.dtype, plan.device, plan.handle, ptr(vals), ptr(diag), ptr(b), ptr(xa), ptr(xb),
+              ptr(omega_dev), k, int(n_sweeps), halo[0], halo[1], stream_ptr())
+    else:
+        _call("jacobi_sweeps", xa.dtype, plan.device, plan.handle, ptr(vals), ptr(diag), ptr(b), ptr(xa), ptr(xb),
+              ptr(omega_dev), k, int(n_sweeps), stream_ptr())
+    return xb if n_sweeps % 2 else xa
+
+
 def cheby_first(plan, vals, b, x_in, x_out, r, p, alpha_dev, rows=None, halo=None):
     k = _k_of(x_in)
     if halo is not None:

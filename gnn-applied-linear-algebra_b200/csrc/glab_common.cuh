@@ -29,10 +29,13 @@ struct glab_plan {
   int16_t* coldelta;       // colidx[slot] - row as int16 (valid in the row tiles flagged in tile16), or NULL
   uint8_t* tile16;         // [ceil(n_rows/256)]: 1 = every |col - row| of the tile's rows fits int16
   int64_t tiles16, tiles_total;
-  int idx16_halo;          // 1 = the fused halo kernels may use coldelta too (GLAB_IDX16=3; measured neutral, off)
+  int idx16_halo;          // 1 = the fused halo kernels stream coldelta too (GLAB_IDX16_HALO, default 1)
   int32_t max_row_nnz;
+  int32_t band_local;      // max |col - row| over the columns < n_rows (the local block of a row partition)
+  uint32_t* ms_state;      // multi-sweep kernels: [tiles_total] tile completion counters, then epoch / ticket words
   void* owned_vals;        // optional plan-owned copy of the values (glab_plan_adopt_vals_*), else NULL
   size_t owned_vals_bytes;
+  void* retired[4];        // allocations replaced by glab_plan_adopt_vals_*, kept until the plan dies
 };
 
 namespace glab {

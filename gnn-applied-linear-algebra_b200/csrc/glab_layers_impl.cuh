@@ -4,6 +4,7 @@
 // (gathers + edge update + scatter + vertex update); citations are in include/glab.h.
 #include <cstdlib>
 #include "glab_pipe.cuh"
+#include "glab_multisweep.cuh"
 
 namespace glab {
 
@@ -313,11 +314,23 @@ struct Tuning {
   int stages;     // 0 = auto, else forced ring depth
   int ctas;       // 0 = auto (occupancy API), else forced CTAs per SM for the pipeline
   int pdl;        // 1 = programmatic dependent launch between consecutive pipeline kernels
+  int ms;         // 1 = several Jacobi sweeps per launch (glab_jacobi_sweeps_*) use the multi-sweep kernel
 };
+
+// Bound of the in-kernel waits: caller's value, else GLAB_SPIN_TIMEOUT_MS, else 20 s; < 0 = forever.
+static unsigned long long spin_timeout_ns(int64_t timeout_ms) {
+  static const int64_t dflt = [] {
+    const char* e = getenv("GLAB_SPIN_TIMEOUT_MS");
+    return e ? (int64_t)atoll(e) : (int64_t)20000;
+  }();
+  const int64_t ms = timeout_ms == 0 ? dflt : timeout_ms;
+  return ms < 0 ? 0ull : (unsigned long long)ms * 1000000ull;
+}
 
 static const Tuning& tuning() {
   static Tuning t = [] {
-    Tuning v{1, 4096, 8, 1, 0, 0, 1};
+    Tuning v{1, 4096, 8, 1, 0, 0, 1, 1};
+    if (const char* e = getenv("GLAB_MS")) v.ms = atoi(e) != 0;
     if (const char* e = getenv("GLAB_RPT")) v.rpt = atoi(e) == 2 ? 2 : 1;
     if (const char* e = getenv("GLAB_CAP")) { int c = atoi(e); if (c >= 256 && c <= 8192) v.cap_max = c & ~31; }
     if (const char* e = getenv("GLAB_PIPE")) v.pipe = atoi(e) != 0;
@@ -439,10 +452,16 @@ static bool make_pipe_layout(const glab_plan* p, const Epi& epi, PipeLayout& L, 
 template <typename T, int K, int U, class Epi>
 static int launch_pipe_halo(const glab_plan* p, const T* vals, const T* x, const Epi& epi, void* stream,
                             const glab_halo_step* hs) {
-  // interior tiles of a row block have local, in-band columns: they stream 16-bit indices (IDX 2)
+  // interior tiles of a row block have local, in-band columns: they stream 16-bit indices (IDX 2, or
+  // IDX 1 when even the tiles that read the halo tail are within +-32767 of their rows)
   if constexpr (idx16_ok<T, K, U>()) {
-    if (p->idx16_halo && index_mode(p, 0) != 0)
-      return launch_pipe_halo_impl<T, K, U, Epi, 2>(p, vals, x, epi, stream, hs);
+    if (p->idx16_halo) {
+      switch (index_mode(p, 0)) {
+        case 1: return launch_pipe_halo_impl<T, K, U, Epi, 1>(p, vals, x, epi, stream, hs);
+        case 2: return launch_pipe_halo_impl<T, K, U, Epi, 2>(p, vals, x, epi, stream, hs);
+        default: break;
+      }
+    }
   }
   return launch_pipe_halo_impl<T, K, U, Epi, 0>(p, vals, x, epi, stream, hs);
 }
@@ -506,10 +525,13 @@ static int launch_pipe_halo_impl(const glab_plan* p, const T* vals, const T* x, 
   h.pushed_counter = hs->pushed_counter;
   h.push_src = hs->push_src;
   h.done_counter = hs->done_counter;
+  h.status = hs->status;
+  h.timeout_ns = spin_timeout_ns(hs->timeout_ms);
   int grid = p->sm_count * occ;   // all co-resident: the communication CTA (block 0) must run
   if (grid > kMaxReduceBlocks) grid = kMaxReduceBlocks;
   if (grid > ntiles + 1) grid = ntiles + 1;
   if (grid < 1) grid = 1;
+  if (grid < 2 && hs->n_push > 0) grid = 2;   // a block without rows still has to publish its arrival
   TileArgs<T> a{p->rowptr, p->colidx, vals, 0, (int)n, (int)slots, IDX ? p->coldelta : nullptr,
                 IDX == 2 ? p->tile16 : nullptr};
   return launch_pdl(kern, grid, kPipeThreads, smem, as_stream(stream), tuning().pdl != 0, a, x, epi, ntiles, L, h);
@@ -689,6 +711,177 @@ static int cheby_next(const glab_plan* p, const T* vals, const T* p_in, T* p_out
     e.alpha_old = alpha_old; e.alpha = alpha; e.beta = beta; return e; }, h);
 }
 
+
+// ---------------------------------------------------------------- multi-sweep Jacobi launch
+// Returns kNoPipe when the multi-sweep kernel cannot run this operator (caller loops over single sweeps).
+template <typename T, int K, int U, int IDX, bool HALO>
+static int launch_jacobi_ms_impl(const glab_plan* p, const T* vals, const T* diag, const T* b, T* xa, T* xb,
+                                 const T* omega, int nsweeps, void* stream, const glab_halo_step* hab,
+                                 const glab_halo_step* hba) {
+  if ((reinterpret_cast<uintptr_t>(p->rowptr) & 15) || (reinterpret_cast<uintptr_t>(diag) & 15) ||
+      (reinterpret_cast<uintptr_t>(b) & 15) || (reinterpret_cast<uintptr_t>(xa) & 15) ||
+      (reinterpret_cast<uintptr_t>(xb) & 15) || !p->ms_state)
+    return kNoPipe;
+  const int64_t slots = (int64_t)kThreads * (p->max_row_nnz > 0 ? p->max_row_nnz : 1);
+  if (slots > 24576) return kNoPipe;
+  PipeLayout L;
+  int off = 0;
+  L.off_row = off; off += round_up((kThreads + 1) * 4 + 32, 128);
+  L.off_col = off; off += round_up((int)slots * (IDX == 1 ? 2 : 4) + 32, 128);
+  L.off_val = off; off += round_up((int)slots * (int)sizeof(T) + 32, 128);
+  L.off_stream[0] = off; off += round_up(kThreads * (int)sizeof(T) + 32, 128);
+  L.off_stream[1] = off; off += round_up(kThreads * K * (int)sizeof(T) + 32, 128);
+  L.off_stream[2] = off;
+  L.stage_bytes = off;
+  auto kern = k_jacobi_ms<T, K, U, IDX, HALO>;
+  static int max_smem_dev[kMaxDevices] = {};
+  static int coop_dev[kMaxDevices] = {};
+  int& max_smem = max_smem_dev[p->device % kMaxDevices];
+  if (!max_smem) {
+    cudaFuncAttributes fa;
+    GLAB_CUDA(cudaFuncGetAttributes(&fa, kern));
+    const int m = 227 * 1024 - (int)fa.sharedSizeBytes;
+    GLAB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, m));
+    int coop = 0;
+    GLAB_CUDA(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, p->device));
+    coop_dev[p->device % kMaxDevices] = coop ? 1 : -1;
+    max_smem = m;
+  }
+  if (coop_dev[p->device % kMaxDevices] < 0) return kNoPipe;
+  if (2 * L.stage_bytes + 128 > max_smem) return kNoPipe;
+  const int want_ctas = tuning().ctas ? tuning().ctas : 4;
+  int stages = tuning().stages ? tuning().stages : (max_smem / want_ctas - 128) / L.stage_bytes;
+  if (stages > 4) stages = 4;
+  while (stages > 2 && (size_t)stages * L.stage_bytes + 128 > (size_t)max_smem) --stages;
+  if (stages < 2) stages = 2;
+  L.stages = stages;
+  const size_t smem = (size_t)stages * L.stage_bytes + 128;
+  int occ = 0;
+  GLAB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kPipeThreads, smem));
+  if (occ < 1) return kNoPipe;
+  if (tuning().ctas && occ > tuning().ctas) occ = tuning().ctas;
+  const int64_t n = p->n_rows;
+  const int ntiles = (int)((n + kThreads - 1) / kThreads);
+  MsCtl m;
+  m.tile_done = p->ms_state;
+  m.epoch = p->ms_state + ntiles;
+  m.ticket = reinterpret_cast<unsigned int*>(p->ms_state + ntiles + 4);
+  m.dep = (p->band_local + kThreads - 1) / kThreads + 1;
+  if (m.dep > ntiles || 2 * m.dep + 1 > 1024) m.dep = ntiles > 0 ? ntiles : 1;   // no useful band: one check per sweep
+  m.status = nullptr;
+  m.timeout_ns = spin_timeout_ns(0);
+  typename std::conditional<HALO, MsHalo, MsNoHalo>::type h;
+  int grid = p->sm_count * occ;    // every CTA co-resident (cooperative launch): they wait on one another
+  bool comm = false;
+  if constexpr (HALO) {
+    const glab_halo_step* st[2] = {hab, hba};
+    int64_t ib = hab->interior_begin, ie = hab->interior_end;
+    if (hba->interior_begin != ib || hba->interior_end != ie || !hab->done_counter) return GLAB_E_ARG;
+    if (ib < 0 || ie < ib || ie > n) return GLAB_E_ARG;
+    if (ib == ie) ib = ie = 0;
+    else if ((ib % kThreads) || (ie % kThreads && ie != n)) return GLAB_E_ARG;
+    h.int_tile0 = (int)(ib / kThreads);
+    h.int_tiles = (int)((ie - ib + kThreads - 1) / kThreads);
+    h.lead_tiles = h.int_tile0;
+    h.trail_tile0 = h.int_tile0 + h.int_tiles;
+    h.done_counter = hab->done_counter;
+    for (int d = 0; d < 2; ++d) {
+      const glab_halo_step* q = st[d];
+      if (q->n_wait < 0 || q->n_wait > GLAB_MAX_PEERS || q->n_push < 0 || q->n_push > GLAB_MAX_PEERS) return GLAB_E_ARG;
+      if ((q->n_wait > 0 && (!q->wait_flags || !q->wait_target)) || (q->n_push > 0 && !q->push)) return GLAB_E_ARG;
+      h.dir[d].n_wait = q->n_wait;
+      h.dir[d].n_push = q->n_push;
+      static const uint32_t zero_word = 0;
+      (void)zero_word;
+      for (int i = 0; i < GLAB_MAX_PEERS; ++i) {
+        h.dir[d].wait_flag[i] = i < q->n_wait ? q->wait_flags[i] : nullptr;
+        if (i < q->n_push) h.dir[d].push[i] = q->push[i];
+        else h.dir[d].push[i] = glab_push_desc{nullptr, -1, 0, nullptr, 0, nullptr};
+      }
+      h.dir[d].wait_target = q->wait_target;
+      h.dir[d].pushed_counter = q->pushed_counter;
+      if (q->n_push > 0) comm = true;
+      if (q->n_wait > 0 && !q->wait_target) return GLAB_E_ARG;
+    }
+    if (!hab->wait_target || !hba->wait_target) return GLAB_E_ARG;   // read unconditionally by the producer
+    m.status = hab->status;
+    m.timeout_ns = spin_timeout_ns(hab->timeout_ms);
+  }
+  if (grid > ntiles + (comm ? 1 : 0)) grid = ntiles + (comm ? 1 : 0);
+  if (grid < 1) grid = 1;
+  if (comm && grid < 2) grid = 2;
+  TileArgs<T> a{p->rowptr, p->colidx, vals, 0, (int)n, (int)slots, IDX ? p->coldelta : nullptr,
+                IDX == 2 ? p->tile16 : nullptr};
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3((unsigned)grid);
+  cfg.blockDim = dim3((unsigned)kPipeThreads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = as_stream(stream);
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeCooperative;
+  attr[0].val.cooperative = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return (int)cudaLaunchKernelEx(&cfg, kern, a, xa, xb, diag, b, omega, nsweeps, ntiles, L, m, h);
+}
+
+template <typename T, int K, int U, bool HALO>
+static int launch_jacobi_ms_u(const glab_plan* p, const T* vals, const T* diag, const T* b, T* xa, T* xb,
+                              const T* omega, int nsweeps, void* stream, const glab_halo_step* hab,
+                              const glab_halo_step* hba) {
+  if constexpr (idx16_ok<T, K, U>()) {
+    if (!HALO || p->idx16_halo) {
+      switch (index_mode(p, 0)) {
+        case 1: return launch_jacobi_ms_impl<T, K, U, 1, HALO>(p, vals, diag, b, xa, xb, omega, nsweeps, stream, hab, hba);
+        case 2: return launch_jacobi_ms_impl<T, K, U, 2, HALO>(p, vals, diag, b, xa, xb, omega, nsweeps, stream, hab, hba);
+        default: break;
+      }
+    }
+  }
+  return launch_jacobi_ms_impl<T, K, U, 0, HALO>(p, vals, diag, b, xa, xb, omega, nsweeps, stream, hab, hba);
+}
+
+template <typename T, bool HALO>
+static int launch_jacobi_ms(const glab_plan* p, const T* vals, const T* diag, const T* b, T* xa, T* xb,
+                            const T* omega, int k, int nsweeps, void* stream, const glab_halo_step* hab,
+                            const glab_halo_step* hba) {
+  switch (k) {
+    case 1:
+      if (p->max_row_nnz == 5) return launch_jacobi_ms_u<T, 1, 5, HALO>(p, vals, diag, b, xa, xb, omega, nsweeps, stream, hab, hba);
+      if (p->max_row_nnz == 9) return launch_jacobi_ms_u<T, 1, 9, HALO>(p, vals, diag, b, xa, xb, omega, nsweeps, stream, hab, hba);
+      return launch_jacobi_ms_u<T, 1, 8, HALO>(p, vals, diag, b, xa, xb, omega, nsweeps, stream, hab, hba);
+    case 2: return launch_jacobi_ms_u<T, 2, 4, HALO>(p, vals, diag, b, xa, xb, omega, nsweeps, stream, hab, hba);
+    case 4: return launch_jacobi_ms_u<T, 4, 2, HALO>(p, vals, diag, b, xa, xb, omega, nsweeps, stream, hab, hba);
+    case 8: return launch_jacobi_ms_u<T, 8, 2, HALO>(p, vals, diag, b, xa, xb, omega, nsweeps, stream, hab, hba);
+    default: return GLAB_E_ARG;
+  }
+}
+
+// n_sweeps weighted-Jacobi sweeps, x ping-ponging xa -> xb -> xa ...: one multi-sweep launch when the
+// operator fits that kernel, else one fused launch per sweep.  Same arithmetic either way.
+template <typename T>
+static int jacobi_sweeps(const glab_plan* p, const T* vals, const T* diag, const T* b, T* xa, T* xb,
+                         const T* omega, int k, int nsweeps, void* stream, const glab_halo_step* hab,
+                         const glab_halo_step* hba) {
+  int rc = check_common(p, vals, xa, 0, p ? p->n_rows : 0);
+  if (rc) return rc;
+  if (!diag || !b || !xb || !omega || xa == xb || nsweeps < 0) return GLAB_E_ARG;
+  if ((hab == nullptr) != (hba == nullptr)) return GLAB_E_ARG;
+  if (nsweeps == 0) return 0;
+  if (tuning().ms && tuning().pipe && nsweeps > 1 && p->n_rows > 0) {
+    rc = hab ? launch_jacobi_ms<T, true>(p, vals, diag, b, xa, xb, omega, k, nsweeps, stream, hab, hba)
+             : launch_jacobi_ms<T, false>(p, vals, diag, b, xa, xb, omega, k, nsweeps, stream, nullptr, nullptr);
+    if (rc != kNoPipe) return rc;
+  }
+  for (int s = 0; s < nsweeps; ++s) {
+    const T* xin = (s & 1) ? xb : xa;
+    T* xout = (s & 1) ? xa : xb;
+    rc = jacobi<T>(p, vals, diag, b, xin, xout, omega, k, 0, p->n_rows, stream, hab ? ((s & 1) ? hba : hab) : nullptr);
+    if (rc) return rc;
+  }
+  return 0;
+}
+
 template <typename T, class Epi>
 static int launch_reducing(const glab_plan* p, const T* vals, const T* x, const Epi& epi,
                            int64_t rb, int64_t re, void* stream, const glab_halo_step* h = nullptr) {
@@ -782,6 +975,10 @@ extern "C" int64_t glab_reduce_workspace_bytes(void) { return 64 + (int64_t)kMax
   extern "C" int glab_xtax_##SUF(const glab_plan* p, const T* v, const T* x, double* so, void* ws, \
                                  int64_t rb, int64_t re, void* s) {                                \
     return xtax<T>(p, v, x, so, ws, rb, re, s);                                                    \
+  }                                                                                                \
+  extern "C" int glab_jacobi_sweeps_##SUF(const glab_plan* p, const T* v, const T* d, const T* b,  \
+                                          T* xa, T* xb, const T* w, int k, int ns, void* s) {      \
+    return jacobi_sweeps<T>(p, v, d, b, xa, xb, w, k, ns, s, nullptr, nullptr);                    \
   }
 
 #define GLAB_HALO_INST(SUF, T)                                                                     \
@@ -800,6 +997,13 @@ extern "C" int64_t glab_reduce_workspace_bytes(void) { return 64 + (int64_t)kMax
                                         const glab_halo_step* h, void* s) {                        \
     if (!p || !h) return GLAB_E_ARG;                                                               \
     return jacobi<T>(p, v, d, b, xi, xo, w, k, 0, p->n_rows, s, h);                                \
+  }                                                                                                \
+  extern "C" int glab_jacobi_sweeps_halo_##SUF(const glab_plan* p, const T* v, const T* d,         \
+                                               const T* b, T* xa, T* xb, const T* w, int k, int ns, \
+                                               const glab_halo_step* hab,                          \
+                                               const glab_halo_step* hba, void* s) {               \
+    if (!p || !hab || !hba) return GLAB_E_ARG;                                                     \
+    return jacobi_sweeps<T>(p, v, d, b, xa, xb, w, k, ns, s, hab, hba);                            \
   }                                                                                                \
   extern "C" int glab_cheby_first_halo_##SUF(const glab_plan* p, const T* v, const T* b,           \
                                              const T* xi, T* xo, T* r, T* pv, const T* a, int k,   \

@@ -110,8 +110,47 @@ struct HaloCtl {
   uint32_t* pushed_counter;
   const void* push_src;
   unsigned int* done_counter;
+  uint32_t* status;                 // device word, OR-ed with GLAB_STATUS_* when a wait times out (may be NULL)
+  unsigned long long timeout_ns;    // 0 = wait forever
 };
 struct NoHalo {};
+
+// ---- bounded device-side waits --------------------------------------------------------------
+// Every in-kernel wait on a flag that ANOTHER CTA or ANOTHER GPU writes is bounded: after
+// `timeout_ns` of wall-clock (%globaltimer) the waiter records GLAB_STATUS_* in the caller's status
+// word and carries on, so that a protocol bug or a lost peer ends in an error code on the host
+// (glab_halo_status / DistOperator.check) instead of a hung GPU.  The results of that launch are
+// then undefined.
+__device__ __forceinline__ unsigned long long gtime_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+struct SpinGuard {
+  unsigned long long t0 = 0, limit;
+  unsigned int it = 0;
+  __device__ __forceinline__ explicit SpinGuard(unsigned long long timeout_ns) : limit(timeout_ns) {}
+  // call once per failed poll; true = give up
+  __device__ __forceinline__ bool expired() {
+    if (limit == 0 || (++it & 1023u) != 0) return false;
+    const unsigned long long t = gtime_ns();
+    if (t0 == 0) { t0 = t; return false; }
+    return t - t0 > limit;
+  }
+};
+__device__ __forceinline__ void flag_timeout(uint32_t* status, uint32_t code) {
+  if (status) atomicOr(status, code);
+}
+__device__ __forceinline__ uint32_t ld_acquire_gpu(const uint32_t* p) {
+  uint32_t v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
+  uint32_t v;
+  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
 
 template <typename T, int K>
 __device__ __forceinline__ void load_vec_cg(T (&dst)[K], const T* p) {
@@ -135,6 +174,78 @@ __device__ __forceinline__ void load_vec_cg(T (&dst)[K], const T* p) {
   }
 }
 
+// Row sum of one CSR row of a staged tile: acc[c] = sum_j v_j * x[col_j, c], added one product at a
+// time in slot order (the accumulation order of scatter_add_).  W16: the tile's columns are 2-byte
+// offsets from the row (else 4-byte absolute indices).  CG: gather through L2 (values written by other
+// SMs / GPUs while this kernel runs), else through the read-only path.  Rows of exactly U entries
+// take an unpredicated straight-line path with U gathers in flight.
+template <typename T, int K, int U, bool W16, bool CG>
+__device__ __forceinline__ void row_sum(T (&acc)[K], const unsigned char* __restrict__ cbuf, int cofs,
+                                        const T* __restrict__ sval, int rs, int re, int r,
+                                        const T* __restrict__ x) {
+  auto col_at = [&](int j) -> int {
+    if constexpr (W16) return r + (int)reinterpret_cast<const int16_t*>(cbuf)[j + cofs];
+    else return reinterpret_cast<const int32_t*>(cbuf)[j + cofs];
+  };
+  auto gather = [&](T (&d)[K], int col) {
+    if constexpr (CG) load_vec_cg<T, K>(d, x + (size_t)col * K);
+    else load_vec<T, K>(d, x + (size_t)col * K);
+  };
+  if (re - rs == U) {
+    T vv[U];
+    T xv[U][K];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int col = col_at(rs + u);
+      vv[u] = sval[rs + u];
+      gather(xv[u], col);
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+#pragma unroll
+      for (int c = 0; c < K; ++c) acc[c] = acc[c] + vv[u] * xv[u][c];
+    }
+  } else {
+    for (int base = rs; base < re; base += U) {
+      T vv[U];
+      T xv[U][K];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        if (base + u < re) {
+          const int col = col_at(base + u);
+          vv[u] = sval[base + u];
+          gather(xv[u], col);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        if (base + u < re) {
+#pragma unroll
+          for (int c = 0; c < K; ++c) acc[c] = acc[c] + vv[u] * xv[u][c];
+        }
+      }
+    }
+  }
+}
+
+// The few tiles of a row block that read the halo tail: one L2-coherent gather at a time (the tail is
+// written by the neighbours while earlier kernels of this rank may still run; these tiles are a
+// vanishing share of the work, so they get the smallest body, not the fastest).
+template <typename T, int K, bool W16>
+__device__ __forceinline__ void row_sum_coherent(T (&acc)[K], const unsigned char* __restrict__ cbuf, int cofs,
+                                                 const T* __restrict__ sval, int rs, int re, int r, const T* x) {
+  for (int j = rs; j < re; ++j) {
+    int col;
+    if constexpr (W16) col = r + (int)reinterpret_cast<const int16_t*>(cbuf)[j + cofs];
+    else col = reinterpret_cast<const int32_t*>(cbuf)[j + cofs];
+    T xv[K];
+    load_vec_cg<T, K>(xv, x + (size_t)col * K);
+    const T v = sval[j];
+#pragma unroll
+    for (int c = 0; c < K; ++c) acc[c] = acc[c] + v * xv[c];
+  }
+}
+
 // Epilogue protocol for the pipeline (all in glab_layers.cu):
 //   static constexpr int kStreams;  const T* stream_ptr(i);  int stream_width(i)  (elements/row)
 //   State, init(State&), finish(State&)
@@ -154,7 +265,6 @@ template <typename T, int K, int U, class Epi, bool HALO, int IDX = 0>
 __global__ void __launch_bounds__(kPipeThreads, (K * sizeof(T) <= 8) ? 4 : 2)
 k_row_pipe(TileArgs<T> a, const T* __restrict__ x, Epi epi, int ntiles, PipeLayout L,
            typename std::conditional<HALO, HaloCtl, NoHalo>::type h) {
-  static_assert(!(HALO && IDX == 1), "row blocks with halo columns are never banded in every tile");
   extern __shared__ __align__(128) unsigned char smem_raw[];
   uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw);
   uint64_t* empty = full + L.stages;
@@ -197,6 +307,14 @@ k_row_pipe(TileArgs<T> a, const T* __restrict__ x, Epi epi, int ntiles, PipeLayo
     }
   }
 
+  if constexpr (HALO) {
+    // A rank with nothing to send still counts this step as one "push" of the produced vector: the
+    // counter is the wait target of the next step that gathers it.
+    if (!comm_cta && h.n_push == 0 && blockIdx.x == 0 && tid == 0 && h.pushed_counter) {
+      pdl_wait();
+      *h.pushed_counter += 1u;
+    }
+  }
   if (comm_cta) {
     pdl_wait();
     epi.init(st);
@@ -204,12 +322,11 @@ k_row_pipe(TileArgs<T> a, const T* __restrict__ x, Epi epi, int ntiles, PipeLayo
       // ---------------------------------------------------------------- communication CTA
       const unsigned int nb = (unsigned int)(ntiles - h.int_tiles);
       if (tid == 0) {
-        unsigned int v;
-        do {
-          asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(h.done_counter) : "memory");
-          if (v >= nb) break;
+        SpinGuard guard(h.timeout_ns);
+        while (ld_acquire_gpu(h.done_counter) < nb) {
           __nanosleep(200);
-        } while (true);
+          if (guard.expired()) { flag_timeout(h.status, GLAB_STATUS_TIMEOUT_TILES); break; }
+        }
       }
       __syncthreads();
       __threadfence();
@@ -261,12 +378,11 @@ k_row_pipe(TileArgs<T> a, const T* __restrict__ x, Epi epi, int ntiles, PipeLayo
           if (bnd && !waited) {  // neighbours' halo rows must have landed before consumers gather them
             const uint32_t want = *reinterpret_cast<const volatile uint32_t*>(h.wait_target);
             for (int i = 0; i < h.n_wait; ++i) {
-              uint32_t v;
-              do {
-                asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(h.wait_flag[i]) : "memory");
-                if ((int32_t)(v - want) >= 0) break;
+              SpinGuard guard(h.timeout_ns);
+              while ((int32_t)(ld_acquire_sys(h.wait_flag[i]) - want) < 0) {
                 __nanosleep(32);
-              } while (true);
+                if (guard.expired()) { flag_timeout(h.status, GLAB_STATUS_TIMEOUT_PEER); break; }
+              }
             }
             waited = true;
           }
@@ -327,59 +443,25 @@ k_row_pipe(TileArgs<T> a, const T* __restrict__ x, Epi epi, int ntiles, PipeLayo
       if (r < r1) {
         const int e0 = srow[0];
         const int rs = srow[tid], re = srow[tid + 1];
-        // slot j's column: 2-byte offset from this row or 4-byte absolute index
+        // the tile's columns are 2-byte offsets from the row or 4-byte absolute indices: ONE block-uniform
+        // branch per tile around straight-line row bodies (no per-element select)
         const unsigned char* cbuf = sb + L.off_col;
-        const int cofs = ((IDX != 0 && t16) ? lead_elems(a.coldelta + e0, 2) : lead_elems(a.colidx + e0, 4)) - e0;
-        auto col_at = [&](int j) -> int {
-          if (IDX != 0 && t16) return r + (int)reinterpret_cast<const int16_t*>(cbuf)[j + cofs];
-          return reinterpret_cast<const int32_t*>(cbuf)[j + cofs];
-        };
         const T* sval = reinterpret_cast<const T*>(sb + L.off_val) + lead_elems(a.vals + e0, sizeof(T)) - e0;
         T acc[K];
 #pragma unroll
         for (int c = 0; c < K; ++c) acc[c] = T(0);
-        if (HALO && bnd) {
-          // rows that read the halo tail: L2-coherent gathers (the tail was written by peers)
-          for (int j = rs; j < re; ++j) {
-            T xv[K];
-            load_vec_cg<T, K>(xv, x + (size_t)col_at(j) * K);
-            const T v = sval[j];
-#pragma unroll
-            for (int c = 0; c < K; ++c) acc[c] = acc[c] + v * xv[c];
-          }
-        } else if (re - rs == U) {
-          T vv[U];
-          T xv[U][K];
-#pragma unroll
-          for (int u = 0; u < U; ++u) {
-            const int col = col_at(rs + u);
-            vv[u] = sval[rs + u];
-            load_vec<T, K>(xv[u], x + (size_t)col * K);
-          }
-#pragma unroll
-          for (int u = 0; u < U; ++u) {
-#pragma unroll
-            for (int c = 0; c < K; ++c) acc[c] = acc[c] + vv[u] * xv[u][c];
+        if (IDX != 0 && t16) {
+          if constexpr (IDX != 0) {
+            const int cofs = lead_elems(a.coldelta + e0, 2) - e0;
+            // rows that read the halo tail gather through L2 (the tail was written by peers)
+            if (HALO && bnd) row_sum_coherent<T, K, true>(acc, cbuf, cofs, sval, rs, re, r, x);
+            else row_sum<T, K, U, true, false>(acc, cbuf, cofs, sval, rs, re, r, x);
           }
         } else {
-          for (int base = rs; base < re; base += U) {
-            T vv[U];
-            T xv[U][K];
-#pragma unroll
-            for (int u = 0; u < U; ++u) {
-              if (base + u < re) {
-                const int col = col_at(base + u);
-                vv[u] = sval[base + u];
-                load_vec<T, K>(xv[u], x + (size_t)col * K);
-              }
-            }
-#pragma unroll
-            for (int u = 0; u < U; ++u) {
-              if (base + u < re) {
-#pragma unroll
-                for (int c = 0; c < K; ++c) acc[c] = acc[c] + vv[u] * xv[u][c];
-              }
-            }
+          if constexpr (IDX != 1) {
+            const int cofs = lead_elems(a.colidx + e0, 4) - e0;
+            if (HALO && bnd) row_sum_coherent<T, K, false>(acc, cbuf, cofs, sval, rs, re, r, x);
+            else row_sum<T, K, U, false, false>(acc, cbuf, cofs, sval, rs, re, r, x);
           }
         }
         const T* sp[kMaxStreams] = {nullptr, nullptr, nullptr};

@@ -74,6 +74,26 @@ __global__ void k_max_row(const int32_t* __restrict__ rowptr, int64_t n_rows, in
   if ((threadIdx.x & 31) == 0 && m > 0) atomicMax(out, m);
 }
 
+// max |col - row| over the local columns (col < n_rows): the dependency band of the multi-sweep kernels
+__global__ void k_band(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ colidx, int64_t n_rows,
+                       int* out) {
+  int m = 0;
+  for (int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; r < n_rows;
+       r += (int64_t)gridDim.x * blockDim.x) {
+    const int e1 = rowptr[r + 1];
+    for (int e = rowptr[r]; e < e1; ++e) {
+      const int64_t c = colidx[e];
+      if (c < n_rows) {
+        const int64_t d = c > r ? c - r : r - c;
+        m = max(m, (int)d);
+      }
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0 && m > 0) atomicMax(out, m);
+}
+
 // delta[slot] = col - row as int16; a row with a delta that does not fit clears its tile's flag
 __global__ void k_col_delta(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ colidx,
                             int64_t n_rows, int16_t* __restrict__ delta, uint8_t* __restrict__ tile16) {
@@ -202,6 +222,9 @@ static void plan_free(glab_plan* p) {
   if (p->coldelta) cudaFree(p->coldelta);
   if (p->tile16) cudaFree(p->tile16);
   if (p->owned_vals) cudaFree(p->owned_vals);
+  if (p->ms_state) cudaFree(p->ms_state);
+  for (void* q : p->retired)
+    if (q) cudaFree(q);
   delete p;
 }
 
@@ -223,13 +246,19 @@ static int plan_alloc(int64_t n_rows, int64_t n_cols, int64_t nnz, glab_plan** o
   p->tiles16 = p->tiles_total = 0;
   p->idx16_halo = 0;
   p->max_row_nnz = 0;
+  p->band_local = 0;
+  p->ms_state = nullptr;
   p->owned_vals = nullptr;
   p->owned_vals_bytes = 0;
+  for (void*& q : p->retired) q = nullptr;
   cudaError_t e = cudaGetDevice(&p->device);
   if (e == cudaSuccess)
     e = cudaDeviceGetAttribute(&p->sm_count, cudaDevAttrMultiProcessorCount, p->device);
   if (e == cudaSuccess) e = cudaMalloc(&p->rowptr, (size_t)(n_rows + 1 + 8) * sizeof(int32_t));
   if (e == cudaSuccess) e = cudaMalloc(&p->colidx, (size_t)(nnz + 8) * sizeof(int32_t));
+  const size_t ms_words = (size_t)((n_rows + kThreads - 1) / kThreads) + 32;
+  if (e == cudaSuccess) e = cudaMalloc(&p->ms_state, ms_words * sizeof(uint32_t));
+  if (e == cudaSuccess) e = cudaMemset(p->ms_state, 0, ms_words * sizeof(uint32_t));
   if (e != cudaSuccess) {
     plan_free(p);
     cudaGetLastError();
@@ -242,9 +271,9 @@ static int plan_alloc(int64_t n_rows, int64_t n_cols, int64_t nnz, glab_plan** o
 // 2-byte row-relative column indices: the pipeline kernels stream 2 B instead of 4 B of index per
 // nonzero in every 256-row tile whose deltas all fit int16.  GLAB_IDX16 = 0 disables it, 1 keeps it
 // only for plans where EVERY tile qualifies (banded operators), 2 (default) also keeps mixed plans
-// (periodic wrap-around rows, halo columns of a row block) when at least half of the tiles qualify,
-// 3 additionally lets the fused multi-GPU halo kernels use it (interior tiles of a row block; measured
-// neutral at 2 GPUs -- 0.0797 vs 0.0803 ms per sweep -- so it is not the default).
+// (periodic wrap-around rows, halo columns of a row block) when at least half of the tiles qualify.
+// GLAB_IDX16_HALO = 0 keeps the fused multi-GPU halo kernels on int32 (default 1: they stream 2-byte
+// indices in the qualifying tiles like the single-GPU kernels).
 // Optional: on allocation failure the plan simply stays on int32.
 static int plan_build_coldelta(glab_plan* p, cudaStream_t st) {
   const char* env = getenv("GLAB_IDX16");
@@ -282,7 +311,8 @@ static int plan_build_coldelta(glab_plan* p, cudaStream_t st) {
   p->tile16 = f;
   p->tiles16 = good;
   p->tiles_total = ntiles;
-  p->idx16_halo = mode >= 3 ? 1 : 0;
+  const char* eh = getenv("GLAB_IDX16_HALO");
+  p->idx16_halo = eh ? (atoi(eh) != 0) : 1;
   return 0;
 }
 
@@ -311,13 +341,13 @@ extern "C" int glab_plan_create(int64_t n_rows, int64_t n_cols, int64_t nnz, con
   int rc = plan_alloc(n_rows, n_cols, nnz, &p);
   if (rc) return rc;
   cudaStream_t st = as_stream(stream_);
-  int* d_flags = nullptr;  // [0] validation flags, [1] max row nnz
-  int h_flags[2] = {0, 0};
+  int* d_flags = nullptr;  // [0] validation flags, [1] max row nnz, [2] local band
+  int h_flags[3] = {0, 0, 0};
   int32_t* keys_in = nullptr;
   int32_t* keys_out = nullptr;
   int32_t* ids_in = nullptr;
   void* tmp = nullptr;
-  cudaError_t e = cudaMalloc(&d_flags, 2 * sizeof(int));
+  cudaError_t e = cudaMalloc(&d_flags, 3 * sizeof(int));
   auto fail = [&](int code) {
     if (d_flags) cudaFree(d_flags);
     if (keys_in) cudaFree(keys_in);
@@ -329,7 +359,7 @@ extern "C" int glab_plan_create(int64_t n_rows, int64_t n_cols, int64_t nnz, con
     return code;
   };
   if (e != cudaSuccess) return fail((int)e);
-  if ((e = cudaMemsetAsync(d_flags, 0, 2 * sizeof(int), st)) != cudaSuccess) return fail((int)e);
+  if ((e = cudaMemsetAsync(d_flags, 0, 3 * sizeof(int), st)) != cudaSuccess) return fail((int)e);
   const int g = grid_for(nnz, p->sm_count);
   if (nnz > 0) k_validate<<<g, 256, 0, st>>>(row, col, nnz, n_rows, n_cols, d_flags);
   if ((e = cudaMemcpyAsync(h_flags, d_flags, sizeof(int), cudaMemcpyDeviceToHost, st)) !=
@@ -362,13 +392,17 @@ extern "C" int glab_plan_create(int64_t n_rows, int64_t n_cols, int64_t nnz, con
                                                                                  n_rows, p->rowptr);
     k_permute_cols<<<g, 256, 0, st>>>(col, p->perm, nnz, p->colidx);
   }
-  if (n_rows > 0) k_max_row<<<grid_for(n_rows, p->sm_count), 256, 0, st>>>(p->rowptr, n_rows, d_flags + 1);
-  if ((e = cudaMemcpyAsync(h_flags + 1, d_flags + 1, sizeof(int), cudaMemcpyDeviceToHost, st)) !=
+  if (n_rows > 0) {
+    k_max_row<<<grid_for(n_rows, p->sm_count), 256, 0, st>>>(p->rowptr, n_rows, d_flags + 1);
+    k_band<<<grid_for(n_rows, p->sm_count), 256, 0, st>>>(p->rowptr, p->colidx, n_rows, d_flags + 2);
+  }
+  if ((e = cudaMemcpyAsync(h_flags + 1, d_flags + 1, 2 * sizeof(int), cudaMemcpyDeviceToHost, st)) !=
       cudaSuccess)
     return fail((int)e);
   if ((e = cudaStreamSynchronize(st)) != cudaSuccess) return fail((int)e);
   if ((e = cudaGetLastError()) != cudaSuccess) return fail((int)e);
   p->max_row_nnz = h_flags[1];
+  p->band_local = h_flags[2];
   if (int rcd = plan_build_coldelta(p, st)) return fail(rcd);
   cudaFree(d_flags);
   if (keys_in) cudaFree(keys_in);
@@ -388,8 +422,8 @@ extern "C" int glab_plan_create_csr(int64_t n_rows, int64_t n_cols, int64_t nnz,
   if (rc) return rc;
   cudaStream_t st = as_stream(stream_);
   int* d_flags = nullptr;
-  int h_flags[2] = {0, 0};
-  cudaError_t e = cudaMalloc(&d_flags, 2 * sizeof(int));
+  int h_flags[3] = {0, 0, 0};
+  cudaError_t e = cudaMalloc(&d_flags, 3 * sizeof(int));
   auto fail = [&](int code) {
     if (d_flags) cudaFree(d_flags);
     plan_free(p);
@@ -397,19 +431,23 @@ extern "C" int glab_plan_create_csr(int64_t n_rows, int64_t n_cols, int64_t nnz,
     return code;
   };
   if (e != cudaSuccess) return fail((int)e);
-  cudaMemsetAsync(d_flags, 0, 2 * sizeof(int), st);
+  cudaMemsetAsync(d_flags, 0, 3 * sizeof(int), st);
   cudaMemcpyAsync(p->rowptr, rowptr, (size_t)(n_rows + 1) * 4, cudaMemcpyDeviceToDevice, st);
   if (nnz > 0) cudaMemcpyAsync(p->colidx, colidx, (size_t)nnz * 4, cudaMemcpyDeviceToDevice, st);
   k_validate_csr<<<grid_for(nnz > n_rows ? nnz : n_rows, p->sm_count), 256, 0, st>>>(
       p->rowptr, p->colidx, n_rows, n_cols, nnz, d_flags);
-  if (n_rows > 0) k_max_row<<<grid_for(n_rows, p->sm_count), 256, 0, st>>>(p->rowptr, n_rows, d_flags + 1);
-  if ((e = cudaMemcpyAsync(h_flags, d_flags, 2 * sizeof(int), cudaMemcpyDeviceToHost, st)) !=
+  if (n_rows > 0) {
+    k_max_row<<<grid_for(n_rows, p->sm_count), 256, 0, st>>>(p->rowptr, n_rows, d_flags + 1);
+    k_band<<<grid_for(n_rows, p->sm_count), 256, 0, st>>>(p->rowptr, p->colidx, n_rows, d_flags + 2);
+  }
+  if ((e = cudaMemcpyAsync(h_flags, d_flags, 3 * sizeof(int), cudaMemcpyDeviceToHost, st)) !=
       cudaSuccess)
     return fail((int)e);
   if ((e = cudaStreamSynchronize(st)) != cudaSuccess) return fail((int)e);
   if ((e = cudaGetLastError()) != cudaSuccess) return fail((int)e);
   if (h_flags[0]) return fail(GLAB_E_RANGE);
   p->max_row_nnz = h_flags[1];
+  p->band_local = h_flags[2];
   if (int rcd = plan_build_coldelta(p, st)) return fail(rcd);
   cudaFree(d_flags);
   *out = p;
@@ -512,12 +550,19 @@ static int adopt_vals(glab_plan* p, const T* vals, const T** out, void* stream) 
   void* buf = nullptr;
   cudaError_t e = cudaMalloc(&buf, col_bytes + val_bytes);
   if (e != cudaSuccess) { cudaGetLastError(); return GLAB_E_NOMEM; }
+  // The replaced allocation may still be referenced (glab_plan_csr pointers handed out earlier, an
+  // earlier adoption's values): it is retired, not freed, until the plan is destroyed.
+  int slot = -1;
+  for (int i = 0; i < 4; ++i)
+    if (!p->retired[i]) { slot = i; break; }
+  if (slot < 0) { cudaFree(buf); return GLAB_E_ARG; }   // adopted too often
   cudaStream_t st = as_stream(stream);
-  GLAB_CUDA(cudaMemcpyAsync(buf, p->colidx, (size_t)p->nnz * 4, cudaMemcpyDeviceToDevice, st));
-  GLAB_CUDA(cudaMemcpyAsync((char*)buf + col_bytes, vals, (size_t)p->nnz * sizeof(T), cudaMemcpyDeviceToDevice, st));
-  GLAB_CUDA(cudaStreamSynchronize(st));
-  cudaFree(p->colidx);
-  if (p->owned_vals) { /* previous adoption lived inside the old colidx allocation */ }
+  e = cudaMemcpyAsync(buf, p->colidx, (size_t)p->nnz * 4, cudaMemcpyDeviceToDevice, st);
+  if (e == cudaSuccess)
+    e = cudaMemcpyAsync((char*)buf + col_bytes, vals, (size_t)p->nnz * sizeof(T), cudaMemcpyDeviceToDevice, st);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+  if (e != cudaSuccess) { cudaFree(buf); return (int)e; }
+  p->retired[slot] = p->colidx;
   p->colidx = reinterpret_cast<int32_t*>(buf);
   p->owned_vals = nullptr;  // the values live inside the colidx allocation: freed with it
   p->owned_vals_bytes = col_bytes + val_bytes;

@@ -29,7 +29,9 @@ import torch
 import torch.distributed as dist
 
 from . import _runtime as rt
-from ._lib import check, lib
+from ._lib import GlabError, check, lib
+
+MAX_PEERS = 8      # GLAB_MAX_PEERS of include/glab.h
 
 
 class RowPartition:
@@ -70,6 +72,11 @@ class HaloPlan:
         self.send_rows = send_rows                      # per peer: LOCAL row ids (int32 tensors)
         self.peers_recv = [q for q in range(part.world) if recv_counts[q] > 0]
         self.peers_send = [q for q in range(part.world) if send_rows[q].numel() > 0]
+        # Every pair of ranks that exchanges rows in EITHER direction signals in BOTH: a rank that only
+        # receives from q still bumps q's arrival counter (an empty push), which is the acknowledgement
+        # the push protocol needs before q may overwrite that halo tail again (structurally
+        # non-symmetric operators: q's rows reach us, ours never reach q).
+        self.peers = sorted(set(self.peers_recv) | set(self.peers_send))
 
     @classmethod
     def build(cls, part, rank, global_cols, group=None):
@@ -264,26 +271,32 @@ class PeerHalo:
         nw = len(names) * world
         # contiguous send blocks (every stencil slab) are copied without index loads
         self._first_row = {}
-        for q in halo.peers_send:
+        if len(halo.peers) > MAX_PEERS:
+            raise GlabError("row block exchanges halo rows with %d ranks; the peer-memory engine handles %d "
+                            "(use engine='torch')" % (len(halo.peers), MAX_PEERS))
+        for q in halo.peers:
             idx = halo.send_rows[q].long()
+            if idx.numel() == 0:
+                self._first_row[q] = 0                  # empty push: only the arrival counter is bumped
+                continue
             first = int(idx[0].item())
             contiguous = bool(torch.equal(idx, torch.arange(first, first + idx.numel(), device=idx.device)))
             self._first_row[q] = first if contiguous else -1
         for nm in names:
-            descs = (PushDesc * max(len(halo.peers_send), 1))()
-            for i, q in enumerate(halo.peers_send):
+            descs = (PushDesc * max(len(halo.peers), 1))()
+            for i, q in enumerate(halo.peers):
                 idx = halo.send_rows[q]
-                descs[i].send_idx = idx.data_ptr()
+                descs[i].send_idx = idx.data_ptr() if idx.numel() else None
                 descs[i].first_row = self._first_row[q]
                 descs[i].count = idx.numel()
                 descs[i].dst = self.bufs[nm].peer_ptr[q]
                 descs[i].dst_offset = peer_n_local[q] + offs[q][self.rank]
                 descs[i].flag = self.flags.peer_ptr[q] + (self.flag_index[nm] * world + self.rank) * 16
             self._push_desc[nm] = descs
-            nf = len(halo.peers_recv)
+            nf = len(halo.peers)
             fl = (ctypes.c_void_p * max(nf, 1))()
             base = self.flags.peer_ptr[self.rank]
-            for i, q in enumerate(halo.peers_recv):
+            for i, q in enumerate(halo.peers):
                 fl[i] = base + (self.flag_index[nm] * world + q) * 16
             pushed = base + (nw + self.flag_index[nm]) * 16
             self._wait_args[nm] = (nf, fl, ctypes.c_void_p(pushed))
@@ -306,7 +319,7 @@ class PeerHalo:
         st.wait_flags = fl
         st.wait_target = pushed_in
         if name_out is not None:
-            st.n_push = len(self.halo.peers_send)
+            st.n_push = len(self.halo.peers)
             st.push = self._push_desc[name_out]
             st.pushed_counter = self._wait_args[name_out][2]
             st.push_src = self.views[name_out].data_ptr()
@@ -315,13 +328,36 @@ class PeerHalo:
             st.push = None
             st.pushed_counter = None
             st.push_src = None
-        st.done_counter = self.flags.peer_ptr[self.rank] + (2 * len(self.flag_index) * world) * 16
+        st.done_counter = self._spare_word(0)      # two counters, 16 bytes apart (words 0 and 1)
+        st.status = self._spare_word(2)
+        st.timeout_ms = 0                           # library default (GLAB_SPIN_TIMEOUT_MS)
         self._steps[key] = st
         return st
 
+    def _spare_word(self, i):
+        """16-byte spaced scratch words behind the counters of the flag buffer: 0, 1 = boundary-tile
+        counters of the fused steps, 2 = status word of the bounded in-kernel waits."""
+        world = self.halo.part.world
+        return self.flags.peer_ptr[self.rank] + (2 * len(self.flag_index) * world + i) * 16
+
+    def status(self):
+        """GLAB_STATUS_* bits recorded by in-kernel waits that gave up (0 = none).  Synchronises."""
+        world = self.halo.part.world
+        torch.cuda.synchronize(self.device)
+        return int(self.flags.local[(2 * len(self.flag_index) * world + 2) * 4].item())
+
+    def check(self):
+        st = self.status()
+        if st:
+            names = [n for bit, n in ((1, "a neighbour's halo rows did not arrive"),
+                                      (2, "this GPU's boundary tiles did not finish"),
+                                      (4, "a tile of the previous sweep did not finish")) if st & bit]
+            raise GlabError("fused halo step timed out on rank %d: %s (status %d); results of that step are "
+                            "undefined" % (self.rank, "; ".join(names), st))
+
     def push(self, name):
         """After the kernel that produced vector `name`: send boundary rows to every neighbour."""
-        n = len(self.halo.peers_send)
+        n = len(self.halo.peers)
         fn = getattr(lib, "glab_halo_push_" + self._suf)
         rt.launch_count += 1
         with torch.cuda.device(self.device):
@@ -385,6 +421,8 @@ class DistOperator:
             self.vec = {nm: torch.zeros(n_ext, k, dtype=self.dtype, device=self.device) for nm in self.names}
         self.n_local, self.n_ext = n_loc, n_ext
         self.side = torch.cuda.Stream(self.device) if (self.peer is not None and local_vals.is_cuda) else None
+        import os
+        self.multi_sweep = os.environ.get("GLAB_DIST_MS", "1") != "0"
 
     # -- halo plumbing -----------------------------------------------------------------------
     def publish(self, name):
@@ -472,7 +510,23 @@ class DistOperator:
         through "va"/"vb" (never overwriting `start` if it is "v0"); returns the name of the
         vector holding the result."""
         cur = start
-        for _ in range(n_iters):
+        todo = n_iters
+        if self.engine == "peer" and self.halo.part.world > 1 and self.multi_sweep and n_iters > 1:
+            # One launch for all sweeps (glab_jacobi_sweeps_halo_*).  The multi-sweep kernel overwrites both
+            # of its buffers, so a start vector that must stay intact ("v0") takes one ordinary sweep first.
+            if cur == "v0":
+                xin, xout = self.vec["v0"], self.vec["va"]
+                self.run_step("v0", lambda **kw: rt.jacobi(self.plan, self.vals, diag, b, xin, xout, omega_dev, **kw),
+                              "va")
+                cur, todo = "va", todo - 1
+            if todo > 1:
+                oth = "vb" if cur == "va" else "va"
+                interior = self._ranges()[0]
+                steps = (self.peer.step(cur, oth, interior), self.peer.step(oth, cur, interior))
+                res = rt.jacobi_sweeps(self.plan, self.vals, diag, b, self.vec[cur], self.vec[oth], omega_dev, todo,
+                                       halo=steps)
+                return oth if res is self.vec[oth] else cur
+        for _ in range(todo):
             nxt = "va" if cur != "va" else "vb"
             xin, xout = self.vec[cur], self.vec[nxt]
             self.run_step(cur, lambda **kw: rt.jacobi(self.plan, self.vals, diag, b, xin, xout, omega_dev, **kw),
@@ -564,6 +618,11 @@ class DistOperator:
         for i, rng in enumerate(boundary):
             launch(rng, tmp[2 * i + 2:2 * i + 4])
         total.copy_(tmp.view(-1, 2).sum(0))
+
+    def check(self):
+        """Raise if an in-kernel wait of a fused step gave up (bounded spins); synchronises."""
+        if self.peer is not None:
+            self.peer.check()
 
     def close(self):
         if self.peer is not None:

@@ -25,6 +25,15 @@
  *     k in {1,2,4,8}); per-edge arrays are in CSR slot order unless the name says `edge order`.
  *   - scalars that the reference keeps in the global attribute tensor `g` (omega, alpha, beta,
  *     1/norm) are read through DEVICE pointers so no step ever needs a host sync.
+ *   - ALIGNMENT AND PADDING of caller arrays.  The pipeline kernels move CSR-ordered per-edge arrays
+ *     (vals, S, aux) and dense vectors with 16-byte bulk copies whose source range is widened to
+ *     16-byte granules: they may READ up to 15 bytes before the first and after the last element a
+ *     call needs (never write).  Every such array must therefore live in an allocation that starts
+ *     16-byte aligned and whose size is a multiple of 16 bytes -- true for cudaMalloc, torch and
+ *     every pooled allocator (256-byte or larger granules); a C caller that sub-allocates must
+ *     round its blocks the same way.  Dense vectors and diag must START 16-byte aligned; vectors
+ *     that are not are still accepted by the non-halo entry points (slower kernel), the *_halo
+ *     entry points return GLAB_E_ARG.
  *   - floating point: element-wise chains use IEEE mul/add/div in the reference's operation
  *     order with FMA contraction disabled, and row sums accumulate sequentially in edge order
  *     (the order of scatter_add_), so results match the reference's CPU path bit for bit
@@ -144,6 +153,22 @@ int glab_jacobi_f32(const glab_plan*, const float* vals, const float* diag, cons
 int glab_jacobi_f64(const glab_plan*, const double* vals, const double* diag, const double* b,
                     const double* x_in, double* x_out, const double* omega_dev, int k,
                     int64_t row_begin, int64_t row_end, void* stream);
+
+/* n_sweeps weighted-Jacobi sweeps in ONE launch (the Python loop `for i in range(n_iters)` of
+ * JacobiGNN.py:143-144 around the block above).  x ping-pongs xa -> xb -> xa ...: xa holds the start
+ * vector, the result is in xb when n_sweeps is odd, in xa when it is even; both buffers are
+ * overwritten.  A persistent, cooperatively launched kernel keeps its TMA ring running across the
+ * sweep boundaries; tile t of sweep s starts once the tiles within the operator's band around t
+ * have finished sweep s - 1 (per-tile completion counters inside the plan), so there is no grid
+ * barrier and no pipeline drain between sweeps.  Same arithmetic, bit for bit, as n_sweeps calls of
+ * glab_jacobi_*; operators that do not fit the pipeline (or devices without cooperative launch, or
+ * GLAB_MS=0) are run as exactly those calls.  One multi-sweep launch at a time per plan. */
+int glab_jacobi_sweeps_f32(const glab_plan*, const float* vals, const float* diag, const float* b,
+                           float* xa, float* xb, const float* omega_dev, int k, int n_sweeps,
+                           void* stream);
+int glab_jacobi_sweeps_f64(const glab_plan*, const double* vals, const double* diag, const double* b,
+                           double* xa, double* xb, const double* omega_dev, int k, int n_sweeps,
+                           void* stream);
 
 /* Chebyshev iteration 1:  r = b - A x_in;  p = r;  x_out = x_in + alpha*p.
  * Replaces ChebyGNN.py:49-70, :73-89, :91-121, :141-163.  alpha_dev -> 1/d (:137). */
@@ -344,7 +369,14 @@ typedef struct glab_halo_step {
   uint32_t* pushed_counter;
   const void* push_src;
   uint32_t* done_counter;
+  uint32_t* status;        /* device word (may be NULL): OR-ed with GLAB_STATUS_* when an in-kernel
+                              wait gave up after timeout_ms; the results of that launch are undefined */
+  int64_t timeout_ms;      /* bound of every in-kernel wait on a flag written by another CTA / GPU;
+                              0 = the library default (GLAB_SPIN_TIMEOUT_MS, else 20000), < 0 = forever */
 } glab_halo_step;
+#define GLAB_STATUS_TIMEOUT_PEER   1u  /* a neighbour's arrival counter did not reach its target   */
+#define GLAB_STATUS_TIMEOUT_TILES  2u  /* this GPU's own boundary tiles did not finish             */
+#define GLAB_STATUS_TIMEOUT_SWEEP  4u  /* multi-sweep kernel: a tile of the previous sweep did not */
 
 int glab_spmm_halo_f32(const glab_plan*, const float* vals, const float* x, int k, float* y,
                        const glab_halo_step* halo, void* stream);
@@ -360,6 +392,16 @@ int glab_jacobi_halo_f32(const glab_plan*, const float* vals, const float* diag,
 int glab_jacobi_halo_f64(const glab_plan*, const double* vals, const double* diag, const double* b,
                          const double* x_in, double* x_out, const double* omega_dev, int k,
                          const glab_halo_step* halo, void* stream);
+/* Multi-sweep Jacobi on a row block: step_ab describes the sweeps that gather xa and produce xb (wait
+ * on xa's arrival counters, push xb), step_ba the others.  Both buffers must be peer-mapped gathered
+ * vectors [n_local + n_halo, k]; done_counter must point at 32 bytes of zero-initialised device
+ * memory (two counters, 16 bytes apart). */
+int glab_jacobi_sweeps_halo_f32(const glab_plan*, const float* vals, const float* diag, const float* b,
+                                float* xa, float* xb, const float* omega_dev, int k, int n_sweeps,
+                                const glab_halo_step* step_ab, const glab_halo_step* step_ba, void* stream);
+int glab_jacobi_sweeps_halo_f64(const glab_plan*, const double* vals, const double* diag, const double* b,
+                                double* xa, double* xb, const double* omega_dev, int k, int n_sweeps,
+                                const glab_halo_step* step_ab, const glab_halo_step* step_ba, void* stream);
 int glab_cheby_first_halo_f32(const glab_plan*, const float* vals, const float* b, const float* x_in,
                               float* x_out, float* r, float* p, const float* alpha_dev, int k,
                               const glab_halo_step* halo, void* stream);

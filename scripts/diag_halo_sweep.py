@@ -43,7 +43,9 @@ def timed(fn, reps):
 
 
 def run_mode(mode, N, sweeps, dev):
-    os.environ["GLAB_IDX16"] = str(mode)
+    # mode: "0" = int32 plans, "2h0" = 16-bit plans but the fused halo kernels stay on int32, "2" = both on 16-bit
+    os.environ["GLAB_IDX16"] = "0" if mode == "0" else "2"
+    os.environ["GLAB_IDX16_HALO"] = "0" if mode == "2h0" else "1"
     rt.clear_caches()
     dt, world = torch.float32, 2
     n = N * N
@@ -133,8 +135,9 @@ def run_mode(mode, N, sweeps, dev):
         state["cur"] = nxt
 
     t_halo = timed(halo_sweep, sweeps) / world
-    # plain kernel on rank 0's block: vectors in the IPC buffers, then in torch memory
-    o = ops[0]
+    # plain kernel on rank 1's block (mixed plan: its first tiles read the halo tail): vectors in the
+    # IPC buffers, then in torch memory
+    o = ops[1]
     t_plain_ipc = timed(lambda: rt.jacobi(o["plan"], o["vals"], o["diag"], o["b"], o["vec"][0], o["vec"][1], w), sweeps)
     xa, xb = o["vec"][0].clone(), torch.empty_like(o["vec"][1])
     t_plain = timed(lambda: rt.jacobi(o["plan"], o["vals"], o["diag"], o["b"], xa, xb, w), sweeps)
@@ -155,12 +158,13 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--grid", type=int, default=4096)
     ap.add_argument("--sweeps", type=int, default=50)
-    ap.add_argument("--modes", default="0,2,3")
+    ap.add_argument("--modes", default="0,2h0,2")
     args = ap.parse_args()
     dev = torch.device("cuda:0")
-    for mode in [int(m) for m in args.modes.split(",")]:
+    for mode in args.modes.split(","):
         print(json.dumps(run_mode(mode, args.grid, args.sweeps, dev)), flush=True)
     os.environ.pop("GLAB_IDX16", None)
+    os.environ.pop("GLAB_IDX16_HALO", None)
 
 
 if __name__ == "__main__":

@@ -31,8 +31,8 @@ def main():
     # N = 512: row blocks of > 32767 rows, so the plans are MIXED (tiles that read the halo tail
     # stream int32 column indices, interior tiles 16-bit row-relative ones)
     for dt, N, gen in ((torch.float32, 96, "lap"), (torch.float64, 64, "heat"), (torch.float32, 512, "lap")):
-        # the last case also lets the fused halo kernels stream 16-bit indices (GLAB_IDX16=3, not the default)
-        os.environ["GLAB_IDX16"] = "3" if N == 512 else "2"
+        # the first case keeps the fused halo kernels on int32 column indices (default: 16-bit where a tile qualifies)
+        os.environ["GLAB_IDX16_HALO"] = "0" if N == 96 else "1"
         n = N * N
         if gen == "lap":
             ei, ev = G.generators.laplacian_2d(N, torch.float64, dev)
@@ -82,7 +82,7 @@ def main():
             ok = ok and e1 and e2 and e3
             op.close()
             dist.barrier()
-    os.environ.pop("GLAB_IDX16", None)
+    os.environ.pop("GLAB_IDX16_HALO", None)
     # ---- row-partitioned two-grid V-cycle (config 5) vs the single-GPU cycle: bit-identical
     from glab_b200.dist_vcycle import DistTwoGrid
     V = G.VCycle
