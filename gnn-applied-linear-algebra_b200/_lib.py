@@ -9,7 +9,8 @@ import os
 from ctypes import POINTER, c_char_p, c_double, c_float, c_int, c_int32, c_int64, c_uint32, c_void_p
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libglab_b200.so")
+# GLAB_LIB_PATH: load another build of the same library (kernel experiments); never a different implementation
+LIB_PATH = os.environ.get("GLAB_LIB_PATH") or os.path.join(_HERE, "libglab_b200.so")
 
 
 class GlabError(RuntimeError):

@@ -768,6 +768,16 @@ static int launch_jacobi_ms_impl(const glab_plan* p, const T* vals, const T* dia
   m.ticket = reinterpret_cast<unsigned int*>(p->ms_state + ntiles + 4);
   m.dep = (p->band_local + kThreads - 1) / kThreads + 1;
   if (m.dep > ntiles || 2 * m.dep + 1 > 1024) m.dep = ntiles > 0 ? ntiles : 1;   // no useful band: one check per sweep
+  {
+    // TIMING EXPERIMENTS ONLY: GLAB_MS_NODEP=1 skips the inter-sweep dependency checks (results are then wrong)
+    static const int nodep = [] { const char* e = getenv("GLAB_MS_NODEP"); return e ? atoi(e) : 0; }();
+    if (nodep) m.dep = -1;
+    static const int chunk = [] { const char* e = getenv("GLAB_MS_CHUNK"); int c = e ? atoi(e) : 4; return c < 1 ? 1 : (c > 64 ? 64 : c); }();
+    m.chunk = chunk;
+    // read per launch so that tests can switch it: formally fenced hand-off (slow) instead of the default
+    const char* es = getenv("GLAB_MS_STRICT");
+    m.strict = (es && atoi(es) != 0) ? 1 : 0;
+  }
   m.status = nullptr;
   m.timeout_ns = spin_timeout_ns(0);
   typename std::conditional<HALO, MsHalo, MsNoHalo>::type h;

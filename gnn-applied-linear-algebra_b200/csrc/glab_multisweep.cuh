@@ -19,8 +19,28 @@
 // structure get dep >= ntiles, which degenerates into one full completion check per sweep.
 //
 // Coherence: vectors that change during the launch are never read through the non-coherent path or
-// the async proxy: gathers use ld.global.cg (L2), the row's own x_i is a coalesced ld.global.cg
-// issued together with the gathers.  Only launch-constant data (CSR arrays, diag, b) is TMA-staged.
+// the async proxy.  Only launch-constant data (CSR arrays, diag, b) is TMA-staged; x is gathered with
+// ordinary (L1-cached) global loads and the row's own x_i is a coalesced load issued with the gathers.
+//
+// The hand-off between CTAs (profiles/r02_multisweep.md has the measurements behind each choice):
+//   * A fenced release per consumer warp and tile (red.release.gpu = MEMBAR.ALL.GPU + RED) stalls the
+//     warp ~2 us in this kernel -- more than the tile's own 1.3 us -- and halves the throughput; moving
+//     it to a helper lane of the producer warp stalls the producer instead.  So the default hand-off
+//     relies on the L2 being the GPU's point of coherence instead of on MEMBAR:
+//       writer  every lane stores its row of x_out and reads its own first element back with
+//               ld.global.cg; a load of an address this thread just stored to travels the same
+//               SM -> L2-slice path behind the store, so when it returns the stored bits the store is
+//               in L2.  One tile later (so the read-back latency is never exposed) the warp votes that
+//               all 32 read-backs matched and lane 0 issues a RELAXED reduction on the tile's counter.
+//       reader  the producer warp polls the counters with relaxed loads (L2), then performs one
+//               acquiring load (LDG.STRONG + CCTL.IVALL: invalidates this SM's L1, so no line cached two
+//               sweeps ago, when the same buffer held older values, survives) before it releases the
+//               stage to the consumers through the stage's mbarrier.
+//     A line of x_in is immutable from the moment the check passes until every tile that reads it has
+//     finished the sweep (the write-after-read half of the same dependency).
+//   * GLAB_MS_STRICT=1 selects the formally fenced hand-off (red.release.gpu / fence.acq_rel.gpu) at
+//     run time; tests run both and require identical bits.  GLAB_MS_GATHER_CG=1 at compile time
+//     switches the gathers to ld.global.cg.
 //
 // Multi-GPU (HALO): per sweep the tiles that read the halo tail or are sent to a neighbour come
 // first; their producer acquires the neighbours' arrival counters of that sweep's input buffer; the
@@ -36,7 +56,9 @@ struct MsCtl {
   uint32_t* tile_done;   // [ntiles] consumer-warp completions, monotonically increasing across launches
   uint32_t* epoch;       // tile_done[*] value at the start of this launch (device word)
   unsigned int* ticket;  // exit ticket (the last CTA advances the epoch)
-  int dep;               // dependency half-width in tiles (>= ntiles: every tile)
+  int dep;               // dependency half-width in tiles (>= ntiles: every tile; < 0: unchecked, timing experiments)
+  int chunk;             // dependencies are verified for this many consecutive tiles of a CTA at once
+  int strict;            // 1 = fenced release / acquire on every hand-off (MEMBAR.GPU per warp and tile: ~2x slower)
   uint32_t* status;
   unsigned long long timeout_ns;
 };
@@ -58,6 +80,51 @@ struct MsNoHalo {};
 
 constexpr int kConsumerWarps = kThreads / 32;
 
+#ifndef GLAB_MS_GATHER_CG
+#define GLAB_MS_GATHER_CG 0
+#endif
+constexpr bool kMsGatherCG = GLAB_MS_GATHER_CG != 0;
+
+__device__ __forceinline__ bool mbar_test(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t"
+      "}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ uint32_t ld_relaxed_gpu(const uint32_t* p) {
+  uint32_t v;
+  asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void fence_acq_rel_gpu() { asm volatile("fence.acq_rel.gpu;" ::: "memory"); }
+// One element through L2, never elided or hoisted by the compiler (the read-back of a lane's own store).
+__device__ __forceinline__ float ld_cg_volatile(const float* p) {
+  float v;
+  asm volatile("ld.global.cg.f32 %0, [%1];" : "=f"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ double ld_cg_volatile(const double* p) {
+  double v;
+  asm volatile("ld.global.cg.f64 %0, [%1];" : "=d"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ bool bits_equal(float a, float b) { return __float_as_uint(a) == __float_as_uint(b); }
+__device__ __forceinline__ bool bits_equal(double a, double b) {
+  return __double_as_longlong(a) == __double_as_longlong(b);
+}
+// own-row / coherent variants of load_vec: plain global loads (L1-cached, honour fences)
+template <typename T, int K>
+__device__ __forceinline__ void load_vec_ca(T (&dst)[K], const T* p) {
+  load_vec_rw<T, K>(dst, p);
+}
+
 template <typename T, int K, int U, int IDX, bool HALO>
 __global__ void __launch_bounds__(kPipeThreads, (K * sizeof(T) <= 8) ? 4 : 2)
 k_jacobi_ms(TileArgs<T> a, T* __restrict__ xa, T* __restrict__ xb, const T* __restrict__ diag,
@@ -68,7 +135,7 @@ k_jacobi_ms(TileArgs<T> a, T* __restrict__ xa, T* __restrict__ xb, const T* __re
   uint64_t* empty = full + L.stages;
   unsigned char* stage0 = smem_raw + 128;
   const int tid = threadIdx.x;
-  const int S = L.stages;
+  const int S = L.stages;   // <= 4: the barriers occupy the first 64 of the 128 reserved bytes
   if (tid == 0) {
     for (int s = 0; s < S; ++s) {
       mbar_init(full + s, 1);
@@ -149,7 +216,8 @@ k_jacobi_ms(TileArgs<T> a, T* __restrict__ xa, T* __restrict__ xb, const T* __re
     if (lt < ntiles) extents(lt);
     int s = 0;
     uint32_t phase = 0;
-    int full_ok_sweep = 0;       // wide dependency: sweeps < this value are known to be complete everywhere
+    int full_ok_sweep = 0;       // wide dependency: sweeps <= this value are known to be complete everywhere
+    int checked_lt = 0;          // logical tiles of the current sweep below this index have verified dependencies
     int halo_ok_sweep = -1;      // HALO: the neighbours' pushes for sweeps <= this value have arrived
     uint32_t want_in[2] = {0, 0};
     if constexpr (HALO) {
@@ -165,33 +233,47 @@ k_jacobi_ms(TileArgs<T> a, T* __restrict__ xa, T* __restrict__ xb, const T* __re
       int nlt = lt + ncta, nsw = sw;
       if (nlt >= ntiles) { nlt = cta; nsw = sw + 1; }
       if (nsw < nsweeps) extents(nlt);   // next tile's extents while this stage drains
-      if (sw > 0) {
-        // the tiles this one gathers from / overwrites must have finished the previous sweep
+      if (sw > 0 && m.dep >= 0 && lt >= checked_lt) {
+        // The tiles this one gathers from / overwrites must have finished the previous sweep.  Verified
+        // for this tile and the next m.chunk - 1 tiles of this CTA at once: relaxed polls, all lanes in
+        // parallel; then the acquire -- a full fence in strict mode, else ONE acquiring load, whose
+        // CCTL.IVALL invalidates this SM's L1 before the consumers gather.
         const uint32_t need = base + (uint32_t)(kConsumerWarps * sw);
-        int lo = tile - m.dep, hi = tile + m.dep;
         const bool wide = (m.dep >= ntiles);
-        if (wide || lo < 0) lo = 0;
-        if (wide || hi > ntiles - 1) hi = ntiles - 1;
         if (!(wide && full_ok_sweep >= sw)) {
           SpinGuard guard(m.timeout_ns);
           while (true) {
             bool ok = true;
-            for (int i = lo + lane; i <= hi; i += 32) ok = ok && ((int32_t)(ld_acquire_gpu(m.tile_done + i) - need) >= 0);
+            for (int g = 0; g < m.chunk; ++g) {
+              const int lt2 = lt + g * ncta;
+              if (lt2 >= ntiles) break;
+              bool b2;
+              const int t2 = phys(lt2, b2);
+              int lo = t2 - m.dep, hi = t2 + m.dep;
+              if (wide || lo < 0) lo = 0;
+              if (wide || hi > ntiles - 1) hi = ntiles - 1;
+              for (int i = lo + lane; i <= hi; i += 32) ok = ok && ((int32_t)(ld_relaxed_gpu(m.tile_done + i) - need) >= 0);
+              if (wide) break;
+            }
             if (__all_sync(0xffffffffu, ok)) break;
             __nanosleep(64);
             if (guard.expired()) { flag_timeout(m.status, GLAB_STATUS_TIMEOUT_SWEEP); break; }
           }
+          if (m.strict) fence_acq_rel_gpu();
+          else if (lane == 0) (void)ld_acquire_gpu(m.tile_done + tile);
+          __syncwarp();
           if (wide) full_ok_sweep = sw;
         }
+        checked_lt = lt + m.chunk * ncta;
       }
       if constexpr (HALO) {
         if (bnd && halo_ok_sweep < sw) {
           // neighbours' halo rows of this sweep's input buffer: pushed before the launch (sweep 0: the
-          // producer of the vector; later sweeps: the neighbours' communication CTA of sweep sw - 1)
+          // producer of the vector; later sweeps: the neighbours' communication CTA of sweep sw - 1).
+          // Pushes of the gathered buffer during this launch before sweep sw: buffer A (even sweeps gather
+          // it) is produced by the odd sweeps 1, 3, .. < sw -> sw / 2;  buffer B by the even sweeps
+          // 0, 2, .. < sw -> (sw + 1) / 2
           const MsHaloDir& d = h.dir[sw & 1];
-          // pushes of the gathered buffer during this launch before sweep sw: buffer A (even sweeps gather it)
-          // is produced by the odd sweeps 1, 3, .. < sw  -> sw / 2;  buffer B by the even sweeps 0, 2, .. < sw
-          // -> (sw + 1) / 2
           const uint32_t target = want_in[sw & 1] + (uint32_t)((sw & 1) ? (sw + 1) / 2 : sw / 2);
           if (lane < d.n_wait) {
             SpinGuard guard(m.timeout_ns);
@@ -232,6 +314,7 @@ k_jacobi_ms(TileArgs<T> a, T* __restrict__ xa, T* __restrict__ xb, const T* __re
       __syncwarp();
       if (++s == S) { s = 0; phase ^= 1u; }
       lt = nlt;
+      if (nsw != sw) checked_lt = 0;
       sw = nsw;
     }
   } else {
@@ -239,9 +322,25 @@ k_jacobi_ms(TileArgs<T> a, T* __restrict__ xa, T* __restrict__ xb, const T* __re
     const T w = __ldg(omega);
     int s = 0;
     uint32_t phase = 0;
+    // Publication of a finished tile, deferred by one tile: (tile, first stored element, its read-back)
+    int pending = -1;
+    T sent = T(0), echo = T(0);
+    auto publish = [&]() {
+      // Every lane's read-back of its own store has returned the stored bits, i.e. the warp's rows of
+      // x_out are in L2 (the GPU's point of coherence): only then is the count incremented.
+      const bool ok = bits_equal(sent, echo);
+      const unsigned int all = __ballot_sync(0xffffffffu, ok);
+      if ((tid & 31) == 0) {
+        if (m.strict)
+          asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(m.tile_done + pending), "r"(all) : "memory");
+        else
+          asm volatile("red.relaxed.gpu.global.add.u32 [%0], 1;" ::"l"(m.tile_done + pending), "r"(all) : "memory");
+      }
+      pending = -1;
+    };
     for (int sw = 0; sw < nsweeps; ++sw) {
-      const T* __restrict__ xin = (sw & 1) ? xb : xa;
-      T* __restrict__ xout = (sw & 1) ? xa : xb;
+      const T* xin = (sw & 1) ? xb : xa;
+      T* xout = (sw & 1) ? xa : xb;
       for (int lt = cta; lt < ntiles; lt += ncta) {
         bool bnd;
         const int tile = phys(lt, bnd);
@@ -251,11 +350,17 @@ k_jacobi_ms(TileArgs<T> a, T* __restrict__ xa, T* __restrict__ xb, const T* __re
         unsigned char* sb = stage0 + (size_t)s * L.stage_bytes;
         const int32_t* srow = reinterpret_cast<const int32_t*>(sb + L.off_row);
         bool t16 = (IDX == 1);
+        // never block while holding an unpublished completion (another CTA may be waiting for it)
+        if (pending >= 0 && !mbar_test(full + s, phase)) publish();
         mbar_wait(full + s, phase);
         if constexpr (IDX == 2) t16 = *reinterpret_cast<const volatile int*>(sb + L.off_row + kTileFlagOff) != 0;
+        T o[K];
+#pragma unroll
+        for (int c = 0; c < K; ++c) o[c] = T(0);
         if (r < r1) {
           T xx[K];
-          load_vec_cg<T, K>(xx, xin + (size_t)r * K);   // in flight together with the gathers
+          if constexpr (kMsGatherCG) load_vec_cg<T, K>(xx, xin + (size_t)r * K);   // in flight together with the gathers
+          else load_vec_ca<T, K>(xx, xin + (size_t)r * K);
           const int e0 = srow[0];
           const int rs = srow[tid], re = srow[tid + 1];
           const unsigned char* cbuf = sb + L.off_col;
@@ -263,15 +368,22 @@ k_jacobi_ms(TileArgs<T> a, T* __restrict__ xa, T* __restrict__ xb, const T* __re
           T acc[K];
 #pragma unroll
           for (int c = 0; c < K; ++c) acc[c] = T(0);
+          // rows that read the halo tail (written by other GPUs): always through L2
           if (IDX != 0 && t16) {
-            if constexpr (IDX != 0)
-              row_sum<T, K, U, true, true>(acc, cbuf, lead_elems(a.coldelta + e0, 2) - e0, sval, rs, re, r, xin);
+            if constexpr (IDX != 0) {
+              const int cofs = lead_elems(a.coldelta + e0, 2) - e0;
+              if (HALO && bnd) row_sum_coherent<T, K, true>(acc, cbuf, cofs, sval, rs, re, r, xin);
+              else row_sum<T, K, U, true, kMsGatherCG ? 1 : 2>(acc, cbuf, cofs, sval, rs, re, r, xin);
+            }
           } else {
-            if constexpr (IDX != 1)
-              row_sum<T, K, U, false, true>(acc, cbuf, lead_elems(a.colidx + e0, 4) - e0, sval, rs, re, r, xin);
+            if constexpr (IDX != 1) {
+              const int cofs = lead_elems(a.colidx + e0, 4) - e0;
+              if (HALO && bnd) row_sum_coherent<T, K, false>(acc, cbuf, cofs, sval, rs, re, r, xin);
+              else row_sum<T, K, U, false, kMsGatherCG ? 1 : 2>(acc, cbuf, cofs, sval, rs, re, r, xin);
+            }
           }
           const T d = reinterpret_cast<const T*>(sb + L.off_stream[0])[tid];
-          T bb[K], o[K];
+          T bb[K];
           const T* sbp = reinterpret_cast<const T*>(sb + L.off_stream[1]) + (size_t)tid * K;
           constexpr int bytes = K * (int)sizeof(T);
           if constexpr (bytes >= 16) {
@@ -289,17 +401,21 @@ k_jacobi_ms(TileArgs<T> a, T* __restrict__ xa, T* __restrict__ xb, const T* __re
           }
 #pragma unroll
           for (int c = 0; c < K; ++c) o[c] = xx[c] + (w * (bb[c] - acc[c])) / d;   // JacobiGNN.py:119
+        }
+        if (pending >= 0) publish();   // the previous tile's read-backs returned long ago
+        sent = o[0];
+        echo = o[0];
+        if (r < r1) {
           store_vec<T, K>(xout + (size_t)r * K, o);
+          echo = ld_cg_volatile(xout + (size_t)r * K);   // L2 read-back of this lane's own store (same 32-byte sector)
         }
         __syncwarp();
-        if ((tid & 31) == 0) {
-          mbar_arrive(empty + s);
-          // release: this warp's rows of x_out are visible before the count is
-          asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(m.tile_done + tile) : "memory");
-        }
+        if ((tid & 31) == 0) mbar_arrive(empty + s);
+        pending = tile;
         if (++s == S) { s = 0; phase ^= 1u; }
         if constexpr (HALO) {
           if (bnd && has_comm) {  // tell the communication CTA that this boundary tile of this sweep is stored
+            publish();
             asm volatile("bar.sync 1, 256;" ::: "memory");
             if (tid == 0) {
               __threadfence();
@@ -309,6 +425,7 @@ k_jacobi_ms(TileArgs<T> a, T* __restrict__ xa, T* __restrict__ xb, const T* __re
         }
       }
     }
+    if (pending >= 0) publish();
   }
   // ---- exit: the last CTA advances the epoch (and the push counters) for the next launch
   __syncthreads();

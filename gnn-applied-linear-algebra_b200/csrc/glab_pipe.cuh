@@ -176,10 +176,11 @@ __device__ __forceinline__ void load_vec_cg(T (&dst)[K], const T* p) {
 
 // Row sum of one CSR row of a staged tile: acc[c] = sum_j v_j * x[col_j, c], added one product at a
 // time in slot order (the accumulation order of scatter_add_).  W16: the tile's columns are 2-byte
-// offsets from the row (else 4-byte absolute indices).  CG: gather through L2 (values written by other
-// SMs / GPUs while this kernel runs), else through the read-only path.  Rows of exactly U entries
+// offsets from the row (else 4-byte absolute indices).  CG: 0 = gather through the read-only path
+// (vectors no kernel writes while this one runs), 1 = through L2 only (ld.global.cg), 2 = ordinary
+// coherent loads (L1-cached, honour fences: vectors other CTAs write during the launch).  Rows of exactly U entries
 // take an unpredicated straight-line path with U gathers in flight.
-template <typename T, int K, int U, bool W16, bool CG>
+template <typename T, int K, int U, bool W16, int CG>
 __device__ __forceinline__ void row_sum(T (&acc)[K], const unsigned char* __restrict__ cbuf, int cofs,
                                         const T* __restrict__ sval, int rs, int re, int r,
                                         const T* __restrict__ x) {
@@ -188,7 +189,8 @@ __device__ __forceinline__ void row_sum(T (&acc)[K], const unsigned char* __rest
     else return reinterpret_cast<const int32_t*>(cbuf)[j + cofs];
   };
   auto gather = [&](T (&d)[K], int col) {
-    if constexpr (CG) load_vec_cg<T, K>(d, x + (size_t)col * K);
+    if constexpr (CG == 1) load_vec_cg<T, K>(d, x + (size_t)col * K);
+    else if constexpr (CG == 2) load_vec_rw<T, K>(d, x + (size_t)col * K);
     else load_vec<T, K>(d, x + (size_t)col * K);
   };
   if (re - rs == U) {
@@ -455,13 +457,13 @@ k_row_pipe(TileArgs<T> a, const T* __restrict__ x, Epi epi, int ntiles, PipeLayo
             const int cofs = lead_elems(a.coldelta + e0, 2) - e0;
             // rows that read the halo tail gather through L2 (the tail was written by peers)
             if (HALO && bnd) row_sum_coherent<T, K, true>(acc, cbuf, cofs, sval, rs, re, r, x);
-            else row_sum<T, K, U, true, false>(acc, cbuf, cofs, sval, rs, re, r, x);
+            else row_sum<T, K, U, true, 0>(acc, cbuf, cofs, sval, rs, re, r, x);
           }
         } else {
           if constexpr (IDX != 1) {
             const int cofs = lead_elems(a.colidx + e0, 4) - e0;
             if (HALO && bnd) row_sum_coherent<T, K, false>(acc, cbuf, cofs, sval, rs, re, r, x);
-            else row_sum<T, K, U, false, false>(acc, cbuf, cofs, sval, rs, re, r, x);
+            else row_sum<T, K, U, false, 0>(acc, cbuf, cofs, sval, rs, re, r, x);
           }
         }
         const T* sp[kMaxStreams] = {nullptr, nullptr, nullptr};

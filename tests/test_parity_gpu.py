@@ -878,15 +878,19 @@ def _ms_operator(G, dev, dt, case):
     return ei.contiguous(), ev.to(dt).contiguous()
 
 
+@pytest.mark.parametrize("strict", [False, True])
 @pytest.mark.parametrize("dt", [torch.float32, torch.float64])
 @pytest.mark.parametrize("case", ["lap5", "heat9", "periodic", "random", "tiny", "lap5_big"])
-def test_multi_sweep_jacobi_bit_exact(G, dev, dt, case):
+def test_multi_sweep_jacobi_bit_exact(G, dev, dt, case, strict, monkeypatch):
     """glab_jacobi_sweeps_* (all sweeps in one persistent launch, per-tile completion counters
     instead of a grid barrier) == the same number of single-sweep launches, bit for bit: banded
     operators (dependency band of a few tiles), a periodic and a random one (full completion check
     per sweep), one tile only, and an operator with many tiles per CTA; k = 1 and k = 8; repeated
-    launches on the same plan (the completion counters keep counting across launches)."""
+    launches on the same plan (the completion counters keep counting across launches).  Both hand-off
+    protocols between CTAs: the default one (L2 read-back + relaxed counter + acquiring load) and the
+    formally fenced one (GLAB_MS_STRICT=1: MEMBAR-based release / acquire fences)."""
     rt = G.runtime
+    monkeypatch.setenv("GLAB_MS_STRICT", "1" if strict else "0")
     ei, ev = _ms_operator(G, dev, dt, case)
     n = int(ei[0].max().item()) + 1
     plan = G.Plan.from_coo(ei, n)
