@@ -35,9 +35,10 @@ class SingleGpuSmoother:
                            "plan_identity_perm": self.plan.identity, "max_row_nnz": self.plan.max_row_nnz,
                            "index_bytes_streamed": self.plan.index_bytes}
         self.index_bytes = self.plan.index_bytes
-        torch.manual_seed(24601)
-        self.b_host = torch.rand(n, 1).pin_memory()
-        self.x_host = torch.rand(n, 1).pin_memory()
+        from bench_extra import hashed_uniform
+        self.N = N
+        self.b_host = hashed_uniform(0, n, 1, "cpu").pin_memory()
+        self.x_host = hashed_uniform(0, n, 2, "cpu").pin_memory()
         self.va_host = torch.cat([-4 * torch.ones(n, 1), self.b_host, self.x_host], 1).pin_memory()
         self.out_host = torch.empty(n, 1).pin_memory()
         self.diag = torch.full((n,), -4.0, device=dev)
@@ -77,6 +78,38 @@ class SingleGpuSmoother:
             p, p2 = p2, p
         self.result = dst
         return ev
+
+    def parity(self):
+        """The layer pass at full size against an independent fp64 formulation: 10 Jacobi sweeps and the
+        degree-4 Chebyshev recurrence applied with shifted grid slices (no CSR code involved)."""
+        from bench_extra import grid_stencil_5pt, relerr
+        N, n, dev = self.N, self.n, self.dev
+        va = self.va_host.to(dev)
+        x1 = self.jac(self.N_JACOBI, va, self.ei, self.ea2, self.gw)
+        v, e, g = self.cheb(self.rt.pack([va[:, 1:2].contiguous(), x1]), self.ei, self.ev, self.gc)
+        del e
+        b = va[:, 1].double().view(N, N, 1)
+        x = va[:, 2].double().view(N, N, 1)
+        for _ in range(self.N_JACOBI):
+            x = x + (self.OMEGA * (b - grid_stencil_5pt(x))) / -4.0
+        e_jac = relerr(x1, x.view(n, 1))
+        c_, d_ = self.CHEB_C, self.CHEB_D
+        r = b - grid_stencil_5pt(x)
+        alpha = 1.0 / d_
+        p = r.clone()
+        x = x + alpha * p
+        for it in range(2, self.CHEB_DEG + 1):
+            r = r - alpha * grid_stencil_5pt(p)
+            beta = 0.5 * (c_ * alpha) ** 2 if it == 2 else ((c_ * alpha) / 2) ** 2
+            alpha = 1.0 / (d_ - beta / alpha)
+            p = r + beta * p
+            x = x + alpha * p
+        e_x = relerr(v[:, 1:2], x.view(n, 1))
+        e_r = relerr(v[:, 2:3], r.view(n, 1))
+        return {"ok": bool(max(e_jac, e_x) <= 1e-5), "tolerance": 1e-5, "jacobi10_rel_err": e_jac,
+                "chebyshev4_x_rel_err": e_x, "chebyshev4_r_rel_err_informative": e_r, "rows_checked": n,
+                "against": "fp64 shifted-slice stencil recompute of the same 10 Jacobi sweeps + degree-4 Chebyshev "
+                           "recurrence on the [N, N] grid (independent of every CSR code path)"}
 
     def _e2e_setup(self):
         """Double-buffered staging so that consecutive steps overlap their PCIe copies with compute:
@@ -118,27 +151,37 @@ class SingleGpuSmoother:
 
 class PartitionedSmoother:
     """The same smoothing pass on an operator row-block partitioned over `world` GPUs (strong
-    scaling): each rank builds only its slab of the stencil, halo rows travel over NVLink peer
-    memory (glab_halo_push / glab_halo_wait), and the whole pass is replayed as one CUDA graph."""
+    scaling): each rank builds only its slab of the stencil and wraps it in a dist.PartitionedGraph,
+    the handle the drop-in layers take in place of `edgeij_pair`.  Halo rows travel over NVLink peer
+    memory from inside the fused kernels.
+      step_kernels  the pass on resident vectors through the partitioned operator, replayed as CUDA graphs
+      step_e2e      JacobiGNN.forward + ChebyRelaxGNN.forward on the PartitionedGraph: per step this rank's
+                    slab of vertex_attr = [A_ii, b, x] is uploaded from pinned host memory (the same three
+                    vectors as at N = 1) and its slab of the result is downloaded"""
 
     N_JACOBI, CHEB_DEG, OMEGA, CHEB_C, CHEB_D = 10, 4, 0.7, -3.4, -4.0
 
     def __init__(self, G, N, dev, rank, world, engine="peer", use_graph=True):
         import torch.distributed as dist
         from glab_b200 import dist as gd
-        self.G, self.rt, self.dev, self.rank, self.world = G, G.runtime, dev, rank, world
+        self.G, self.rt, self.dev, self.rank, self.world, self.N = G, G.runtime, dev, rank, world, N
         n = N * N
+        self.n = n
         t0 = time.perf_counter()
         self.part = gd.RowPartition(n, world, align=256)
         r0, r1 = self.part.bounds(rank)
+        self.r0, self.r1 = r0, r1
         ei, ev = G.generators.laplacian_2d(N, torch.float64, dev, rows=(r0, r1))
-        ev = ev.float().contiguous()
-        self.halo = gd.HaloPlan.build(self.part, rank, ei[1])
-        lei = torch.stack([ei[0] - r0, self.halo.local_columns(ei[1])]).contiguous()
+        self.ev = ev.float().contiguous()
+        self.pg = gd.PartitionedGraph(ei, n, self.part, rank, world, engine=engine)
+        self.halo = self.pg.halo
         del ei
         torch.cuda.synchronize()
         t1 = time.perf_counter()
-        self.op = gd.DistOperator(lei, ev, self.halo, k=1, engine=engine)
+        # operator-side inputs of the layer API (step-invariant); one edge_attr tensor for both layers so
+        # that they share one partitioned operator (its plan, values and peer-mapped vectors)
+        self.ea2 = torch.cat([self.ev, torch.zeros_like(self.ev)], 1)
+        self.op = self.pg.operator(self.ea2, 1, torch.float32)
         torch.cuda.synchronize()
         t2 = time.perf_counter()
         nl = self.halo.n_local
@@ -150,29 +193,32 @@ class PartitionedSmoother:
                            "rows_local": nl, "halo_rows": self.halo.n_halo, "interior": [self.op.lo, self.op.hi],
                            "cuda_graph": bool(use_graph),
                            "index16_tiles": [self.op.plan.index16_tiles, self.op.plan.tiles]}
-        # effective bytes of column index streamed per nonzero: the fused halo kernels (engine "peer") stay on
-        # int32 unless GLAB_IDX16=3; the other engines launch the plain kernels, which stream 2 bytes in the
-        # tiles flagged for 16-bit indices
-        halo16 = os.environ.get("GLAB_IDX16", "2") == "3"
+        # effective bytes of column index streamed per nonzero: 2 in the tiles flagged for 16-bit indices
+        halo16 = os.environ.get("GLAB_IDX16_HALO", "1") != "0"
         frac16 = self.op.plan.index16_tiles / max(self.op.plan.tiles, 1)
         self.index_bytes = 4 - 2.0 * frac16 if (halo16 or engine != "peer") else 4.0
         self.setup_info["halo_kernels_use_index16"] = bool(halo16 and engine == "peer")
-        g = torch.Generator().manual_seed(24601 + rank)
-        self.b_host = torch.rand(nl, 1, generator=g).pin_memory()
-        self.x_host = torch.rand(nl, 1, generator=g).pin_memory()
-        self.out_host = torch.empty(nl, 1).pin_memory()
+        self.setup_info["jacobi_sweeps_per_launch"] = "multi-sweep kernel" if getattr(self.op, "multi_sweep", False) \
+            and engine == "peer" else "one launch per sweep"
+        from bench_extra import hashed_uniform
+        self.b_host = hashed_uniform(r0, r1, 1, "cpu").pin_memory()
+        self.x_host = hashed_uniform(r0, r1, 2, "cpu").pin_memory()
+        self.va_host = torch.cat([-4 * torch.ones(nl, 1), self.b_host, self.x_host], 1).pin_memory()
         self.diag = torch.full((nl,), -4.0, device=dev)
         self.b = self.b_host.to(dev).contiguous()
-        self.x_stage = torch.empty(nl, 1, device=dev)
         self.w = torch.tensor([self.OMEGA], device=dev)
         rows, _ = G.ChebyGNN._recurrence(self.CHEB_DEG, torch.tensor([self.CHEB_C, self.CHEB_D]))
         self.table = torch.stack([torch.stack(r) for r in rows]).to(dev).contiguous()
         self.x = torch.empty(nl, 1, device=dev)
         self.r = torch.empty(nl, 1, device=dev)
+        self.gw = torch.tensor(self.OMEGA).reshape(-1)
+        self.gc = torch.tensor([self.CHEB_C, self.CHEB_D])
+        self.jac = G.JacobiGNN.JacobiGNN()
+        self.cheb = G.ChebyGNN.ChebyRelaxGNN(self.CHEB_DEG)
         self.op.load("v0", self.x_host.to(dev))
         torch.cuda.synchronize()
         dist.barrier()
-        self.h2d_bytes = 2 * nl * 4
+        self.h2d_bytes = self.va_host.numel() * 4
         self.d2h_bytes = nl * 4
         self.graph = None
         self.jac_graph = None
@@ -229,11 +275,16 @@ class PartitionedSmoother:
             self.op.chebyshev(self.CHEB_DEG, self.b, self.table, cur, self.x, self.r)
         return ev
 
+    def layer_pass(self, va):
+        """The drop-in layer calls on this rank's slab (va = [A_ii, b, x] on the device)."""
+        x1 = self.jac(self.N_JACOBI, va, self.pg, self.ea2, self.gw)
+        v, e, g = self.cheb(self.rt.pack([va[:, 1:2].contiguous(), x1]), self.pg, self.ea2, self.gc)
+        return v[:, 1:2]
+
     def _e2e_setup(self):
         dev, nl = self.dev, self.n_local
         self.s_in, self.s_out = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
-        self.b_stage = [torch.empty(nl, 1, device=dev) for _ in range(2)]
-        self.x_stage2 = [torch.empty(nl, 1, device=dev) for _ in range(2)]
+        self.va_dev = [torch.empty(nl, 3, device=dev) for _ in range(2)]
         self.res_dev = [torch.empty(nl, 1, device=dev) for _ in range(2)]
         self.out_hosts = [torch.empty(nl, 1).pin_memory() for _ in range(2)]
         self.ev_in = [torch.cuda.Event() for _ in range(2)]
@@ -242,9 +293,9 @@ class PartitionedSmoother:
         self.e2e_i = 0
 
     def step_e2e(self):
-        """Per step: this rank's slab of b and x0 is uploaded from pinned host memory, the captured
-        smoothing pass runs, the slab of the result is downloaded; double-buffered staging lets the
-        copies of neighbouring steps overlap the compute."""
+        """Per step: this rank's slab of vertex_attr is uploaded from pinned host memory, the layers
+        run on the PartitionedGraph, the slab of the result is downloaded; double-buffered staging
+        lets the copies of neighbouring steps overlap the compute."""
         if not hasattr(self, "s_in"):
             self._e2e_setup()
         i = self.e2e_i % 2
@@ -252,21 +303,44 @@ class PartitionedSmoother:
         cur = torch.cuda.current_stream(self.dev)
         with torch.cuda.stream(self.s_in):
             self.s_in.wait_event(self.ev_comp[i])
-            self.b_stage[i].copy_(self.b_host, non_blocking=True)
-            self.x_stage2[i].copy_(self.x_host, non_blocking=True)
+            self.va_dev[i].copy_(self.va_host, non_blocking=True)
             self.ev_in[i].record(self.s_in)
         cur.wait_event(self.ev_in[i])
         cur.wait_event(self.ev_out[i])
-        self.b.copy_(self.b_stage[i])
-        self.op.vec["v0"][:self.n_local].copy_(self.x_stage2[i])
-        self.step_kernels()
-        self.res_dev[i].copy_(self.x)
+        self.res_dev[i].copy_(self.layer_pass(self.va_dev[i]))
         self.ev_comp[i].record(cur)
         with torch.cuda.stream(self.s_out):
             self.s_out.wait_event(self.ev_comp[i])
             self.out_hosts[i].copy_(self.res_dev[i], non_blocking=True)
             self.ev_out[i].record(self.s_out)
         return self.out_hosts[i]
+
+    def parity(self):
+        """Collective.  The partitioned layer pass on the deterministic global inputs, gathered on rank 0
+        and compared BIT FOR BIT with the same layer calls on the unpartitioned operator on one GPU."""
+        import torch.distributed as dist
+        G, dev = self.G, self.dev
+        va = self.va_host.to(dev)
+        mine = self.layer_pass(va).contiguous()
+        self.op.check()
+        full = [torch.empty(self.part.bounds(q)[1] - self.part.bounds(q)[0], 1, device=dev)
+                for q in range(self.world)] if self.rank == 0 else None
+        dist.gather(mine, full, dst=0)
+        if self.rank != 0:
+            return None
+        from bench_extra import hashed_uniform
+        n, N = self.n, self.N
+        ei, ev = G.UtilsGNN.laplacianfun_torch(N, device=dev)
+        ev = ev.float().contiguous()
+        b, x = hashed_uniform(0, n, 1, dev), hashed_uniform(0, n, 2, dev)
+        vg = torch.cat([-4 * torch.ones(n, 1, device=dev), b, x], 1)
+        x1 = self.jac(self.N_JACOBI, vg, ei, torch.cat([ev, torch.zeros_like(ev)], 1), self.gw)
+        ref = self.cheb(torch.cat([b, x1], 1), ei, ev, self.gc)[0][:, 1:2]
+        got = torch.cat(full)
+        ok = bool(torch.equal(got, ref))
+        return {"ok": ok, "bit_exact": True, "max_abs": float((got - ref).abs().max().item()), "rows_checked": n,
+                "against": "the same JacobiGNN.forward(10) + ChebyRelaxGNN(4).forward calls on the UNPARTITIONED "
+                           "operator on one GPU (rank 0); every row of the gathered result, bit for bit"}
 
     def close(self):
         self.op.close()

@@ -35,9 +35,32 @@ class ChebyRelaxGNN(torch.nn.Module):
         super().__init__()
         self.deg = deg
 
+    def _forward_partitioned(self, vertex_attr, pg, edge_attr, g):
+        """This rank's row block of a row-partitioned operator (edgeij_pair = dist.PartitionedGraph)."""
+        io = Placement(vertex_attr, edge_attr)
+        dt = float_dtype(vertex_attr, edge_attr)
+        n, F = vertex_attr.shape
+        k = F // 2
+        op = pg.operator(edge_attr, k, dt)
+        va = io.up(vertex_attr, dt)
+        b, _ = rt.unpack(va, [(0, k), (k, k)], outs=[None, op.local("v0")])
+        op.publish("v0")
+        rows, g_out = _recurrence(self.deg, g)
+        table = torch.stack([torch.stack(r) for r in rows]).to(device=io.device, dtype=dt,
+                                                               non_blocking=True).contiguous()
+        x, r, pname = op.chebyshev(self.deg, b, table, "v0")
+        if op.halo.part.world > 1:
+            op.acquire(op.last_gathered)      # the message column reads that vector's halo tail
+        e_out = rt.with_messages(op.plan, op.vals, op.vec[op.last_gathered])
+        v_out = rt.pack([b, x, r, op.local(pname)])
+        return io.down(v_out), io.down(e_out), g_out
+
     def forward(self, vertex_attr, edgeij_pair, edge_attr, g, batch=None):
         if self.deg <= 0:
             return vertex_attr, edge_attr, g
+        from .dist import is_partitioned
+        if is_partitioned(edgeij_pair):
+            return self._forward_partitioned(vertex_attr, edgeij_pair, edge_attr, g)
         io = Placement(vertex_attr, edgeij_pair, edge_attr)
         dt = float_dtype(vertex_attr, edge_attr)
         n, F = vertex_attr.shape

@@ -10,6 +10,16 @@ class GNNResidual(torch.nn.Module):
     -> r [n,1].  Extension: vertex_attr = [b (k cols) | x (k cols)] gives r [n,k]."""
 
     def forward(self, vertex_attr, edgeij_pair, edge_attr, batch=None):
+        from .dist import is_partitioned
+        if is_partitioned(edgeij_pair):      # this rank's row block of a row-partitioned operator
+            io = Placement(vertex_attr, edge_attr)
+            dt = float_dtype(vertex_attr, edge_attr)
+            k = vertex_attr.shape[1] // 2
+            op = edgeij_pair.operator(edge_attr, k, dt)
+            va = io.up(vertex_attr, dt)
+            b, _ = rt.unpack(va, [(0, k), (k, k)], outs=[None, op.local("v0")])
+            op.publish("v0")
+            return io.down(op.spmv("v0", torch.empty_like(b), b=b))
         io = Placement(vertex_attr, edgeij_pair, edge_attr)
         dt = float_dtype(vertex_attr, edge_attr)
         n, F = vertex_attr.shape

@@ -32,7 +32,26 @@ class JacobiGNN(torch.nn.Module):
         v_out = rt.pack([diag, b, x_new])
         return io.down(v_out), io.down(e_out), g
 
+    def _forward_partitioned(self, n_iters, vertex_attr, pg, edge_attr, g):
+        """This rank's row block of a row-partitioned operator (edgeij_pair = dist.PartitionedGraph):
+        the same sweeps, halo rows pushed from inside the kernels."""
+        io = Placement(vertex_attr, edge_attr)
+        dt = float_dtype(vertex_attr, edge_attr)
+        n, F = vertex_attr.shape
+        k = (F - 1) // 2
+        op = pg.operator(edge_attr, k, dt)
+        va = io.up(vertex_attr, dt)
+        x0 = op.local("v0")
+        diag, b, _ = rt.unpack(va, [(0, 1), (1, k), (1 + k, k)], outs=[None, None, x0])
+        w = rt.scalar(g[0] if isinstance(g, torch.Tensor) else g, io.device, dt)
+        op.publish("v0")
+        cur = op.jacobi(n_iters, diag.view(-1), b, w, "v0")
+        return io.down(op.local(cur).clone())
+
     def forward(self, n_iters, vertex_attr, edgeij_pair, edge_attr, g, batch=None):
+        from .dist import is_partitioned
+        if is_partitioned(edgeij_pair):
+            return self._forward_partitioned(n_iters, vertex_attr, edgeij_pair, edge_attr, g)
         io, dt, plan, vals, va, diag, b, x, w = self._setup(vertex_attr, edgeij_pair, edge_attr, g)
         # all sweeps in one launch of the multi-sweep kernel (x is a private copy from unpack)
         x = rt.jacobi_sweeps(plan, vals, diag, b, x, torch.empty_like(x), w, n_iters)

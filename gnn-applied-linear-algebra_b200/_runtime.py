@@ -459,14 +459,24 @@ def pack(parts):
     return out
 
 
-def unpack(src, spans):
+def unpack(src, spans, outs=None):
     """Dense copies of column blocks of an interleaved [n, F] device tensor: spans = [(offset,
-    width), ...] -> list of [n, width] tensors (one coalesced kernel instead of strided copies)."""
+    width), ...] -> list of [n, width] tensors (one coalesced kernel instead of strided copies).
+    outs: optional list with a preallocated dense [n, width] destination (or None) per span."""
     n, ld = src.shape
+    given = list(outs) if outs is not None else [None] * len(spans)
     if len(spans) > 8 or ld > 64:
-        return [dense(src[:, o:o + w]) for o, w in spans]
+        res = []
+        for (o, w), t in zip(spans, given):
+            if t is None:
+                res.append(dense(src[:, o:o + w]))
+            else:
+                t.view(n, w).copy_(src[:, o:o + w])
+                res.append(t)
+        return res
     src = src.contiguous()
-    outs = [torch.empty((n, w), dtype=src.dtype, device=src.device) for _, w in spans]
+    outs = [torch.empty((n, w), dtype=src.dtype, device=src.device) if t is None else t.view(n, w)
+            for (_, w), t in zip(spans, given)]
     ptrs = (ctypes.c_void_p * len(spans))(*[t.data_ptr() for t in outs])
     w = (ctypes.c_int32 * len(spans))(*[w_ for _, w_ in spans])
     o = (ctypes.c_int32 * len(spans))(*[o_ for o_, _ in spans])

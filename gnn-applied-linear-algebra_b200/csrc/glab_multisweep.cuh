@@ -115,10 +115,12 @@ __device__ __forceinline__ double ld_cg_volatile(const double* p) {
   asm volatile("ld.global.cg.f64 %0, [%1];" : "=d"(v) : "l"(p) : "memory");
   return v;
 }
-__device__ __forceinline__ bool bits_equal(float a, float b) { return __float_as_uint(a) == __float_as_uint(b); }
-__device__ __forceinline__ bool bits_equal(double a, double b) {
-  return __double_as_longlong(a) == __double_as_longlong(b);
-}
+// A comparison whose only purpose is to make an instruction depend on a loaded register (the
+// hardware scoreboard then holds the warp until the load has returned).  The pattern is a signalling
+// NaN payload no computation here produces; the outcome is not used for control flow.
+__device__ __forceinline__ bool is_poison(float a) { return __float_as_uint(a) == 0x7fa5a5a5u; }
+__device__ __forceinline__ bool is_poison(double a) { return __double_as_longlong(a) == 0x7ff5a5a5a5a5a5a5ll; }
+constexpr int kMsDefer = 3;   // tiles between a warp's stores and the publication of their completion
 // own-row / coherent variants of load_vec: plain global loads (L1-cached, honour fences)
 template <typename T, int K>
 __device__ __forceinline__ void load_vec_ca(T (&dst)[K], const T* p) {
@@ -204,16 +206,22 @@ k_jacobi_ms(TileArgs<T> a, T* __restrict__ xa, T* __restrict__ xb, const T* __re
     // -------------------------------------------------------------------- producer warp
     const int lane = tid - kThreads;
     int sw = 0, lt = cta;
-    int e0n = 0, e1n = 0;
-    bool t16n = (IDX == 1), bnd = false;
-    auto extents = [&](int t) {
-      bool b2;
-      const int r0 = phys(t, b2) * kThreads;
-      e0n = __ldg(a.rowptr + r0);
-      e1n = __ldg(a.rowptr + min(r0 + kThreads, a.row_end));
-      if constexpr (IDX == 2) t16n = __ldg(a.tile16 + r0 / kThreads) != 0;
+    bool bnd = false;
+    // CSR extents prefetched 32 tiles ahead (see k_row_pipe): lane l holds those of this CTA's
+    // (32 j + l)-th tile of the launch; the sequence simply continues across sweeps.
+    const int per_sweep = (cta < ntiles) ? (ntiles - cta + ncta - 1) / ncta : 0;   // tiles of this CTA per sweep
+    int my_e0 = 0, my_e1 = 0, my_t16 = (IDX == 1) ? 1 : 0;
+    auto fetch = [&](int seq) {
+      if (per_sweep > 0 && seq < per_sweep * nsweeps) {
+        bool b2;
+        const int r0 = phys(cta + (seq % per_sweep) * ncta, b2) * kThreads;
+        my_e0 = __ldg(a.rowptr + r0);
+        my_e1 = __ldg(a.rowptr + min(r0 + kThreads, a.row_end));
+        if constexpr (IDX == 2) my_t16 = __ldg(a.tile16 + r0 / kThreads) != 0;
+      }
     };
-    if (lt < ntiles) extents(lt);
+    fetch(lane);
+    int seq = 0;
     int s = 0;
     uint32_t phase = 0;
     int full_ok_sweep = 0;       // wide dependency: sweeps <= this value are known to be complete everywhere
@@ -228,11 +236,14 @@ k_jacobi_ms(TileArgs<T> a, T* __restrict__ xa, T* __restrict__ xb, const T* __re
       const int tile = phys(lt, bnd);
       const int r0 = tile * kThreads;
       const int r1 = min(r0 + kThreads, a.row_end);
-      const int e0 = e0n, e1 = e1n;
-      const bool t16 = t16n;
+      const int srcl = seq & 31;
+      const int e0 = __shfl_sync(0xffffffffu, my_e0, srcl);
+      const int e1 = __shfl_sync(0xffffffffu, my_e1, srcl);
+      const bool t16 = __shfl_sync(0xffffffffu, my_t16, srcl) != 0;
+      if (lane == srcl) fetch(seq + 32);
+      ++seq;
       int nlt = lt + ncta, nsw = sw;
       if (nlt >= ntiles) { nlt = cta; nsw = sw + 1; }
-      if (nsw < nsweeps) extents(nlt);   // next tile's extents while this stage drains
       if (sw > 0 && m.dep >= 0 && lt >= checked_lt) {
         // The tiles this one gathers from / overwrites must have finished the previous sweep.  Verified
         // for this tile and the next m.chunk - 1 tiles of this CTA at once: relaxed polls, all lanes in
@@ -322,21 +333,37 @@ k_jacobi_ms(TileArgs<T> a, T* __restrict__ xa, T* __restrict__ xb, const T* __re
     const T w = __ldg(omega);
     int s = 0;
     uint32_t phase = 0;
-    // Publication of a finished tile, deferred by one tile: (tile, first stored element, its read-back)
-    int pending = -1;
-    T sent = T(0), echo = T(0);
-    auto publish = [&]() {
-      // Every lane's read-back of its own store has returned the stored bits, i.e. the warp's rows of
-      // x_out are in L2 (the GPU's point of coherence): only then is the count incremented.
-      const bool ok = bits_equal(sent, echo);
-      const unsigned int all = __ballot_sync(0xffffffffu, ok);
-      if ((tid & 31) == 0) {
-        if (m.strict)
-          asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(m.tile_done + pending), "r"(all) : "memory");
-        else
-          asm volatile("red.relaxed.gpu.global.add.u32 [%0], 1;" ::"l"(m.tile_done + pending), "r"(all) : "memory");
+    // Publication of a finished tile is deferred by kMsDefer tiles: a write takes ~2 us to be acknowledged
+    // by L2 under this kernel's load, longer than one tile, and nothing may wait for it on the spot.
+    // (tile, read-back of this lane's first stored element) per pending tile, oldest first.
+    int ptile[kMsDefer];
+    T echo[kMsDefer];
+#pragma unroll
+    for (int i = 0; i < kMsDefer; ++i) { ptile[i] = -1; echo[i] = T(0); }
+    // A fixed-position shift register (no dynamic indexing: it lives in registers): slot 0 is the oldest.
+    auto publish_slot = [&](int tile_id, T e) {
+      // Every lane's read-back of its own store has returned, i.e. the warp's rows of x_out are in L2 (the
+      // GPU's point of coherence): only then is the tile's count incremented.  The vote consumes the echo.
+      if (tile_id >= 0) {
+        const unsigned int all = __ballot_sync(0xffffffffu, !is_poison(e));
+        if ((tid & 31) == 0) {
+          if (m.strict)
+            asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(m.tile_done + tile_id), "r"(all) : "memory");
+          else
+            asm volatile("red.relaxed.gpu.global.add.u32 [%0], 1;" ::"l"(m.tile_done + tile_id), "r"(all) : "memory");
+        }
       }
-      pending = -1;
+    };
+    auto push_pending = [&](int tile_id, T e) {   // publishes the tile stored kMsDefer tiles ago, appends this one
+      publish_slot(ptile[0], echo[0]);
+#pragma unroll
+      for (int i = 0; i + 1 < kMsDefer; ++i) { ptile[i] = ptile[i + 1]; echo[i] = echo[i + 1]; }
+      ptile[kMsDefer - 1] = tile_id;
+      echo[kMsDefer - 1] = e;
+    };
+    auto publish_all = [&]() {
+#pragma unroll
+      for (int i = 0; i < kMsDefer; ++i) { publish_slot(ptile[i], echo[i]); ptile[i] = -1; }
     };
     for (int sw = 0; sw < nsweeps; ++sw) {
       const T* xin = (sw & 1) ? xb : xa;
@@ -351,7 +378,7 @@ k_jacobi_ms(TileArgs<T> a, T* __restrict__ xa, T* __restrict__ xb, const T* __re
         const int32_t* srow = reinterpret_cast<const int32_t*>(sb + L.off_row);
         bool t16 = (IDX == 1);
         // never block while holding an unpublished completion (another CTA may be waiting for it)
-        if (pending >= 0 && !mbar_test(full + s, phase)) publish();
+        if (!mbar_test(full + s, phase)) publish_all();
         mbar_wait(full + s, phase);
         if constexpr (IDX == 2) t16 = *reinterpret_cast<const volatile int*>(sb + L.off_row + kTileFlagOff) != 0;
         T o[K];
@@ -402,20 +429,18 @@ k_jacobi_ms(TileArgs<T> a, T* __restrict__ xa, T* __restrict__ xb, const T* __re
 #pragma unroll
           for (int c = 0; c < K; ++c) o[c] = xx[c] + (w * (bb[c] - acc[c])) / d;   // JacobiGNN.py:119
         }
-        if (pending >= 0) publish();   // the previous tile's read-backs returned long ago
-        sent = o[0];
-        echo = o[0];
+        T eb = T(0);
         if (r < r1) {
           store_vec<T, K>(xout + (size_t)r * K, o);
-          echo = ld_cg_volatile(xout + (size_t)r * K);   // L2 read-back of this lane's own store (same 32-byte sector)
+          eb = ld_cg_volatile(xout + (size_t)r * K);   // L2 read-back of this lane's own store (same 32-byte sector)
         }
         __syncwarp();
         if ((tid & 31) == 0) mbar_arrive(empty + s);
-        pending = tile;
+        push_pending(tile, eb);   // also publishes the tile whose read-backs were issued kMsDefer tiles ago
         if (++s == S) { s = 0; phase ^= 1u; }
         if constexpr (HALO) {
           if (bnd && has_comm) {  // tell the communication CTA that this boundary tile of this sweep is stored
-            publish();
+            publish_all();
             asm volatile("bar.sync 1, 256;" ::: "memory");
             if (tid == 0) {
               __threadfence();
@@ -425,7 +450,7 @@ k_jacobi_ms(TileArgs<T> a, T* __restrict__ xa, T* __restrict__ xb, const T* __re
         }
       }
     }
-    if (pending >= 0) publish();
+    publish_all();
   }
   // ---- exit: the last CTA advances the epoch (and the push counters) for the next launch
   __syncthreads();

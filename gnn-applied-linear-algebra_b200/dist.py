@@ -558,10 +558,12 @@ class DistOperator:
         self.run_step(start, lambda **kw: rt.cheby_first(self.plan, self.vals, b, xin, x, r, pv, table[0, 1:2], **kw),
                       other)
         cur, nxt = other, second
+        self.last_gathered = start
         for it in range(1, deg):
             pin, pout = self.vec[cur], self.vec[nxt]
             self.run_step(cur, lambda **kw: rt.cheby_next(self.plan, self.vals, pin, pout, r, x,
                                                           table[it, 0:1], table[it, 1:2], table[it, 2:3], **kw), nxt)
+            self.last_gathered = cur
             cur, nxt = nxt, cur
         return x, r, cur
 
@@ -627,3 +629,63 @@ class DistOperator:
     def close(self):
         if self.peer is not None:
             self.peer.close()
+
+
+# ---------------------------------------------------------------------------- layer-level handle
+class PartitionedGraph:
+    """The row-partitioned counterpart of `edgeij_pair` for the drop-in layers.
+
+    One process per GPU; every rank holds the edges of ITS contiguous row block with GLOBAL indices,
+    exactly the rows [offsets[rank], offsets[rank+1]) of the reference's `edgeij_pair`.  Passing this
+    handle where a layer expects `edgeij_pair`
+
+        pg = glab_b200.dist.PartitionedGraph(edgeij_pair_of_my_rows, n_global)
+        x_local = JacobiGNN()(n_iters, vertex_attr_of_my_rows, pg, edge_attr_of_my_rows, g)
+
+    runs the same fused layer steps on the row block, with the halo rows of every gathered vector
+    pushed into the neighbours' memory from inside the kernels (NVLink peer memory; engine "torch"
+    falls back to isend/irecv).  vertex_attr / edge_attr / results are this rank's rows / edges; the
+    column layouts and return values are those of the single-GPU layers.  Construction and the first
+    use with a new edge_attr are collective (all ranks, same order)."""
+
+    def __init__(self, edge_index, n_global, part=None, rank=None, world=None, group=None, engine=None,
+                 align=256):
+        if edge_index.dtype != torch.int64 or edge_index.dim() != 2 or edge_index.shape[0] != 2:
+            raise GlabError("edgeij_pair must be an int64 [2, nnz] tensor")
+        inited = dist.is_initialized()
+        self.group = group
+        self.rank = (dist.get_rank(group) if inited else 0) if rank is None else rank
+        self.world = (dist.get_world_size(group) if inited else 1) if world is None else world
+        self.part = RowPartition(n_global, self.world, align=align) if part is None else part
+        self.n_global = n_global
+        self.r0, self.r1 = self.part.bounds(self.rank)
+        self.device = rt.compute_device(edge_index)
+        ei = rt.to_device(edge_index, self.device)
+        if ei.numel() and (int(ei[0].min()) < self.r0 or int(ei[0].max()) >= self.r1):
+            raise GlabError("rank %d owns rows [%d, %d); edgeij_pair holds other rows" % (self.rank, self.r0, self.r1))
+        self.halo = HaloPlan.build(self.part, self.rank, ei[1], group)
+        self.local_edge_index = torch.stack([ei[0] - self.r0, self.halo.local_columns(ei[1])]).contiguous()
+        self.n_local = self.halo.n_local
+        self.nnz_local = int(ei.shape[1])
+        if engine is None:
+            import os
+            engine = os.environ.get("GLAB_DIST_ENGINE", "peer" if self.device.type == "cuda" else "torch")
+        self.engine = engine
+        self._ops = rt._Cache(4)
+
+    def operator(self, edge_attr, k, dtype, col=0):
+        """The DistOperator for these values (cached per edge_attr tensor, k and dtype)."""
+        extra = (k, dtype, col)
+        hit = self._ops.get(edge_attr, extra)
+        if hit is not None:
+            return hit
+        ea = rt.to_device(edge_attr, self.device)
+        ea = ea.view(-1, 1) if ea.dim() == 1 else ea
+        vals = ea[:, col].to(dtype).contiguous()
+        op = DistOperator(self.local_edge_index, vals, self.halo, k=k, engine=self.engine, group=self.group)
+        self._ops.put(edge_attr, op, extra)
+        return op
+
+
+def is_partitioned(edgeij_pair):
+    return isinstance(edgeij_pair, PartitionedGraph)
