@@ -314,8 +314,13 @@ struct Tuning {
   int stages;     // 0 = auto, else forced ring depth
   int ctas;       // 0 = auto (occupancy API), else forced CTAs per SM for the pipeline
   int pdl;        // 1 = programmatic dependent launch between consecutive pipeline kernels
-  int ms;         // 1 = several Jacobi sweeps per launch (glab_jacobi_sweeps_*) use the multi-sweep kernel
+  int ms;         // several Jacobi sweeps per launch (glab_jacobi_sweeps_*): 0 = never the multi-sweep kernel,
+                  // 1 = for operators of at most kMsAutoTiles tiles (where it wins), 2 = always
 };
+// Measured on B200 (profiles/r02_multisweep.md): 10 sweeps on 0.26 M rows take 0.0067 ms per sweep in one
+// multi-sweep launch vs 0.0147 ms as ten launches; break-even near 1 M rows; above, the per-tile cost of
+// publishing completions (an L2 read-back per tile) outweighs the saved launch ramps.
+constexpr int kMsAutoTiles = 4096;
 
 // Bound of the in-kernel waits: caller's value, else GLAB_SPIN_TIMEOUT_MS, else 20 s; < 0 = forever.
 static unsigned long long spin_timeout_ns(int64_t timeout_ms) {
@@ -330,7 +335,7 @@ static unsigned long long spin_timeout_ns(int64_t timeout_ms) {
 static const Tuning& tuning() {
   static Tuning t = [] {
     Tuning v{1, 4096, 8, 1, 0, 0, 1, 1};
-    if (const char* e = getenv("GLAB_MS")) v.ms = atoi(e) != 0;
+    if (const char* e = getenv("GLAB_MS")) { int c = atoi(e); v.ms = c < 0 ? 0 : (c > 2 ? 2 : c); }
     if (const char* e = getenv("GLAB_RPT")) v.rpt = atoi(e) == 2 ? 2 : 1;
     if (const char* e = getenv("GLAB_CAP")) { int c = atoi(e); if (c >= 256 && c <= 8192) v.cap_max = c & ~31; }
     if (const char* e = getenv("GLAB_PIPE")) v.pipe = atoi(e) != 0;
@@ -878,7 +883,8 @@ static int jacobi_sweeps(const glab_plan* p, const T* vals, const T* diag, const
   if (!diag || !b || !xb || !omega || xa == xb || nsweeps < 0) return GLAB_E_ARG;
   if ((hab == nullptr) != (hba == nullptr)) return GLAB_E_ARG;
   if (nsweeps == 0) return 0;
-  if (tuning().ms && tuning().pipe && nsweeps > 1 && p->n_rows > 0) {
+  const int64_t ms_tiles = (p->n_rows + kThreads - 1) / kThreads;
+  if (tuning().ms && tuning().pipe && nsweeps > 1 && p->n_rows > 0 && (tuning().ms == 2 || ms_tiles <= kMsAutoTiles)) {
     rc = hab ? launch_jacobi_ms<T, true>(p, vals, diag, b, xa, xb, omega, k, nsweeps, stream, hab, hba)
              : launch_jacobi_ms<T, false>(p, vals, diag, b, xa, xb, omega, k, nsweeps, stream, nullptr, nullptr);
     if (rc != kNoPipe) return rc;

@@ -27,11 +27,12 @@
 //     warp ~2 us in this kernel -- more than the tile's own 1.3 us -- and halves the throughput; moving
 //     it to a helper lane of the producer warp stalls the producer instead.  So the default hand-off
 //     relies on the L2 being the GPU's point of coherence instead of on MEMBAR:
-//       writer  every lane stores its row of x_out and reads its own first element back with
-//               ld.global.cg; a load of an address this thread just stored to travels the same
-//               SM -> L2-slice path behind the store, so when it returns the stored bits the store is
-//               in L2.  One tile later (so the read-back latency is never exposed) the warp votes that
-//               all 32 read-backs matched and lane 0 issues a RELAXED reduction on the tile's counter.
+//       writer  every lane stores its row of x_out; two tiles later (the store is long past the LSU by
+//               then, so the load is not held behind it) it reads its own first element back from L2
+//               with ld.global.cg, and one tile after that the warp votes that every lane read the
+//               bits it had stored.  That is a VERIFIED statement about the L2 -- which every reader
+//               reads -- not an ordering assumption; a mismatch simply repeats the read.  Then lane 0
+//               issues a RELAXED reduction on the tile's counter.
 //       reader  the producer warp polls the counters with relaxed loads (L2), then performs one
 //               acquiring load (LDG.STRONG + CCTL.IVALL: invalidates this SM's L1, so no line cached two
 //               sweeps ago, when the same buffer held older values, survives) before it releases the
@@ -80,6 +81,9 @@ struct MsNoHalo {};
 
 constexpr int kConsumerWarps = kThreads / 32;
 
+#ifndef GLAB_MS_RING
+#define GLAB_MS_RING 1    // 1 = CSR extents prefetched a 32-tile batch ahead, 0 = one tile ahead
+#endif
 #ifndef GLAB_MS_GATHER_CG
 #define GLAB_MS_GATHER_CG 0
 #endif
@@ -120,6 +124,10 @@ __device__ __forceinline__ double ld_cg_volatile(const double* p) {
 // NaN payload no computation here produces; the outcome is not used for control flow.
 __device__ __forceinline__ bool is_poison(float a) { return __float_as_uint(a) == 0x7fa5a5a5u; }
 __device__ __forceinline__ bool is_poison(double a) { return __double_as_longlong(a) == 0x7ff5a5a5a5a5a5a5ll; }
+__device__ __forceinline__ bool bits_equal(float a, float b) { return __float_as_uint(a) == __float_as_uint(b); }
+__device__ __forceinline__ bool bits_equal(double a, double b) {
+  return __double_as_longlong(a) == __double_as_longlong(b);
+}
 constexpr int kMsDefer = 3;   // tiles between a warp's stores and the publication of their completion
 // own-row / coherent variants of load_vec: plain global loads (L1-cached, honour fences)
 template <typename T, int K>
@@ -210,17 +218,20 @@ k_jacobi_ms(TileArgs<T> a, T* __restrict__ xa, T* __restrict__ xb, const T* __re
     // CSR extents prefetched 32 tiles ahead (see k_row_pipe): lane l holds those of this CTA's
     // (32 j + l)-th tile of the launch; the sequence simply continues across sweeps.
     const int per_sweep = (cta < ntiles) ? (ntiles - cta + ncta - 1) / ncta : 0;   // tiles of this CTA per sweep
-    int my_e0 = 0, my_e1 = 0, my_t16 = (IDX == 1) ? 1 : 0;
-    auto fetch = [&](int seq) {
+    int cur_e0 = 0, cur_e1 = 0, cur_t16 = (IDX == 1) ? 1 : 0;
+    int nxt_e0 = 0, nxt_e1 = 0, nxt_t16 = (IDX == 1) ? 1 : 0;
+    auto fetch = [&](int seq, int& f0, int& f1, int& f16) {
       if (per_sweep > 0 && seq < per_sweep * nsweeps) {
         bool b2;
         const int r0 = phys(cta + (seq % per_sweep) * ncta, b2) * kThreads;
-        my_e0 = __ldg(a.rowptr + r0);
-        my_e1 = __ldg(a.rowptr + min(r0 + kThreads, a.row_end));
-        if constexpr (IDX == 2) my_t16 = __ldg(a.tile16 + r0 / kThreads) != 0;
+        f0 = __ldg(a.rowptr + r0);
+        f1 = __ldg(a.rowptr + min(r0 + kThreads, a.row_end));
+        if constexpr (IDX == 2) f16 = __ldg(a.tile16 + r0 / kThreads) != 0;
       }
     };
-    fetch(lane);
+#if GLAB_MS_RING
+    fetch(lane, nxt_e0, nxt_e1, nxt_t16);
+#endif
     int seq = 0;
     int s = 0;
     uint32_t phase = 0;
@@ -236,12 +247,24 @@ k_jacobi_ms(TileArgs<T> a, T* __restrict__ xa, T* __restrict__ xb, const T* __re
       const int tile = phys(lt, bnd);
       const int r0 = tile * kThreads;
       const int r1 = min(r0 + kThreads, a.row_end);
+#if GLAB_MS_RING
       const int srcl = seq & 31;
-      const int e0 = __shfl_sync(0xffffffffu, my_e0, srcl);
-      const int e1 = __shfl_sync(0xffffffffu, my_e1, srcl);
-      const bool t16 = __shfl_sync(0xffffffffu, my_t16, srcl) != 0;
-      if (lane == srcl) fetch(seq + 32);
+      if (srcl == 0) {   // next batch becomes current, the one after is requested (two register sets, see k_row_pipe)
+        cur_e0 = nxt_e0; cur_e1 = nxt_e1; cur_t16 = nxt_t16;
+        fetch(seq + 32 + lane, nxt_e0, nxt_e1, nxt_t16);
+      }
+      const int e0 = __shfl_sync(0xffffffffu, cur_e0, srcl);
+      const int e1 = __shfl_sync(0xffffffffu, cur_e1, srcl);
+      const bool t16 = __shfl_sync(0xffffffffu, cur_t16, srcl) != 0;
       ++seq;
+#else
+      // one-tile look-ahead, every lane loading the same (uniform) addresses
+      if (seq == 0) { const int l0 = lane; fetch(0 - l0 + l0, nxt_e0, nxt_e1, nxt_t16); }
+      const int e0 = nxt_e0, e1 = nxt_e1;
+      const bool t16 = nxt_t16 != 0;
+      ++seq;
+      fetch(seq, nxt_e0, nxt_e1, nxt_t16);
+#endif
       int nlt = lt + ncta, nsw = sw;
       if (nlt >= ntiles) { nlt = cta; nsw = sw + 1; }
       if (sw > 0 && m.dep >= 0 && lt >= checked_lt) {
@@ -333,37 +356,57 @@ k_jacobi_ms(TileArgs<T> a, T* __restrict__ xa, T* __restrict__ xb, const T* __re
     const T w = __ldg(omega);
     int s = 0;
     uint32_t phase = 0;
-    // Publication of a finished tile is deferred by kMsDefer tiles: a write takes ~2 us to be acknowledged
-    // by L2 under this kernel's load, longer than one tile, and nothing may wait for it on the spot.
-    // (tile, read-back of this lane's first stored element) per pending tile, oldest first.
-    int ptile[kMsDefer];
-    T echo[kMsDefer];
+    // Publication of a finished tile.  A write takes ~2 us to reach L2 under this kernel's load --
+    // longer than a tile -- and anything that waits for it on the spot (MEMBAR, or a read-back of the
+    // address just stored, which the LSU holds behind the store) stalls the warp's next gathers.  So a
+    // finished tile rides a 3-slot shift register: two tiles after its stores the lane reads its own
+    // first element back from L2 (ld.global.cg), one tile later the warp votes that every lane saw
+    // the bits it had stored -- i.e. the L2, which is what every reader reads, HOLDS the new values
+    // -- and only then lane 0 increments the tile's counter (a mismatch just repeats the read).
+    int ptile[kMsDefer], ppar[kMsDefer];
+    T pexp[kMsDefer];
+    T echo = T(0);
+    bool echo_valid = false;
 #pragma unroll
-    for (int i = 0; i < kMsDefer; ++i) { ptile[i] = -1; echo[i] = T(0); }
-    // A fixed-position shift register (no dynamic indexing: it lives in registers): slot 0 is the oldest.
-    auto publish_slot = [&](int tile_id, T e) {
-      // Every lane's read-back of its own store has returned, i.e. the warp's rows of x_out are in L2 (the
-      // GPU's point of coherence): only then is the tile's count incremented.  The vote consumes the echo.
-      if (tile_id >= 0) {
-        const unsigned int all = __ballot_sync(0xffffffffu, !is_poison(e));
-        if ((tid & 31) == 0) {
-          if (m.strict)
-            asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(m.tile_done + tile_id), "r"(all) : "memory");
-          else
-            asm volatile("red.relaxed.gpu.global.add.u32 [%0], 1;" ::"l"(m.tile_done + tile_id), "r"(all) : "memory");
-        }
-      }
+    for (int i = 0; i < kMsDefer; ++i) { ptile[i] = -1; ppar[i] = 0; pexp[i] = T(0); }
+    auto read_back0 = [&]() {   // slot 0: this lane's first stored element, through L2
+      const int row = ptile[0] * kThreads + tid;
+      echo = pexp[0];
+      if (row < a.row_end) echo = ld_cg_volatile((ppar[0] ? xa : xb) + (size_t)row * K);
+      echo_valid = true;
     };
-    auto push_pending = [&](int tile_id, T e) {   // publishes the tile stored kMsDefer tiles ago, appends this one
-      publish_slot(ptile[0], echo[0]);
+    auto publish0 = [&]() {     // slot 0 must hold a tile
+      while (true) {
+        if (!echo_valid) read_back0();
+        if (__all_sync(0xffffffffu, bits_equal(echo, pexp[0])) || m.dep < 0) break;   // (dep < 0: timing experiments)
+        echo_valid = false;
+      }
+      if ((tid & 31) == 0) {
+        if (m.strict) asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(m.tile_done + ptile[0]) : "memory");
+        else asm volatile("red.relaxed.gpu.global.add.u32 [%0], 1;" ::"l"(m.tile_done + ptile[0]) : "memory");
+      }
+      ptile[0] = -1;
+      echo_valid = false;
+    };
+    auto shift = [&]() {
 #pragma unroll
-      for (int i = 0; i + 1 < kMsDefer; ++i) { ptile[i] = ptile[i + 1]; echo[i] = echo[i + 1]; }
+      for (int i = 0; i + 1 < kMsDefer; ++i) { ptile[i] = ptile[i + 1]; ppar[i] = ppar[i + 1]; pexp[i] = pexp[i + 1]; }
+      ptile[kMsDefer - 1] = -1;
+    };
+    auto push_pending = [&](int tile_id, int parity, T first) {
+      if (ptile[0] >= 0) publish0();      // its read-back was issued one tile ago
+      shift();
       ptile[kMsDefer - 1] = tile_id;
-      echo[kMsDefer - 1] = e;
+      ppar[kMsDefer - 1] = parity;
+      pexp[kMsDefer - 1] = first;
+      if (ptile[0] >= 0) read_back0();    // stored two tiles ago: long past the LSU
     };
     auto publish_all = [&]() {
 #pragma unroll
-      for (int i = 0; i < kMsDefer; ++i) { publish_slot(ptile[i], echo[i]); ptile[i] = -1; }
+      for (int i = 0; i < kMsDefer; ++i) {
+        if (ptile[0] >= 0) publish0();
+        shift();
+      }
     };
     for (int sw = 0; sw < nsweeps; ++sw) {
       const T* xin = (sw & 1) ? xb : xa;
@@ -429,14 +472,10 @@ k_jacobi_ms(TileArgs<T> a, T* __restrict__ xa, T* __restrict__ xb, const T* __re
 #pragma unroll
           for (int c = 0; c < K; ++c) o[c] = xx[c] + (w * (bb[c] - acc[c])) / d;   // JacobiGNN.py:119
         }
-        T eb = T(0);
-        if (r < r1) {
-          store_vec<T, K>(xout + (size_t)r * K, o);
-          eb = ld_cg_volatile(xout + (size_t)r * K);   // L2 read-back of this lane's own store (same 32-byte sector)
-        }
+        if (r < r1) store_vec<T, K>(xout + (size_t)r * K, o);
         __syncwarp();
         if ((tid & 31) == 0) mbar_arrive(empty + s);
-        push_pending(tile, eb);   // also publishes the tile whose read-backs were issued kMsDefer tiles ago
+        push_pending(tile, sw & 1, o[0]);   // also publishes the tile stored kMsDefer tiles ago
         if (++s == S) { s = 0; phase ^= 1u; }
         if constexpr (HALO) {
           if (bnd && has_comm) {  // tell the communication CTA that this boundary tile of this sweep is stored

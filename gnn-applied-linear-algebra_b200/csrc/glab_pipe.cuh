@@ -344,25 +344,114 @@ k_row_pipe(TileArgs<T> a, const T* __restrict__ x, Epi epi, int ntiles, PipeLayo
       }
     }
   } else if (tid >= kThreads) {
+   if constexpr (!HALO) {
+    // Single-GPU kernels: one producer lane with a one-tile look-ahead on the CSR extents.  (The
+    // batch prefetch below was measured SLOWER here -- L4096 Jacobi 0.135 -> 0.153 ms -- although it
+    // is faster for the row blocks of the halo kernels: profiles/r02_halo_gap.md.)
+    // ------------------------------------------------------------------ producer warp
+    if (tid != kThreads) {
+      pdl_wait();
+      epi.init(st);
+    } else {
+      int lt = cta;
+      int e0n = 0, e1n = 0;
+      bool t16n = (IDX == 1);
+      bool bnd = false, waited = false;
+      if (lt < ntiles) {
+        const int r0 = a.row_begin + phys(lt, bnd) * kThreads;
+        e0n = __ldg(a.rowptr + r0);
+        e1n = __ldg(a.rowptr + min(r0 + kThreads, a.row_end));
+        if constexpr (IDX == 2) t16n = __ldg(a.tile16 + r0 / kThreads) != 0;
+      }
+      pdl_wait();  // rowptr is constant; everything copied below may come from the previous kernel
+      epi.init(st);
+      int s = 0;
+      uint32_t phase = 0;
+      for (; lt < ntiles; lt += ncta) {
+        const int r0 = a.row_begin + phys(lt, bnd) * kThreads;
+        const int r1 = min(r0 + kThreads, a.row_end);
+        const int e0 = e0n, e1 = e1n;
+        const bool t16 = t16n;
+        const int nt = lt + ncta;
+        if (nt < ntiles) {  // prefetch the next tile's extents while this stage drains
+          bool b2;
+          const int q0 = a.row_begin + phys(nt, b2) * kThreads;
+          e0n = __ldg(a.rowptr + q0);
+          e1n = __ldg(a.rowptr + min(q0 + kThreads, a.row_end));
+          if constexpr (IDX == 2) t16n = __ldg(a.tile16 + q0 / kThreads) != 0;
+        }
+        if constexpr (HALO) {
+          if (bnd && !waited) {  // neighbours' halo rows must have landed before consumers gather them
+            const uint32_t want = *reinterpret_cast<const volatile uint32_t*>(h.wait_target);
+            for (int i = 0; i < h.n_wait; ++i) {
+              SpinGuard guard(h.timeout_ns);
+              while ((int32_t)(ld_acquire_sys(h.wait_flag[i]) - want) < 0) {
+                __nanosleep(32);
+                if (guard.expired()) { flag_timeout(h.status, GLAB_STATUS_TIMEOUT_PEER); break; }
+              }
+            }
+            waited = true;
+          }
+        }
+        mbar_wait(empty + s, phase ^ 1u);
+        unsigned char* sb = stage0 + (size_t)s * L.stage_bytes;
+        const void *src_c = nullptr, *src_v = nullptr;
+        uint32_t nb_c = 0, nb_v = 0, nb_s[kMaxStreams];
+        const uint32_t nb_r = (uint32_t)(((r1 - r0 + 1) * 4 + 15) & ~15);
+        uint32_t total = nb_r;
+        if (e1 > e0) {
+          if (IDX != 0 && t16) align16(a.coldelta + e0, (e1 - e0) * 2, src_c, nb_c);
+          else align16(a.colidx + e0, (e1 - e0) * 4, src_c, nb_c);
+          align16(a.vals + e0, (e1 - e0) * (int)sizeof(T), src_v, nb_v);
+          total += nb_c + nb_v;
+        }
+#pragma unroll
+        for (int i = 0; i < kMaxStreams; ++i) {
+          nb_s[i] = 0;
+          if (i < Epi::kStreams) {
+            nb_s[i] = (uint32_t)(((r1 - r0) * epi.stream_width(i) * (int)sizeof(T) + 15) & ~15);
+            total += nb_s[i];
+          }
+        }
+        // ordinary shared store; the arrive below releases it to the consumers' acquire on `full`
+        if constexpr (IDX == 2) *reinterpret_cast<volatile int*>(sb + L.off_row + kTileFlagOff) = t16 ? 1 : 0;
+        mbar_expect_tx(full + s, total);
+        bulk_g2s(sb + L.off_row, a.rowptr + r0, nb_r, full + s);
+        if (nb_c) {
+          bulk_g2s(sb + L.off_col, src_c, nb_c, full + s);
+          bulk_g2s(sb + L.off_val, src_v, nb_v, full + s);
+        }
+#pragma unroll
+        for (int i = 0; i < kMaxStreams; ++i)
+          if (i < Epi::kStreams)
+            bulk_g2s(sb + L.off_stream[i], epi.stream_ptr(i) + (size_t)r0 * epi.stream_width(i), nb_s[i],
+                     full + s);
+        if (++s == S) { s = 0; phase ^= 1u; }
+      }
+    }
+   } else {
     // ------------------------------------------------------------------ producer warp
     // Lane 0 feeds the ring.  The CSR extents of a tile (two dependent global loads, ~1-3 us under
-    // load) are prefetched 32 tiles ahead: lane l holds the extents of this CTA's (32 j + l)-th tile and
-    // re-arms itself right after its values have been broadcast (profiles/r02_halo_gap.md: with a
-    // one-tile look-ahead the producer sat on that load for ~40 % of its time and the consumers
-    // waited on `full` for 17-30 % of theirs).
+    // load) are prefetched in batches of 32 tiles, one tile per lane, a whole batch ahead: `cur`
+    // holds the batch being issued, `nxt` the following one, whose loads were issued 32 tiles
+    // earlier (profiles/r02_halo_gap.md: with a one-tile look-ahead the producer sat on that load for
+    // ~40 % of its time and the consumers waited on `full` for 17-30 % of theirs).  Two register
+    // sets, because the scoreboard tracks a register for the whole warp: a load into one lane of the
+    // set being broadcast would stall every shuffle behind it.
     const int lane = tid - kThreads;
-    int my_e0 = 0, my_e1 = 0, my_t16 = (IDX == 1) ? 1 : 0;
-    auto fetch = [&](int seq) {
+    int cur_e0 = 0, cur_e1 = 0, cur_t16 = (IDX == 1) ? 1 : 0;
+    int nxt_e0 = 0, nxt_e1 = 0, nxt_t16 = (IDX == 1) ? 1 : 0;
+    auto fetch = [&](int seq, int& f0, int& f1, int& f16) {
       const int lt2 = cta + seq * ncta;
       if (lt2 < ntiles) {
         bool b2;
         const int q0 = a.row_begin + phys(lt2, b2) * kThreads;
-        my_e0 = __ldg(a.rowptr + q0);
-        my_e1 = __ldg(a.rowptr + min(q0 + kThreads, a.row_end));
-        if constexpr (IDX == 2) my_t16 = __ldg(a.tile16 + q0 / kThreads) != 0;
+        f0 = __ldg(a.rowptr + q0);
+        f1 = __ldg(a.rowptr + min(q0 + kThreads, a.row_end));
+        if constexpr (IDX == 2) f16 = __ldg(a.tile16 + q0 / kThreads) != 0;
       }
     };
-    if (cta >= 0) fetch(lane);
+    fetch(lane, nxt_e0, nxt_e1, nxt_t16);
     pdl_wait();  // rowptr is constant; everything copied below may come from the previous kernel
     epi.init(st);
     {
@@ -371,10 +460,13 @@ k_row_pipe(TileArgs<T> a, const T* __restrict__ x, Epi epi, int ntiles, PipeLayo
       uint32_t phase = 0;
       for (int lt = cta; lt >= 0 && lt < ntiles; lt += ncta, ++seq) {
         const int src = seq & 31;
-        const int e0 = __shfl_sync(0xffffffffu, my_e0, src);
-        const int e1 = __shfl_sync(0xffffffffu, my_e1, src);
-        const bool t16 = __shfl_sync(0xffffffffu, my_t16, src) != 0;
-        if (lane == src) fetch(seq + 32);
+        if (src == 0) {   // next batch becomes current (its loads are 32 tiles old), the one after is requested
+          cur_e0 = nxt_e0; cur_e1 = nxt_e1; cur_t16 = nxt_t16;
+          fetch(seq + 32 + lane, nxt_e0, nxt_e1, nxt_t16);
+        }
+        const int e0 = __shfl_sync(0xffffffffu, cur_e0, src);
+        const int e1 = __shfl_sync(0xffffffffu, cur_e1, src);
+        const bool t16 = __shfl_sync(0xffffffffu, cur_t16, src) != 0;
         if (lane == 0) {
           const int r0 = a.row_begin + phys(lt, bnd) * kThreads;
           const int r1 = min(r0 + kThreads, a.row_end);
@@ -429,6 +521,7 @@ k_row_pipe(TileArgs<T> a, const T* __restrict__ x, Epi epi, int ntiles, PipeLayo
         if (++s == S) { s = 0; phase ^= 1u; }
       }
     }
+   }
   } else {
     // ------------------------------------------------------------------ consumer warps
     pdl_wait();
@@ -561,54 +654,49 @@ k_edge_pipe(TileArgs<T> a, const T* __restrict__ aux, const int32_t* __restrict_
   __syncthreads();
 
   if (tid >= kThreads) {
-    {  // ------------------------------------------------------------------------- producer warp
-      // lane 0 feeds the ring; extents are prefetched 32 tiles ahead, one tile per lane (see k_row_pipe)
-      const int lane = tid - kThreads;
-      int my_e0 = 0, my_e1 = 0;
-      auto fetch = [&](int seq) {
-        const int t2 = (int)blockIdx.x + seq * (int)gridDim.x;
-        if (t2 < ntiles) {
-          const int q0 = t2 * kThreads;
-          my_e0 = __ldg(a.rowptr + q0);
-          my_e1 = __ldg(a.rowptr + min(q0 + kThreads, a.row_end));
-        }
-      };
-      fetch(lane);
-      int s = 0, seq = 0;
+    if (tid == kThreads) {  // ---------------------------------------------------- producer
+      int tile = blockIdx.x;
+      int e0n = 0, e1n = 0;
+      if (tile < ntiles) {
+        const int r0 = tile * kThreads;
+        e0n = __ldg(a.rowptr + r0);
+        e1n = __ldg(a.rowptr + min(r0 + kThreads, a.row_end));
+      }
+      int s = 0;
       uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++seq) {
-        const int src = seq & 31;
-        const int e0 = __shfl_sync(0xffffffffu, my_e0, src);
-        const int e1 = __shfl_sync(0xffffffffu, my_e1, src);
-        if (lane == src) fetch(seq + 32);
-        if (lane == 0) {
-          const int r0 = tile * kThreads;
-          const int r1 = min(r0 + kThreads, a.row_end);
-          mbar_wait(empty + s, phase ^ 1u);
-          unsigned char* sb = stage0 + (size_t)s * L.stage_bytes;
-          const void *src_c = nullptr, *src_v = nullptr, *src_a = nullptr;
-          uint32_t nb_c = 0, nb_v = 0, nb_a = 0;
-          const uint32_t nb_r = (uint32_t)(((r1 - r0 + 1) * 4 + 15) & ~15);
-          uint32_t total = nb_r;
-          if (e1 > e0) {
-            align16(a.vals + e0, (e1 - e0) * (int)sizeof(T), src_v, nb_v);
-            total += nb_v;
-            if (Op::kNeedCol) {
-              align16(a.colidx + e0, (e1 - e0) * 4, src_c, nb_c);
-              total += nb_c;
-            }
-            if (Op::kNarr > 1) {
-              align16(aux + e0, (e1 - e0) * (int)sizeof(T), src_a, nb_a);
-              total += nb_a;
-            }
-          }
-          mbar_expect_tx(full + s, total);
-          bulk_g2s(sb + L.off_row, a.rowptr + r0, nb_r, full + s);
-          if (nb_v) bulk_g2s(sb + L.off_val, src_v, nb_v, full + s);
-          if (nb_c) bulk_g2s(sb + L.off_col, src_c, nb_c, full + s);
-          if (nb_a) bulk_g2s(sb + L.off_aux, src_a, nb_a, full + s);
+      for (; tile < ntiles; tile += gridDim.x) {
+        const int r0 = tile * kThreads;
+        const int r1 = min(r0 + kThreads, a.row_end);
+        const int e0 = e0n, e1 = e1n;
+        const int nt = tile + gridDim.x;
+        if (nt < ntiles) {
+          const int q0 = nt * kThreads;
+          e0n = __ldg(a.rowptr + q0);
+          e1n = __ldg(a.rowptr + min(q0 + kThreads, a.row_end));
         }
-        __syncwarp();
+        mbar_wait(empty + s, phase ^ 1u);
+        unsigned char* sb = stage0 + (size_t)s * L.stage_bytes;
+        const void *src_c = nullptr, *src_v = nullptr, *src_a = nullptr;
+        uint32_t nb_c = 0, nb_v = 0, nb_a = 0;
+        const uint32_t nb_r = (uint32_t)(((r1 - r0 + 1) * 4 + 15) & ~15);
+        uint32_t total = nb_r;
+        if (e1 > e0) {
+          align16(a.vals + e0, (e1 - e0) * (int)sizeof(T), src_v, nb_v);
+          total += nb_v;
+          if (Op::kNeedCol) {
+            align16(a.colidx + e0, (e1 - e0) * 4, src_c, nb_c);
+            total += nb_c;
+          }
+          if (Op::kNarr > 1) {
+            align16(aux + e0, (e1 - e0) * (int)sizeof(T), src_a, nb_a);
+            total += nb_a;
+          }
+        }
+        mbar_expect_tx(full + s, total);
+        bulk_g2s(sb + L.off_row, a.rowptr + r0, nb_r, full + s);
+        if (nb_v) bulk_g2s(sb + L.off_val, src_v, nb_v, full + s);
+        if (nb_c) bulk_g2s(sb + L.off_col, src_c, nb_c, full + s);
+        if (nb_a) bulk_g2s(sb + L.off_aux, src_a, nb_a, full + s);
         if (++s == S) { s = 0; phase ^= 1u; }
       }
     }

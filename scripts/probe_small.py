@@ -12,6 +12,7 @@ import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
+os.environ.setdefault("GLAB_MS", "2")      # time the multi-sweep kernel on every size
 import torch  # noqa: E402
 import glab_b200 as G  # noqa: E402
 

@@ -10,6 +10,8 @@ and the torch.sparse glue of the V-cycle use the tolerances.
 """
 import ctypes
 
+import os
+
 import pytest
 import torch
 
@@ -891,6 +893,7 @@ def test_multi_sweep_jacobi_bit_exact(G, dev, dt, case, strict, monkeypatch):
     formally fenced one (GLAB_MS_STRICT=1: MEMBAR-based release / acquire fences)."""
     rt = G.runtime
     monkeypatch.setenv("GLAB_MS_STRICT", "1" if strict else "0")
+    assert os.environ.get("GLAB_MS") == "2", "run the GPU suite with GLAB_MS=2 (tests/conftest.py sets it)"
     ei, ev = _ms_operator(G, dev, dt, case)
     n = int(ei[0].max().item()) + 1
     plan = G.Plan.from_coo(ei, n)
