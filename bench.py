@@ -179,6 +179,67 @@ class ClockSampler:
         return out
 
 
+def bind_to_gpu_numa(cuda_index):
+    """Pin this process (and therefore the pinned host buffers it allocates from now on) to the NUMA node
+    its GPU hangs off, when the platform exposes it.  Returns what was found for the JSON line."""
+    info = {"numa_node": None, "bound": False}
+    try:
+        props = torch.cuda.get_device_properties(cuda_index)
+        bdf = "%04x:%02x:%02x.0" % (getattr(props, "pci_domain_id", 0), props.pci_bus_id, props.pci_device_id)
+        info["pci"] = bdf
+        node = int(open("/sys/bus/pci/devices/%s/numa_node" % bdf).read().strip())
+        info["numa_node"] = node
+        nodes = [d for d in os.listdir("/sys/devices/system/node") if d.startswith("node") and d[4:].isdigit()]
+        info["numa_nodes_visible"] = len(nodes)
+        if node >= 0 and len(nodes) > 1:
+            cpus = set()
+            for part in open("/sys/devices/system/node/node%d/cpulist" % node).read().strip().split(","):
+                a, _, b = part.partition("-")
+                cpus.update(range(int(a), int(b or a) + 1))
+            allowed = os.sched_getaffinity(0)
+            use = cpus & allowed
+            if use:
+                os.sched_setaffinity(0, use)
+                info["bound"] = True
+                info["cpus"] = len(use)
+    except Exception as exc:          # no sysfs / no permission: not fatal, just reported
+        info["error"] = str(exc)[:80]
+    return info
+
+
+def e2e_phases(prob, reps=3):
+    """Where an end-to-end step spends its time, measured on serialised steps AFTER the timed region:
+    H2D of the step's inputs, the layer calls (device time and host time to issue them), D2H."""
+    import statistics
+    if not hasattr(prob, "layer_pass"):
+        return None
+    dev = prob.dev
+    va_dev = torch.empty_like(prob.va_host, device=dev)
+    out_host = torch.empty(prob.va_host.shape[0], 1).pin_memory()
+    rows = []
+    for _ in range(reps + 1):
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+        torch.cuda.synchronize()
+        ev[0].record()
+        va_dev.copy_(prob.va_host, non_blocking=True)
+        ev[1].record()
+        t0 = time.perf_counter()
+        res = prob.layer_pass(va_dev)
+        t_issue = time.perf_counter() - t0
+        ev[2].record()
+        out_host.copy_(res, non_blocking=True)
+        ev[3].record()
+        torch.cuda.synchronize()
+        rows.append((ev[0].elapsed_time(ev[1]), ev[1].elapsed_time(ev[2]), t_issue * 1e3, ev[2].elapsed_time(ev[3])))
+    rows = rows[1:]
+    med = [statistics.median(r[i] for r in rows) for i in range(4)]
+    h2d_gbs = prob.h2d_bytes / (med[0] * 1e-3) / 1e9 if med[0] > 0 else None
+    return {"h2d_ms": med[0], "layers_device_ms": med[1], "layers_host_issue_ms": med[2], "d2h_ms": med[3],
+            "h2d_GBps": h2d_gbs, "serialised_sum_ms": med[0] + med[1] + med[3],
+            "note": "medians of %d serialised steps on this rank; the timed e2e loop overlaps H2D / compute / D2H of "
+                    "neighbouring steps, so its step time is bounded below by the largest phase" % reps}
+
+
 def jacobi_bytes(n, z, s=4, k=1):
     return z * (4 + s) + 4 * (n + 1) + (3 * k + 1) * n * s
 
@@ -282,6 +343,7 @@ def main_gpu(args):
             raise SystemExit("--gpus %d needs torchrun with %d ranks" % (args.gpus, args.gpus))
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    numa = bind_to_gpu_numa(local_rank)      # before any pinned allocation
     if world > 1:
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=dev)
@@ -361,6 +423,12 @@ def main_gpu(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms_total, jac_ms, e2e_ms = t.tolist()
 
+    # ---------------- parity of the measured path (outside the timed regions), phases of an e2e step
+    parity = prob.parity()
+    phases = e2e_phases(prob)
+    if world > 1 and getattr(prob, "op", None) is not None:
+        prob.op.check()                      # bounded in-kernel waits: raises if one gave up
+
     ms_step = ms_total / args.steps
     value = LAUNCHES_PER_STEP * z_global / (ms_step * 1e-3)
     e2e_value = LAUNCHES_PER_STEP * z_global / (e2e_ms / args.steps * 1e-3)
@@ -390,16 +458,36 @@ def main_gpu(args):
                      "traffic": None if not traffic else traffic.get(
                          "jacobi_dram_bytes_per_launch_idx16" if idx_bytes == 2 else "jacobi_dram_bytes_per_launch")
                      if world == 1 else None,
-                     "traffic_source": None if not traffic else traffic.get(
-                         "source_idx16" if idx_bytes == 2 else "source")},
+                     "traffic_source": (None if not traffic else traffic.get(
+                         "source_idx16" if idx_bytes == 2 else "source")) if world == 1 else None},
         "e2e": {"value": e2e_value, "unit": "nnz/s", "ms_per_step": e2e_ms / args.steps,
                 "h2d_bytes_per_step": prob.h2d_bytes * world, "d2h_bytes_per_step": prob.d2h_bytes * world,
-                "api": "JacobiGNN.forward(10, ...) + ChebyRelaxGNN(4).forward(...) on device copies of pinned host vectors",
-                "pipelining": "double-buffered: step i+1's H2D and step i-1's D2H overlap step i's compute (N = 1)"},
+                "api": ("JacobiGNN.forward(10, vertex_attr, edgeij_pair, ...) + ChebyRelaxGNN(4).forward(...) on device "
+                        "copies of pinned host vectors" if world == 1 else
+                        "JacobiGNN.forward(10, vertex_attr_slab, dist.PartitionedGraph, ...) + ChebyRelaxGNN(4).forward(...) "
+                        "on each rank's slab, device copies of pinned host vectors"),
+                "uploaded_per_step": "vertex_attr = [A_ii, b, x] (3 vectors) of every rank's rows",
+                "pipelining": "double-buffered: step i+1's H2D and step i-1's D2H overlap step i's compute",
+                "phases": phases, "numa": numa},
+        "parity": parity,
         "gpu_launches": launches,
         "clocks": clocks,
         "setup": prob.setup_info,
     }
+    if parity is not None and not parity.get("ok", False):
+        line["parity_failed"] = True
+    # ---------------- the other BASELINE configs as sub-results (each guarded: a failure is reported, not fatal)
+    extras = [e for e in (args.extras or "").split(",") if e and e != "none"]
+    if "all" in extras:
+        extras = ["L8192_layers", "config3_power", "config4_amg", "config5_vcycle"]
+    if extras:
+        if hasattr(prob, "close"):
+            prob.close()
+        del prob
+        import gc
+        gc.collect()
+        torch.cuda.empty_cache()
+        line["extra"] = run_extras(G, dev, rank, world, peak, extras, not args.no_cpu_baseline)
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         r = run_cpu_reference(args.workload, 1, 0)
         line["cpu_baseline"] = {"value": r["value"], "unit": "nnz/s", "cores": r["cores"], "kind": r["kind"],
@@ -413,6 +501,40 @@ def main_gpu(args):
     return 0
 
 
+def run_extras(G, dev, rank, world, peak, names, cpu_baseline):
+    """bench_extra.* one by one; every rank takes part in the partitioned ones.  The single-GPU-only
+    sub-results (the 67 M-row layer table and the AMG setup kernels) run on rank 0's GPU at N = 1 only."""
+    import bench_extra as X
+    out = {}
+    grid_big = int(os.environ.get("GLAB_BENCH_BIG", "8192"))       # shrink for smoke runs of the bench itself
+    grid_amg = int(os.environ.get("GLAB_BENCH_AMG", "4096"))
+    for name in names:
+        t0 = time.perf_counter()
+        try:
+            if name == "L8192_layers":
+                res = X.l8192_layers(G, dev, peak, N=grid_big) if world == 1 else None
+            elif name == "config3_power":
+                res = X.config3_power(G, dev, rank, world, peak, N=grid_big, cpu_baseline=cpu_baseline)
+            elif name == "config4_amg":
+                res = X.config4_amg(G, dev, peak, N=grid_amg, cpu_baseline=cpu_baseline) if world == 1 else None
+            elif name == "config5_vcycle":
+                res = X.config5_vcycle(G, dev, rank, world, peak, N=grid_big, cpu_baseline=cpu_baseline)
+            else:
+                res = {"error": "unknown extra %r" % name}
+        except Exception as exc:       # noqa: BLE001 -- reported in the JSON line
+            import traceback
+            res = {"error": "%s: %s" % (type(exc).__name__, str(exc)[:300]),
+                   "where": traceback.format_exc().strip().splitlines()[-3:]}
+            torch.cuda.synchronize()
+        if res is not None:
+            res["wall_s"] = time.perf_counter() - t0
+            out[name] = res
+        if world > 1:
+            import torch.distributed as dist
+            dist.barrier()
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -421,6 +543,8 @@ def main():
     ap.add_argument("--impl", default="glab", choices=["glab", "reference"])
     ap.add_argument("--workload", default=os.environ.get("GLAB_BENCH_WORKLOAD", "L4096"), choices=sorted(GRID))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--extras", default=os.environ.get("GLAB_BENCH_EXTRAS", "all"),
+                    help="comma list of L8192_layers,config3_power,config4_amg,config5_vcycle | all | none")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "glab":
         args.warmup = 3

@@ -79,6 +79,12 @@ class SingleGpuSmoother:
         self.result = dst
         return ev
 
+    def layer_pass(self, va):
+        """The drop-in layer calls on device-resident vertex_attr = [A_ii, b, x]."""
+        x1 = self.jac(self.N_JACOBI, va, self.ei, self.ea2, self.gw)
+        v, e, g = self.cheb(self.rt.pack([va[:, 1:2].contiguous(), x1]), self.ei, self.ev, self.gc)
+        return v[:, 1:2]
+
     def parity(self):
         """The layer pass at full size against an independent fp64 formulation: 10 Jacobi sweeps and the
         degree-4 Chebyshev recurrence applied with shifted grid slices (no CSR code involved)."""

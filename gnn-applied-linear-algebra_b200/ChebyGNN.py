@@ -24,6 +24,27 @@ def _recurrence(deg, g):
     return rows, g_out
 
 
+_table_cache = {}
+
+
+def _device_table(deg, g, device, dt):
+    """(per-iteration [alpha_old, alpha, beta] table on the device, final g) for host-resident g, cached
+    per (deg, c, d, dtypes, device): the recurrence is ~20 tiny CPU tensor ops plus an upload, more host
+    time per call than the kernels take on a partitioned operator."""
+    if g.is_cuda:
+        rows, g_out = _recurrence(deg, g)
+        return torch.stack([torch.stack(r) for r in rows]).to(device=device, dtype=dt).contiguous(), g_out
+    key = (deg, float(g[0]), float(g[1]), g.dtype, str(device), dt)
+    hit = _table_cache.get(key)
+    if hit is None:
+        if len(_table_cache) > 64:
+            _table_cache.clear()
+        rows, g_out = _recurrence(deg, g)
+        hit = (torch.stack([torch.stack(r) for r in rows]).to(device=device, dtype=dt).contiguous(), g_out)
+        _table_cache[key] = hit
+    return hit[0], hit[1].clone()
+
+
 class ChebyRelaxGNN(torch.nn.Module):
     """ChebyGNN.py:287-353.  in: vertex_attr=[b,x], edge_attr=[A_ij], g=[c,d];
     out: vertex_attr=[b,x,r,p], edge_attr=[A_ij,z_ij], g=[c,d,alpha,beta].
@@ -43,12 +64,11 @@ class ChebyRelaxGNN(torch.nn.Module):
         k = F // 2
         op = pg.operator(edge_attr, k, dt)
         va = io.up(vertex_attr, dt)
-        b, _ = rt.unpack(va, [(0, k), (k, k)], outs=[None, op.local("v0")])
-        op.publish("v0")
-        rows, g_out = _recurrence(self.deg, g)
-        table = torch.stack([torch.stack(r) for r in rows]).to(device=io.device, dtype=dt,
-                                                               non_blocking=True).contiguous()
-        x, r, pname = op.chebyshev(self.deg, b, table, "v0")
+        ent = op.entry()
+        b, _ = rt.unpack(va, [(0, k), (k, k)], outs=[None, op.local(ent)])
+        op.publish(ent)
+        table, g_out = _device_table(self.deg, g, io.device, dt)
+        x, r, pname = op.chebyshev(self.deg, b, table, ent)
         if op.halo.part.world > 1:
             op.acquire(op.last_gathered)      # the message column reads that vector's halo tail
         e_out = rt.with_messages(op.plan, op.vals, op.vec[op.last_gathered])
@@ -69,9 +89,7 @@ class ChebyRelaxGNN(torch.nn.Module):
         vals = rt.get_vals(plan, edge_attr, 0, dt)
         va = io.up(vertex_attr, dt)
         b, x0 = rt.unpack(va, [(0, k), (k, k)])
-        rows, g_out = _recurrence(self.deg, g)
-        table = torch.stack([torch.stack(r) for r in rows]).to(device=io.device, dtype=dt,
-                                                               non_blocking=True).contiguous()
+        table, g_out = _device_table(self.deg, g, io.device, dt)
         x = torch.empty_like(x0)
         r = torch.empty_like(x0)
         p = torch.empty_like(x0)

@@ -17,9 +17,10 @@ class GNNResidual(torch.nn.Module):
             k = vertex_attr.shape[1] // 2
             op = edgeij_pair.operator(edge_attr, k, dt)
             va = io.up(vertex_attr, dt)
-            b, _ = rt.unpack(va, [(0, k), (k, k)], outs=[None, op.local("v0")])
-            op.publish("v0")
-            return io.down(op.spmv("v0", torch.empty_like(b), b=b))
+            ent = op.entry()
+            b, _ = rt.unpack(va, [(0, k), (k, k)], outs=[None, op.local(ent)])
+            op.publish(ent)
+            return io.down(op.spmv(ent, torch.empty_like(b), b=b))
         io = Placement(vertex_attr, edgeij_pair, edge_attr)
         dt = float_dtype(vertex_attr, edge_attr)
         n, F = vertex_attr.shape

@@ -41,11 +41,11 @@ class JacobiGNN(torch.nn.Module):
         k = (F - 1) // 2
         op = pg.operator(edge_attr, k, dt)
         va = io.up(vertex_attr, dt)
-        x0 = op.local("v0")
-        diag, b, _ = rt.unpack(va, [(0, 1), (1, k), (1 + k, k)], outs=[None, None, x0])
+        ent = op.entry()
+        diag, b, _ = rt.unpack(va, [(0, 1), (1, k), (1 + k, k)], outs=[None, None, op.local(ent)])
         w = rt.scalar(g[0] if isinstance(g, torch.Tensor) else g, io.device, dt)
-        op.publish("v0")
-        cur = op.jacobi(n_iters, diag.view(-1), b, w, "v0")
+        op.publish(ent)
+        cur = op.jacobi(n_iters, diag.view(-1), b, w, ent)
         return io.down(op.local(cur).clone())
 
     def forward(self, n_iters, vertex_attr, edgeij_pair, edge_attr, g, batch=None):

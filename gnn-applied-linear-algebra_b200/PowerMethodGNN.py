@@ -23,15 +23,16 @@ class PowerMethodGNN(torch.nn.Module):
         dt = float_dtype(vertex_attr, edge_attr)
         op = pg.operator(edge_attr, 1, dt)
         va = io.up(vertex_attr, dt)
-        rt.unpack(va, [(0, 1)], outs=[op.local("v0")])
-        op.publish("v0")
-        res, b_out, y_out = op.power_method(self.num_iter, "v0")      # res = [lambda, n, n_A] (fp64, device)
+        ent = op.entry()
+        rt.unpack(va, [(0, 1)], outs=[op.local(ent)])
+        op.publish(ent)
+        res, b_out, y_out = op.power_method(self.num_iter, ent)       # res = [lambda, n, n_A] (fp64, device)
         g_dev = io.up(g).to(torch.float64)
         norm = res[1] if self.num_iter > 0 else g_dev[0]
         g_out = torch.stack([norm, res[2], res[0]]).to(g.dtype if g.dtype.is_floating_point else dt)
-        op.load("v0", b_out)                       # the message column gathers the normalised iterate,
-        op.acquire("v0")                           # halo rows included
-        e_out = rt.with_messages(op.plan, op.vals, op.vec["v0"])
+        op.load(ent, b_out)                        # the message column gathers the normalised iterate,
+        op.acquire(ent)                            # halo rows included
+        e_out = rt.with_messages(op.plan, op.vals, op.vec[ent])
         v_out = rt.pack([b_out, y_out])
         return io.down(v_out), io.down(e_out), io.down(g_out)
 

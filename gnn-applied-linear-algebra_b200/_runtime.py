@@ -262,12 +262,27 @@ def slot_order(plan, per_edge, dtype=None):
     return get_vals(plan, per_edge.view(-1, 1) if per_edge.dim() == 1 else per_edge, 0, dtype)
 
 
+_scalar_cache = {}
+
+
 def scalar(value, device, dtype):
     """A 1-element device tensor holding `value` (python number or 0-d/1-element tensor),
-    rounded to `dtype` the way torch rounds a 0-d operand of a tensor op.  No host sync."""
+    rounded to `dtype` the way torch rounds a 0-d operand of a tensor op.  Device tensors stay on
+    the device (no sync); host values are uploaded once per distinct (value, dtype, device) and
+    cached -- a layer's omega is the same number call after call, and an upload from pageable
+    memory per call costs more host time than the kernels it parameterises."""
     if isinstance(value, torch.Tensor):
-        return value.reshape(-1)[:1].to(device=device, dtype=dtype, non_blocking=True)
-    return torch.tensor([value], dtype=dtype).to(device, non_blocking=True)
+        if value.is_cuda:
+            return value.reshape(-1)[:1].to(device=device, dtype=dtype, non_blocking=True)
+        value = value.reshape(-1)[0].item()
+    key = (float(value), str(device), dtype)
+    hit = _scalar_cache.get(key)
+    if hit is None:
+        if len(_scalar_cache) > 256:
+            _scalar_cache.clear()
+        hit = torch.tensor([value], dtype=dtype).to(device)
+        _scalar_cache[key] = hit
+    return hit
 
 
 _workspaces = {}

@@ -396,8 +396,10 @@ class DistOperator:
     torch.distributed: NCCL on GPUs; the same HaloPlan logic is what tests/test_dist_cpu.py
     exercises with gloo)."""
 
+    ENTRY = ("v0", "v1")      # vectors a caller loads / publishes; never overwritten by the steps below
+
     def __init__(self, local_edge_index, local_vals, halo, k=1, engine="peer", group=None, n_rows=None,
-                 names=("v0", "va", "vb")):
+                 names=("v0", "v1", "va", "vb")):
         """n_rows: number of local ROWS when it differs from the local length of the gathered
         vector (rectangular operators: restriction / prolongation); such operators are applied
         with apply_rect() (stand-alone wait, whole-block kernel), not with the fused steps."""
@@ -423,6 +425,17 @@ class DistOperator:
         self.side = torch.cuda.Stream(self.device) if (self.peer is not None and local_vals.is_cuda) else None
         import os
         self.multi_sweep = os.environ.get("GLAB_DIST_MS", "1") != "0"
+        self._entry = 0
+
+    def entry(self):
+        """Name of the vector the next layer call loads its input into: "v0" and "v1" alternate.
+        A step that only READS a gathered vector (residual, Rayleigh quotient, the message column)
+        pushes nothing back, so the neighbours get no signal that this rank is done with that
+        vector's halo tail.  With alternating entry vectors a neighbour overwrites a tail only two
+        layer calls later, and it cannot get there without having received this rank's publish of the
+        call in between -- which is stream-ordered behind every kernel of the earlier call."""
+        self._entry ^= 1
+        return self.ENTRY[self._entry]
 
     # -- halo plumbing -----------------------------------------------------------------------
     def publish(self, name):
@@ -514,9 +527,9 @@ class DistOperator:
         if self.engine == "peer" and self.halo.part.world > 1 and self.multi_sweep and n_iters > 1:
             # One launch for all sweeps (glab_jacobi_sweeps_halo_*).  The multi-sweep kernel overwrites both
             # of its buffers, so a start vector that must stay intact ("v0") takes one ordinary sweep first.
-            if cur == "v0":
-                xin, xout = self.vec["v0"], self.vec["va"]
-                self.run_step("v0", lambda **kw: rt.jacobi(self.plan, self.vals, diag, b, xin, xout, omega_dev, **kw),
+            if cur in self.ENTRY:
+                xin, xout, first = self.vec[cur], self.vec["va"], cur
+                self.run_step(first, lambda **kw: rt.jacobi(self.plan, self.vals, diag, b, xin, xout, omega_dev, **kw),
                               "va")
                 cur, todo = "va", todo - 1
             if todo > 1:
@@ -550,7 +563,7 @@ class DistOperator:
         # p ping-pongs between two named vectors, never `start` if that is "v0" (kept intact so
         # that the same start vector can be reused by the next call)
         other = "va" if start != "va" else "vb"
-        second = "vb" if start == "v0" else start
+        second = "vb" if start in self.ENTRY else start
         xin = self.vec[start]
         x = torch.empty(n, k, dtype=self.dtype, device=self.device) if x is None else x
         r = torch.empty_like(x) if r is None else r

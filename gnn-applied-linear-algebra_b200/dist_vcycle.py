@@ -102,6 +102,11 @@ class DistTwoGrid:
         self.cur = A.jacobi(self.n_post, self.diag, b_local, self.w, cur)                # :229-231
         return self.x_local()
 
+    def check(self):
+        """Raise if a bounded in-kernel wait of any fused step gave up (synchronises)."""
+        for o in (self.A, self.Ac, self.P, self.PT):
+            o.check()
+
     def close(self):
         for o in (self.A, self.Ac, self.P, self.PT):
             o.close()
