@@ -25,8 +25,17 @@ from .dist import DistOperator, RowPartition, partition_coo
 class DistTwoGrid:
     def __init__(self, edge_index, edge_val, k, rank, world, engine="peer", splitting=None, group=None,
                  n_pre=3, n_post=3):
+        import time
         dev = edge_val.device
         n = int(edge_index[0].max().item()) + 1
+        t_ = [time.perf_counter()]
+
+        def lap(name):
+            torch.cuda.synchronize()
+            t_.append(time.perf_counter())
+            self.setup_times[name] = t_[-1] - t_[-2]
+
+        self.setup_times = {}
         self.rank, self.world, self.k, self.group = rank, world, k, group
         self.n_pre, self.n_post = n_pre, n_post
         # ---- replicated setup (single-GPU code path, whole operator)
@@ -35,6 +44,7 @@ class DistTwoGrid:
         op = V._operator(A)
         tg = V._two_grid(A, splitting)
         cop = V._operator(tg.Ac)
+        lap("replicated_setup_soc_interp_galerkin")
         split = V.default_splitting(n, dev) if splitting is None else splitting.to(dev).reshape(-1)
         coarse = split > 0
         new_id = torch.cumsum(coarse.to(torch.int64), 0)          # number of coarse points with index <= i
@@ -50,9 +60,12 @@ class DistTwoGrid:
         self.dtype = dt
         # ---- row blocks
         ai, av, ah = partition_coo(op.edge_index, op.edge_attr, self.fine, rank, group)
+        lap("partition_A")
         self.A = DistOperator(ai, av.contiguous(), ah, k=k, engine=engine, group=group)
+        lap("operator_A")
         ci, cv, ch = partition_coo(cop.edge_index, cop.edge_attr, self.coarse, rank, group)
         self.Ac = DistOperator(ci, cv.contiguous(), ch, k=k, engine=engine, group=group)
+        lap("partition_and_operator_Ac")
         P = tg.P
         pidx, pval = P.indices(), P.values().reshape(-1, 1)
         pi, pv, ph = partition_coo(pidx, pval, self.fine, rank, group, col_part=self.coarse)
@@ -60,6 +73,7 @@ class DistTwoGrid:
         tidx = torch.stack([pidx[1], pidx[0]])
         ti, tv, th = partition_coo(tidx, pval, self.coarse, rank, group, col_part=self.fine)
         self.PT = DistOperator(ti, tv.contiguous(), th, k=k, engine=engine, group=group, n_rows=self.ncl, names=("g",))
+        lap("partition_and_operators_P_PT")
         self.nnz = {"A": int(op.edge_index.shape[1]), "P": int(pidx.shape[1]), "Ac": int(cop.edge_index.shape[1])}
         # ---- per-rank data of the cycle
         self.diag = op.diag.to(dt).reshape(-1)[f0:f1].contiguous()
