@@ -63,16 +63,20 @@ class _Operator:
 
 
 _operators = {}
+_MAX_OPERATORS = 32
 
 
 def _operator(A):
     key = id(A)
     hit = _operators.get(key)
     if hit is not None and hit[0]() is A and hit[2] == A._version:
+        _operators[key] = _operators.pop(key)       # most recently used last
         return hit[1]
     op = _Operator(A)
-    if len(_operators) > 8:
-        _operators.clear()
+    for k_ in [k_ for k_, v_ in _operators.items() if v_[0]() is None]:     # operators whose tensor died
+        del _operators[k_]
+    while len(_operators) >= _MAX_OPERATORS:                                # least recently inserted / used first
+        del _operators[next(iter(_operators))]
     _operators[key] = (weakref.ref(A), op, A._version)
     return op
 
@@ -184,12 +188,26 @@ class _TwoGrid:
 
 def _two_grid(A, splitting, coarse_rows="reference"):
     op = _operator(A)
-    key = ("two_grid", coarse_rows) if splitting is None else ("two_grid", coarse_rows, splitting.data_ptr(),
-                                                              splitting._version)
-    tg = op.hierarchy.get(key)
-    if tg is None:
-        tg = _TwoGrid(A, splitting, coarse_rows)
-        op.hierarchy[key] = tg
+    if splitting is None:
+        key = ("two_grid", coarse_rows)
+        tg = op.hierarchy.get(key)
+        if tg is None:
+            tg = _TwoGrid(A, splitting, coarse_rows)
+            op.hierarchy[key] = tg
+        return tg
+    # A caller-supplied splitting: an entry is valid only for the SAME CONTENT.  Tensors filled through
+    # raw pointers (runCFSplit) never bump _version, and a freed tensor's address is recycled by the caching
+    # allocator, so neither the address nor the version identifies it: keep a private copy and compare.
+    entries = op.hierarchy.setdefault(("two_grid_split", coarse_rows), [])
+    flat = splitting.detach().reshape(-1)
+    for saved, tg in entries:
+        if saved.shape == flat.shape and saved.dtype == flat.dtype and saved.device == flat.device and \
+                torch.equal(saved, flat):
+            return tg
+    tg = _TwoGrid(A, splitting, coarse_rows)
+    entries.append((flat.clone(), tg))
+    if len(entries) > 4:
+        entries.pop(0)
     return tg
 
 
@@ -246,6 +264,44 @@ def runVCycle(A, b, x, n_presmooth, n_postsmooth, n_coarsesolve, use_jacobi=True
     rt.spmm_add(tg.plan_P, tg.vals_P, xc, cur, other)                                                    # :226  x + P xc
     res = _jacobi_inplace(f["plan_A"], f["vals_A"], f["diag"], bd, other, cur, f["w"], n_postsmooth)     # :229-231
     return _back(b, res.clone())
+
+
+def _ml_hierarchy(A, **options):
+    from .multilevel import Hierarchy
+    op = _operator(A)
+    key = ("ml",) + tuple(sorted(options.items()))
+    h = op.hierarchy.get(key)
+    if h is None:
+        h = Hierarchy(A, **options)
+        op.hierarchy[key] = h
+    return h
+
+
+def runVCycleML(A, b, x, n_presmooth=3, n_postsmooth=3, gamma=2, **options):
+    """One cycle of the RECURSIVE multilevel hierarchy (BASELINE configs[4]: "VCycle multilevel (Jacobi
+    smoother + interpolation)"); returns the new x.  Extension of runVCycle: same Jacobi smoother,
+    residual, restriction / prolongation and Galerkin coarse operators, but on a smoothed-aggregation
+    hierarchy down to a dense-inverted coarsest operator instead of one Chebyshev-"solved" coarse
+    grid, W-cycling (gamma = 2) on the coarse levels -- see multilevel.py.  The hierarchy is built on
+    the device on the first call and cached with the operator; options: theta, omega_p, jacobi_weight,
+    power_iters, coarsest_n, max_levels, seed."""
+    h = _ml_hierarchy(A, **options)
+    lev0 = h.levels[0]
+    bd = rt.dense(rt.to_device(b, lev0.device).to(lev0.dtype))
+    xd = rt.dense(rt.to_device(x, lev0.device).to(lev0.dtype))
+    return _back(b, h.cycle(bd, xd, n_presmooth, n_postsmooth, gamma))
+
+
+def hierarchy_info(A, which="two_grid", n_presmooth=3, n_postsmooth=3, gamma=2, **options):
+    """Sizes / work of the cached hierarchy of A ("two_grid": runVCycle, "multilevel": runVCycleML)."""
+    if which == "multilevel":
+        return _ml_hierarchy(A, **options).info(n_presmooth, n_postsmooth, gamma)
+    op = _operator(A)
+    tg = _two_grid(A, None)
+    z, zp, zc = int(op.edge_index.shape[1]), tg.plan_P.nnz, int(tg.Ac._nnz())
+    return {"levels": 2, "rows_per_level": [op.n, int(tg.P.shape[1])], "nnz_per_level": [z, zc], "nnz_P": zp,
+            "spmv_nnz_per_cycle": (n_presmooth + n_postsmooth + 1) * z + 2 * zp + cheb_deg * zc,
+            "cycle": "two-grid, Chebyshev degree %d coarse solve (VCycle.py:221-223)" % cheb_deg}
 
 
 def _runVCycle_layers(A, b, x, n_presmooth, n_postsmooth, n_coarsesolve, use_jacobi=True, splitting=None):
