@@ -108,6 +108,7 @@ for _suf, _ct in (("f32", c_float), ("f64", c_double)):
     _sig("glab_segment_max_" + _suf, c_int, P, P, P, P)
     _sig("glab_segment_min_" + _suf, c_int, P, P, P, P)
     _sig("glab_segment_mean_" + _suf, c_int, P, P, _INT, P, P)
+    _sig("glab_segment_agg4_" + _suf, c_int, P, P, _INT, P, P)
     _sig("glab_soc_classic_" + _suf, c_int, P, P, _ct, P, P, P)
     _sig("glab_soc_sa_" + _suf, c_int, P, P, P, P, P)
     _sig("glab_direct_interp_" + _suf, c_int, P, P, P, P, P, P, P)

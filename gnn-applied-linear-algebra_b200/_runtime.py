@@ -531,29 +531,70 @@ def segment_mean(plan, src_slots, out=None):
     return out
 
 
-def scatter(src, index, dim=0, dim_size=None, reduce="sum"):
-    """torch_scatter.scatter(src, index, dim=0, dim_size=n, reduce=sum|max|min|mean) on the GPU:
-    the reference's seam as a drop-in function (index = edgeij_pair[0])."""
-    if dim != 0:
-        raise GlabError("only dim=0 (aggregation over edges) is supported")
+_scatter_plans = _Cache(16)
+
+
+def _index_plan(index, n):
+    """Plan that groups by `index` (edgeij_pair[0] for edge -> vertex aggregation, the `batch` vector
+    of a batch of graphs for vertex / edge -> graph aggregation), cached per index tensor."""
+    plan = _scatter_plans.get(index, (n,))
+    if plan is None:
+        device = compute_device(index)
+        idx = to_device(index, device).reshape(-1).to(torch.int64)
+        ei = torch.stack([idx, torch.zeros_like(idx)]).contiguous()
+        plan = Plan.from_coo(ei, n, 1)
+        _scatter_plans.put(index, plan, (n,))
+    return plan
+
+
+def _slots(plan, src2):
+    """[z, F] rows of src in CSR slot order (zero-copy when the index was already sorted)."""
+    if plan.identity:
+        return src2.contiguous()
+    perm = plan.csr()[2]
+    return src2.index_select(0, perm.long()).contiguous()
+
+
+def aggregate4(src, index, dim_size=None):
+    """cat([scatter(min), scatter(mean), scatter(sum), scatter(max)], 1) of the reference's 4-way
+    aggregations (TrainableJacobiGNN.py:53-70, LearnDiffusionCoeffs.py:291-342) in ONE kernel pass:
+    src [z, F] (F <= 64), index [z] -> [n, 4 F].  `index` may be edgeij_pair[0] or a `batch` vector."""
     device = compute_device(src, index)
     host = not src.is_cuda
-    idx = to_device(index, device)
-    n = int(dim_size) if dim_size is not None else (int(idx.max().item()) + 1 if idx.numel() else 0)
-    ei = torch.stack([idx, torch.zeros_like(idx)]).contiguous()
-    plan = Plan.from_coo(ei, n, 1)
+    n = int(dim_size) if dim_size is not None else (int(index.max().item()) + 1 if index.numel() else 0)
+    plan = _index_plan(index, n)
     s2 = to_device(src, device)
     s2 = s2.view(-1, 1) if s2.dim() == 1 else s2
-    slots = torch.stack([get_vals(plan, s2, j) for j in range(s2.shape[1])], 1).contiguous()
-    if reduce in ("sum", "add"):
-        out = segment_sum(plan, slots)
-    elif reduce == "mean":
-        out = segment_mean(plan, slots)
-    elif reduce in ("max", "min"):
-        fn = segment_max if reduce == "max" else segment_min
-        out = torch.stack([fn(plan, slots[:, j].contiguous()) for j in range(slots.shape[1])], 1)
-    else:
+    F = s2.shape[1]
+    slots = _slots(plan, s2)
+    out = torch.empty((n, 4 * F), dtype=s2.dtype, device=device)
+    _call("segment_agg4", s2.dtype, device, plan.handle, ptr(slots), F, ptr(out), stream_ptr())
+    return out.cpu() if host else out
+
+
+def scatter(src, index, dim=0, dim_size=None, reduce="sum"):
+    """torch_scatter.scatter(src, index, dim=0, dim_size=n, reduce=sum|max|min|mean) on the GPU:
+    the reference's seam as a drop-in function (index = edgeij_pair[0], or a `batch` vector).  The
+    plan is cached per index tensor; any number of feature columns in one launch."""
+    if dim != 0:
+        raise GlabError("only dim=0 (aggregation over edges) is supported")
+    if reduce not in ("sum", "add", "mean", "max", "min"):
         raise GlabError("unknown reduce %r" % (reduce,))
+    device = compute_device(src, index)
+    host = not src.is_cuda
+    n = int(dim_size) if dim_size is not None else (int(index.max().item()) + 1 if index.numel() else 0)
+    plan = _index_plan(index, n)
+    s2 = to_device(src, device)
+    s2 = s2.view(-1, 1) if s2.dim() == 1 else s2
+    F = s2.shape[1]
+    slots = _slots(plan, s2)
+    if reduce in ("sum", "add", "mean") and F in SUPPORTED_K and plan.max_row_nnz <= 64:
+        out = (segment_sum if reduce != "mean" else segment_mean)(plan, slots)
+    else:
+        all4 = torch.empty((n, 4 * F), dtype=s2.dtype, device=device)
+        _call("segment_agg4", s2.dtype, device, plan.handle, ptr(slots), F, ptr(all4), stream_ptr())
+        block = {"min": 0, "mean": 1, "sum": 2, "add": 2, "max": 3}[reduce]
+        out = all4[:, block * F:(block + 1) * F].contiguous()
     out = out.view(-1) if src.dim() == 1 else out
     return out.cpu() if host else out
 

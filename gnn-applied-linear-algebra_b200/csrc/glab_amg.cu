@@ -235,9 +235,128 @@ static int segment_reduce(const glab_plan* p, const T* src, int k, T* out, void*
   return (int)cudaGetLastError();
 }
 
+// ------------------------------------------------------------------------------------------
+// Fused 4-way aggregation  out[i, :] = [min | mean | sum | max] over the row's slots of src[slot, 0..F)
+// in ONE pass over src (TrainableJacobiDiag/TrainableJacobiGNN.py:53-70 and
+// DiffCoeffs/LearnDiffusionCoeffs.py:291-342 call torch_scatter.scatter four times on the same
+// tensor; their `batch` vector -- vertex or edge -> graph id of a batch of small graphs -- is just
+// another sorted index with LONG segments).  Two paths:
+//   thread per (row, feature)   short rows (edge -> vertex aggregation): sequential in edge order, so
+//                               sum / mean are bit-identical to scatter_add_ on the CPU;
+//   warp per row                long rows (vertex / edge -> graph aggregation of batched graphs): lanes
+//                               stride over the row (coalesced), shuffle reduction; min / max stay exact,
+//                               sum / mean add in a fixed (launch-independent) but different order.
+// amin / amax propagate NaN like torch; empty rows give 0 in every block, like torch_scatter.
+// ------------------------------------------------------------------------------------------
+template <typename T> struct Agg4 {
+  T mn, mx, s;
+  bool any;
+  __device__ __forceinline__ void init() { mn = mx = s = T(0); any = false; }
+  __device__ __forceinline__ void add(T v) {
+    if (!any) { mn = mx = v; any = true; }
+    else {
+      if (v < mn || v != v) mn = (mn != mn) ? mn : v;
+      if (v > mx || v != v) mx = (mx != mx) ? mx : v;
+    }
+    s = s + v;
+  }
+  __device__ __forceinline__ void merge(const Agg4& o) {   // min / max only (NaN sticks)
+    if (!o.any) return;
+    if (!any) { mn = o.mn; mx = o.mx; any = true; return; }
+    if (o.mn < mn || o.mn != o.mn) mn = (mn != mn) ? mn : o.mn;
+    if (o.mx > mx || o.mx != o.mx) mx = (mx != mx) ? mx : o.mx;
+  }
+};
+
+template <typename T>
+__global__ void k_segment_agg4_thread(const int32_t* __restrict__ rowptr, const T* __restrict__ src, int F,
+                                      int64_t n_rows, T* __restrict__ out) {
+  const int64_t total = n_rows * F;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = i / F;
+    const int f = (int)(i - r * F);
+    const int rs = __ldg(rowptr + r), re = __ldg(rowptr + r + 1);
+    Agg4<T> a;
+    a.init();
+    for (int j = rs; j < re; ++j) a.add(__ldg(src + (size_t)j * F + f));
+    const T cnt = (T)(re - rs > 0 ? re - rs : 1);
+    T* o = out + (size_t)r * 4 * F;
+    o[f] = a.mn;
+    o[F + f] = a.s / cnt;
+    o[2 * F + f] = a.s;
+    o[3 * F + f] = a.mx;
+  }
+}
+
+template <typename T>
+__global__ void k_segment_agg4_warp(const int32_t* __restrict__ rowptr, const T* __restrict__ src, int F,
+                                    int64_t n_rows, T* __restrict__ out) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp0 = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t r = warp0; r < n_rows; r += nwarps) {
+    const int rs = __ldg(rowptr + r), re = __ldg(rowptr + r + 1);
+    const int64_t e0 = (int64_t)rs * F, e1 = (int64_t)re * F;   // the row is one contiguous run of src
+    for (int f = 0; f < F; ++f) {
+      Agg4<T> a;
+      a.init();
+      double s = 0.0;    // lane-partial sums in fp64, combined in a fixed order
+      for (int64_t e = e0 + f + (int64_t)lane * F; e < e1; e += 32 * (int64_t)F) {
+        const T v = __ldg(src + e);
+        a.add(v);
+        s += (double)v;
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        Agg4<T> b;
+        b.mn = __shfl_xor_sync(0xffffffffu, a.mn, o);
+        b.mx = __shfl_xor_sync(0xffffffffu, a.mx, o);
+        b.any = __shfl_xor_sync(0xffffffffu, (int)a.any, o) != 0;
+        b.s = T(0);
+        a.merge(b);
+        s += __shfl_xor_sync(0xffffffffu, s, o);
+      }
+      if (lane == 0) {
+        const T cnt = (T)(re - rs > 0 ? re - rs : 1);
+        T* o = out + (size_t)r * 4 * F;
+        const T sum = (T)s;
+        o[f] = a.mn;
+        o[F + f] = sum / cnt;
+        o[2 * F + f] = sum;
+        o[3 * F + f] = a.mx;
+      }
+    }
+  }
+}
+
+template <typename T>
+static int segment_agg4(const glab_plan* p, const T* src, int F, T* out, void* stream) {
+  if (!p || !out || F < 1 || F > 64 || (p->nnz > 0 && !src)) return GLAB_E_ARG;
+  if (p->n_rows == 0) return 0;
+  cudaStream_t st = as_stream(stream);
+  const int64_t capb = (int64_t)p->sm_count * 32;
+  if (p->max_row_nnz > 64) {
+    int64_t b = (p->n_rows * 32 + 255) / 256;
+    const int grid = (int)(b < capb ? b : capb);
+    k_segment_agg4_warp<T><<<grid, 256, 0, st>>>(p->rowptr, src, F, p->n_rows, out);
+  } else {
+    int64_t b = (p->n_rows * F + 255) / 256;
+    const int grid = (int)(b < capb ? b : capb);
+    k_segment_agg4_thread<T><<<grid, 256, 0, st>>>(p->rowptr, src, F, p->n_rows, out);
+  }
+  return (int)cudaGetLastError();
+}
+
 }  // namespace glab
 
 using namespace glab;
+
+extern "C" int glab_segment_agg4_f32(const glab_plan* p, const float* src, int F, float* out, void* s) {
+  return segment_agg4<float>(p, src, F, out, s);
+}
+extern "C" int glab_segment_agg4_f64(const glab_plan* p, const double* src, int F, double* out, void* s) {
+  return segment_agg4<double>(p, src, F, out, s);
+}
 
 #define GLAB_AMG_INST(SUF, T)                                                                      \
   extern "C" int glab_soc_classic_##SUF(const glab_plan* p, const T* v, T theta, T* S, T* rowmax,  \

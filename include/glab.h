@@ -253,6 +253,17 @@ int glab_segment_min_f64(const glab_plan*, const double* src_slots, double* out,
 int glab_segment_mean_f32(const glab_plan*, const float* src_slots, int k, float* out, void* stream);
 int glab_segment_mean_f64(const glab_plan*, const double* src_slots, int k, double* out, void* stream);
 
+/* The 4-way aggregation in ONE pass: out[i, :] = [min | mean | sum | max] (F columns each, out is
+ * [n_rows, 4 F]) over the slots of row i of src [nnz, F] (F <= 64, CSR slot order) -- what
+ * TrainableJacobiDiag/TrainableJacobiGNN.py:53-70 and DiffCoeffs/LearnDiffusionCoeffs.py:291-342
+ * compute with four torch_scatter.scatter calls.  The plan's rows are whatever the index groups by:
+ * vertices (edge -> vertex aggregation) or the graphs of a batch (the reference's `batch` vector:
+ * vertex / edge -> graph aggregation; long segments).  Rows of at most 64 slots are reduced
+ * sequentially in edge order (sum / mean bit-identical to scatter_add_); longer rows by one warp each
+ * (min / max exact, sum / mean in a fixed but different order).  Empty rows give 0. */
+int glab_segment_agg4_f32(const glab_plan*, const float* src_slots, int F, float* out, void* stream);
+int glab_segment_agg4_f64(const glab_plan*, const double* src_slots, int F, double* out, void* stream);
+
 /* out_edges[e, 0] = A_ij and out_edges[e, 1..k] = A_ij * x_j in ONE pass: the reference layers'
  * returned edge_attr = torch.cat([A_ij, c_ij], 1) (MatVecGNN.py:84, JacobiGNN.py:88,
  * ChebyGNN.py:70,183, PowerMethodGNN.py:106).  out_edges is [nnz, ld], ld >= 1 + k. */
