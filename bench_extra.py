@@ -435,6 +435,8 @@ def config5_vcycle(G, dev, rank, world, peak, N=8192, k=8, cycles=3, cpu_baselin
                 variants[name]["value_nnz_columns_per_s"] = work * k / (min(ts) * 1e-3)
             if name == "two_grid":
                 x_tg = xx
+            else:
+                x_ml = xx
         out["variants"] = variants
         out["nnz_A"] = z
         # ---- parity (two-grid cycle): independent fp64 residual of the returned x, and column == single-RHS run
@@ -450,70 +452,103 @@ def config5_vcycle(G, dev, rank, world, peak, N=8192, k=8, cycles=3, cpu_baselin
                          "column_equals_single_rhs_run_bitwise": col_equal,
                          "against": "fp64 shifted-slice residual b - A x of the returned iterate (all rows, all columns); "
                                     "column 3 of the 8-column run vs the same cycles run on that column alone"}
+        if "multilevel" in variants:
+            r_gpu = V.runResidual(A, b, x_ml)
+            r_ref = b.double().view(N, N, k) - grid_stencil_5pt(x_ml.double().view(N, N, k))
+            e_ml = relerr(r_gpu, r_ref.view(n, k))
+            rate = max(variants["multilevel"]["worst_column_reduction_per_cycle"][1:])
+            out["parity"]["multilevel_residual_rel_err"] = e_ml
+            out["parity"]["multilevel_worst_reduction_after_first_cycle"] = rate
+            out["parity"]["ok"] = bool(out["parity"]["ok"] and e_ml <= 10 * TOL32 and rate <= 0.5)
+            del x_ml
         if cpu_baseline:
             out["cpu_baseline"] = _cpu_vcycle(64)
         del A, b, x, xx, x_tg, r_gpu, r_ref, x1, b1
+        G.VCycle._operators.clear()
     else:
         from glab_b200.dist_vcycle import DistTwoGrid
+        from glab_b200.dist_multilevel import DistMultilevel
         ei, ev = G.UtilsGNN.laplacianfun_torch(N, device=dev)
-        tg = DistTwoGrid(ei, ev, k, rank, world, engine=os.environ.get("GLAB_DIST_ENGINE", "peer"))
-        torch.cuda.synchronize()
-        out["setup_s"] = time.perf_counter() - t0
-        out["setup_breakdown_s"] = getattr(tg, "setup_times", None)
-        f0, f1 = tg.fine.bounds(rank)
-        b = hashed_uniform(f0, f1, 5, dev, cols=k)
-        tg.load_x(torch.zeros(f1 - f0, k, device=dev))
-
-        def rnorm():
-            r = tg.residual_local(b)
-            s_ = (r.double() ** 2).sum(0)
-            dist.all_reduce(s_)
-            return torch.sqrt(s_)
-
-        norms = [rnorm()]
-        tg.cycle(b)
-        norms.append(rnorm())
-        ts = []
-        for _ in range(cycles):
+        A_full = torch.sparse_coo_tensor(ei, ev.flatten().float(), (n, n))
+        engine = os.environ.get("GLAB_DIST_ENGINE", "peer")
+        variants, par = {}, {}
+        for name in (["two_grid", "multilevel"] if multilevel is not False else ["two_grid"]):
+            t1 = time.perf_counter()
+            if name == "two_grid":
+                tg = DistTwoGrid(ei, ev, k, rank, world, engine=engine)
+                part0 = tg.fine
+                work = 7 * tg.nnz["A"] + 2 * tg.nnz["P"] + 4 * tg.nnz["Ac"]
+                extra_info = {"nnz_A": tg.nnz["A"], "nnz_P": tg.nnz["P"], "nnz_Ac": tg.nnz["Ac"]}
+            else:
+                tg = DistMultilevel(A_full, k, rank, world, engine=engine)
+                part0 = tg.parts[0]
+                extra_info = tg.info()
+                work = extra_info["spmv_nnz_per_cycle"]
             torch.cuda.synchronize()
-            dist.barrier()
-            a, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            a.record()
+            setup_s = time.perf_counter() - t1
+            f0, f1 = part0.bounds(rank)
+            b = hashed_uniform(f0, f1, 5, dev, cols=k)
+            tg.load_x(torch.zeros(f1 - f0, k, device=dev))
+
+            def rnorm():
+                r = tg.residual_local(b)
+                s_ = (r.double() ** 2).sum(0)
+                dist.all_reduce(s_)
+                return torch.sqrt(s_)
+
+            norms = [rnorm()]
             tg.cycle(b)
-            e.record()
-            torch.cuda.synchronize()
-            dist.barrier()
-            ts.append(a.elapsed_time(e))
             norms.append(rnorm())
-        t = torch.tensor([min(ts)], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms = float(t.item())
-        work = 7 * tg.nnz["A"] + 2 * tg.nnz["P"] + 4 * tg.nnz["Ac"]
-        out["variants"] = {"two_grid": {"ms_per_cycle": ms, "spmv_nnz_per_cycle": work,
-                                        "value_nnz_columns_per_s": work * k / (ms * 1e-3),
-                                        "residual_norm_col0": [float(v_[0]) for v_ in norms],
-                                        "worst_column_reduction_per_cycle":
-                                            [float((norms[i + 1] / norms[i]).max().item()) for i in range(len(norms) - 1)]}}
-        out["nnz_A"], out["nnz_P"], out["nnz_Ac"] = tg.nnz["A"], tg.nnz["P"], tg.nnz["Ac"]
-        # ---- parity: the partitioned iterate after these cycles == the single-GPU cycle on rank 0, bit for bit
-        xl = tg.x_local().contiguous()
-        full = [torch.empty(tg.fine.bounds(q)[1] - tg.fine.bounds(q)[0], k, device=dev) for q in range(world)] \
-            if rank == 0 else None
-        dist.gather(xl, full, dst=0)
-        tg.check()
-        if rank == 0:
-            A = torch.sparse_coo_tensor(ei, ev.flatten().float(), (n, n))
-            b_all = hashed_uniform(0, n, 5, dev, cols=k)
-            xr = torch.zeros(n, k, device=dev)
-            for _ in range(cycles + 1):
-                xr = G.VCycle.runVCycle(A, b_all, xr, 3, 3, 5, True)
-            got = torch.cat(full)
-            out["parity"] = {"ok": bool(torch.equal(got, xr)), "bit_exact": True,
+            ts = []
+            for _ in range(cycles):
+                torch.cuda.synchronize()
+                dist.barrier()
+                a, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record()
+                tg.cycle(b)
+                e.record()
+                torch.cuda.synchronize()
+                dist.barrier()
+                ts.append(a.elapsed_time(e))
+                norms.append(rnorm())
+            t = torch.tensor([min(ts)], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+            variants[name] = {"ms_per_cycle": ms, "spmv_nnz_per_cycle": int(work),
+                              "value_nnz_columns_per_s": work * k / (ms * 1e-3), "setup_s": setup_s,
+                              "setup_breakdown_s": getattr(tg, "setup_times", None),
+                              "residual_norm_col0": [float(v_[0]) for v_ in norms],
+                              "worst_column_reduction_per_cycle":
+                                  [float((norms[i + 1] / norms[i]).max().item()) for i in range(len(norms) - 1)],
+                              **extra_info}
+            # ---- parity: the partitioned iterate after these cycles == the single-GPU cycle on rank 0, bit for bit
+            xl = tg.x_local().contiguous()
+            full = [torch.empty(part0.bounds(q)[1] - part0.bounds(q)[0], k, device=dev) for q in range(world)] \
+                if rank == 0 else None
+            dist.gather(xl, full, dst=0)
+            tg.check()
+            tg.close()
+            del tg
+            _free()
+            if rank == 0:
+                b_all = hashed_uniform(0, n, 5, dev, cols=k)
+                xr = torch.zeros(n, k, device=dev)
+                for _ in range(cycles + 1):
+                    xr = G.VCycle.runVCycle(A_full, b_all, xr, 3, 3, 5, True) if name == "two_grid" else \
+                        G.VCycle.runVCycleML(A_full, b_all, xr, 3, 3)
+                got = torch.cat(full)
+                par[name] = {"ok": bool(torch.equal(got, xr)), "bit_exact": True,
                              "max_abs": float((got - xr).abs().max().item()),
-                             "against": "VCycle.runVCycle on ONE GPU (rank 0) for the same %d cycles, all rows and columns" % (cycles + 1)}
-            del A, b_all, xr, got
-        tg.close()
-        del ei, ev, b
+                             "against": "VCycle.%s on ONE GPU (rank 0) for the same %d cycles, all rows and columns"
+                                        % ("runVCycle" if name == "two_grid" else "runVCycleML", cycles + 1)}
+                del b_all, xr, got
+                G.VCycle._operators.clear()
+                _free()
+            dist.barrier()
+        out["variants"] = variants
+        if rank == 0:
+            out["parity"] = {"ok": all(p_["ok"] for p_ in par.values()), **par}
+        del ei, ev, b, A_full
     _free()
     return out
 
