@@ -132,10 +132,7 @@ class DistMultilevel:
                 off += cnt
         else:
             bufs[l0]["b"].copy_(self.rep_send[:self.nrep])
-        visits = self.gamma if l0 < len(self.h.levels) - 1 else 1
-        for g in range(visits):
-            self.h._visit(l0, bufs, self.n_pre, self.n_post, self.gamma, zero_guess=(g == 0))
-        return bufs[l0]["x"][0]
+        return self.h.run_from(l0, self.k, self.n_pre, self.n_post, self.gamma, first_zero=True)
 
     def _visit(self, l, b_local, zero_guess):
         D = self.lev[l]

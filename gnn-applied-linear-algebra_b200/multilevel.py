@@ -157,6 +157,7 @@ class Hierarchy:
         last.inv_plan = rt.Plan.from_csr(rowptr, colidx, nn_, nn_)
         last.inv_vals = inv.reshape(-1)
         self.buffers = {}
+        self.graphs = {}
 
     # ------------------------------------------------------------------ the cycle
     def _bufs(self, k):
@@ -190,14 +191,51 @@ class Hierarchy:
         if res is not xs[0]:
             xs[0].copy_(res)
 
+    def run_from(self, l0, k, n_pre, n_post, gamma, first_zero):
+        """The part of a cycle rooted at level l0 (right-hand side in the level's "b" buffer, result in
+        its "x"[0] buffer), as many visits as the W-cycle makes there.  The coarse levels are launch-bound
+        -- a W-cycle on 7 levels is ~50 level visits of ~8 tiny kernels -- so the whole sequence is captured
+        once per (l0, k, sweeps, gamma) in a CUDA graph and replayed (GLAB_ML_GRAPH=0: launch one by one)."""
+        import os
+        bufs = self._bufs(k)
+        visits = (gamma if l0 < len(self.levels) - 1 else 1) if l0 > 0 else 1
+
+        def body():
+            for g in range(visits):
+                self._visit(l0, bufs, n_pre, n_post, gamma, zero_guess=(first_zero and g == 0))
+
+        if os.environ.get("GLAB_ML_GRAPH", "1") == "0":
+            body()
+            return bufs[l0]["x"][0]
+        key = (l0, k, n_pre, n_post, gamma, first_zero)
+        gr = self.graphs.get(key)
+        if gr is None:
+            save_b = bufs[l0]["b"].clone()
+            save_x = bufs[l0]["x"][0].clone()
+            side = torch.cuda.Stream(self.levels[0].device)
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                body()                      # warm-up: lazy attribute setup of every kernel variant involved
+            torch.cuda.current_stream().wait_stream(side)
+            torch.cuda.synchronize()
+            bufs[l0]["b"].copy_(save_b)
+            bufs[l0]["x"][0].copy_(save_x)
+            gr = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(gr):
+                body()
+            self.graphs[key] = gr
+            bufs[l0]["b"].copy_(save_b)
+            bufs[l0]["x"][0].copy_(save_x)
+        gr.replay()
+        return bufs[l0]["x"][0]
+
     def cycle(self, b, x, n_pre=3, n_post=3, gamma=2):
         """One cycle on k = b.shape[1] right-hand sides; returns the new iterate (a fresh tensor)."""
         k = b.shape[1]
         bufs = self._bufs(k)
         bufs[0]["b"].copy_(b)
         bufs[0]["x"][0].copy_(x)
-        self._visit(0, bufs, n_pre, n_post, gamma, zero_guess=False)
-        return bufs[0]["x"][0].clone()
+        return self.run_from(0, k, n_pre, n_post, gamma, first_zero=False).clone()
 
     # ------------------------------------------------------------------ bookkeeping
     def info(self, n_pre=3, n_post=3, gamma=2):
