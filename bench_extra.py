@@ -453,13 +453,17 @@ def config5_vcycle(G, dev, rank, world, peak, N=8192, k=8, cycles=3, cpu_baselin
                          "against": "fp64 shifted-slice residual b - A x of the returned iterate (all rows, all columns); "
                                     "column 3 of the 8-column run vs the same cycles run on that column alone"}
         if "multilevel" in variants:
+            # (the iterate of a random right-hand side is ~N^2 larger than b, so r = b - A x cancels heavily in
+            # fp32: its error is measured against |A x|, the magnitude the subtraction works on)
             r_gpu = V.runResidual(A, b, x_ml)
-            r_ref = b.double().view(N, N, k) - grid_stencil_5pt(x_ml.double().view(N, N, k))
-            e_ml = relerr(r_gpu, r_ref.view(n, k))
+            ax = grid_stencil_5pt(x_ml.double().view(N, N, k))
+            r_ref = b.double().view(N, N, k) - ax
+            e_ml = float(((r_gpu.double() - r_ref.view(n, k)).norm() / ax.norm()).item())
+            del ax
             rate = max(variants["multilevel"]["worst_column_reduction_per_cycle"][1:])
-            out["parity"]["multilevel_residual_rel_err"] = e_ml
+            out["parity"]["multilevel_residual_err_rel_to_Ax"] = e_ml
             out["parity"]["multilevel_worst_reduction_after_first_cycle"] = rate
-            out["parity"]["ok"] = bool(out["parity"]["ok"] and e_ml <= 10 * TOL32 and rate <= 0.5)
+            out["parity"]["ok"] = bool(out["parity"]["ok"] and e_ml <= TOL32 and rate <= 0.5)
             del x_ml
         if cpu_baseline:
             out["cpu_baseline"] = _cpu_vcycle(64)
