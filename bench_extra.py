@@ -453,15 +453,13 @@ def config5_vcycle(G, dev, rank, world, peak, N=8192, k=8, cycles=3, cpu_baselin
                          "against": "fp64 shifted-slice residual b - A x of the returned iterate (all rows, all columns); "
                                     "column 3 of the 8-column run vs the same cycles run on that column alone"}
         if "multilevel" in variants:
-            # (the iterate of a random right-hand side is ~N^2 larger than b, so r = b - A x cancels heavily in
-            # fp32: its error is measured against |A x|, the magnitude the subtraction works on)
+            # (the iterate of a random right-hand side is ~N^2 larger than b: every row sum -4 x_i + sum x_j
+            # cancels ~7 digits, so the fp32 residual is compared on the scale |A| |x| = 8 |x| the sum works on)
             r_gpu = V.runResidual(A, b, x_ml)
-            ax = grid_stencil_5pt(x_ml.double().view(N, N, k))
-            r_ref = b.double().view(N, N, k) - ax
-            e_ml = float(((r_gpu.double() - r_ref.view(n, k)).norm() / ax.norm()).item())
-            del ax
+            r_ref = b.double().view(N, N, k) - grid_stencil_5pt(x_ml.double().view(N, N, k))
+            e_ml = float(((r_gpu.double() - r_ref.view(n, k)).norm() / (8.0 * x_ml.double().norm())).item())
             rate = max(variants["multilevel"]["worst_column_reduction_per_cycle"][1:])
-            out["parity"]["multilevel_residual_err_rel_to_Ax"] = e_ml
+            out["parity"]["multilevel_residual_err_rel_to_normA_normx"] = e_ml
             out["parity"]["multilevel_worst_reduction_after_first_cycle"] = rate
             out["parity"]["ok"] = bool(out["parity"]["ok"] and e_ml <= TOL32 and rate <= 0.5)
             del x_ml
