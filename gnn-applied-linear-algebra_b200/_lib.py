@@ -64,12 +64,23 @@ class PushDesc(ctypes.Structure):
                 ("dst_offset", c_int64), ("flag", c_void_p)]
 
 
+MAX_PEERS = 8
+
+
+class PeerReduce(ctypes.Structure):
+    """glab_peer_reduce (include/glab.h)."""
+    _fields_ = [("world", c_int32), ("rank", c_int32), ("mail_local", c_void_p), ("flag_local", c_void_p),
+                ("mail_peer", c_void_p * MAX_PEERS), ("flag_peer", c_void_p * MAX_PEERS),
+                ("parity_counter", c_void_p)]
+
+
 class HaloStep(ctypes.Structure):
     """glab_halo_step (include/glab.h)."""
     _fields_ = [("interior_begin", c_int64), ("interior_end", c_int64), ("n_wait", c_int32),
                 ("wait_flags", POINTER(c_void_p)), ("wait_target", c_void_p), ("n_push", c_int32),
                 ("push", POINTER(PushDesc)), ("pushed_counter", c_void_p), ("push_src", c_void_p),
-                ("done_counter", c_void_p), ("status", c_void_p), ("timeout_ms", c_int64)]
+                ("done_counter", c_void_p), ("status", c_void_p), ("timeout_ms", c_int64),
+                ("reduce", POINTER(PeerReduce))]
 
 
 _sig("glab_halo_wait", c_int, c_int, POINTER(c_void_p), P, P)

@@ -220,15 +220,55 @@ template <typename T, int K> struct EpiChebyNext {  // ChebyGNN.py:214, :240-241
   __device__ void finish(State&) const {}
 };
 
+// Sum over the ranks of the partial sums the previous launch published (glab_peer_reduce): one thread
+// per CTA waits for all arrival counters and adds the partials in rank order; the CTA shares the result.
+__device__ __forceinline__ void peer_sums(const PeerReduceDev& pr, double& t0, double& t1) {
+  __shared__ double sh[2];
+  if (threadIdx.x == 0) {
+    pdl_wait();                                // the publishing launch precedes this one on the stream
+    const uint32_t want = *reinterpret_cast<const volatile uint32_t*>(pr.parity_counter);   // own publishes so far
+    const uint32_t par = (want - 1u) & 1u;     // parity of the most recent publish
+    for (int q = 0; q < pr.world; ++q) {
+      SpinGuard guard(pr.timeout_ns);
+      while ((int32_t)(ld_acquire_sys(pr.flag_local + 4 * q) - want) < 0) {
+        __nanosleep(32);
+        if (guard.expired()) { flag_timeout(pr.status, GLAB_STATUS_TIMEOUT_PEER); break; }
+      }
+    }
+    double a = 0.0, b = 0.0;
+    for (int q = 0; q < pr.world; ++q) {
+      const volatile double* m = pr.mail_local + ((size_t)par * GLAB_MAX_PEERS + q) * 2;
+      a += m[0];
+      b += m[1];
+    }
+    sh[0] = a;
+    sh[1] = b;
+  }
+  __syncthreads();
+  t0 = sh[0];
+  t1 = sh[1];
+}
+
 template <typename T> struct EpiPower {  // PowerMethodGNN.py:156, :124, :183, :205
   T* y;
   const double* sumsq_in;
   double* sumsq_out;
   void* ws;
+  PeerReduceDev pr;            // world == 0: rank-local sums (single GPU, or the caller reduces them)
   struct State { T n; bool scale; double s; };
+  // called by EVERY thread of the CTA before the roles split (it contains a CTA barrier)
+  __device__ void prologue(State& s) const {
+    s.scale = sumsq_in != nullptr;
+    s.n = T(1);
+    if (s.scale && pr.world > 0) {
+      double t0, t1;
+      peer_sums(pr, t0, t1);
+      s.n = (T)sqrt(t0);
+    }
+  }
   __device__ void init(State& s) const {
     s.scale = sumsq_in != nullptr;
-    s.n = s.scale ? (T)sqrt(__ldg(sumsq_in)) : T(1);
+    if (!(s.scale && pr.world > 0)) s.n = s.scale ? (T)sqrt(__ldg(sumsq_in)) : T(1);
     s.s = 0.0;
   }
   __device__ void row(State& s, int r, const T (&acc)[1]) const {
@@ -241,8 +281,9 @@ template <typename T> struct EpiPower {  // PowerMethodGNN.py:156, :124, :183, :
   __host__ __device__ const T* stream_ptr(int) const { return nullptr; }
   __host__ __device__ int stream_width(int) const { return 0; }
   __device__ void row_staged(State& s, int r, const T (&acc)[1], const T*, const T*, const T*) const { row(s, r, acc); }
-  __device__ void finish(State& s) const { grid_reduce2(s.s, 0.0, ws, sumsq_out); }
+  __device__ void finish(State& s) const { grid_reduce2(s.s, 0.0, ws, sumsq_out, pr.world > 0 ? &pr : nullptr); }
 };
+template <typename T> struct has_prologue<EpiPower<T>> { static constexpr bool value = true; };
 
 template <typename T> struct EpiRayleigh {  // PowerMethodGNN.py:205, :235, :264, :124, :292
   const T* b_in;
@@ -251,10 +292,20 @@ template <typename T> struct EpiRayleigh {  // PowerMethodGNN.py:205, :235, :264
   const double* sumsq_in;
   double* sums_out;
   void* ws;
+  PeerReduceDev pr;            // consumes the norm the last power step published; its own sums stay rank-local
   struct State { T n; bool scale; double s0, s1; };
+  __device__ void prologue(State& s) const {
+    s.scale = sumsq_in != nullptr;
+    s.n = T(1);
+    if (s.scale && pr.world > 0) {
+      double t0, t1;
+      peer_sums(pr, t0, t1);
+      s.n = (T)sqrt(t0);
+    }
+  }
   __device__ void init(State& s) const {
     s.scale = sumsq_in != nullptr;
-    s.n = s.scale ? (T)sqrt(__ldg(sumsq_in)) : T(1);
+    if (!(s.scale && pr.world > 0)) s.n = s.scale ? (T)sqrt(__ldg(sumsq_in)) : T(1);
     s.s0 = s.s1 = 0.0;
   }
   __device__ void row(State& s, int r, const T (&acc)[1]) const {
@@ -284,6 +335,7 @@ template <typename T> struct EpiRayleigh {  // PowerMethodGNN.py:205, :235, :264
   }
   __device__ void finish(State& s) const { grid_reduce2(s.s0, s.s1, ws, sums_out); }
 };
+template <typename T> struct has_prologue<EpiRayleigh<T>> { static constexpr bool value = true; };
 
 template <typename T> struct EpiXtAx {  // MatrixWeightedNorm.py:107-109
   const T* x;
@@ -898,6 +950,25 @@ static int jacobi_sweeps(const glab_plan* p, const T* vals, const T* diag, const
   return 0;
 }
 
+static PeerReduceDev peer_reduce_dev(const glab_halo_step* h) {
+  PeerReduceDev d{};
+  if (h && h->reduce && h->reduce->world > 0 && h->reduce->world <= GLAB_MAX_PEERS) {
+    const glab_peer_reduce* r = h->reduce;
+    d.world = r->world;
+    d.rank = r->rank;
+    d.mail_local = r->mail_local;
+    d.flag_local = r->flag_local;
+    for (int q = 0; q < GLAB_MAX_PEERS; ++q) {
+      d.mail_peer[q] = q < r->world ? r->mail_peer[q] : nullptr;
+      d.flag_peer[q] = q < r->world ? r->flag_peer[q] : nullptr;
+    }
+    d.parity_counter = r->parity_counter;
+    d.status = h->status;
+    d.timeout_ns = spin_timeout_ns(h->timeout_ms);
+  }
+  return d;
+}
+
 template <typename T, class Epi>
 static int launch_reducing(const glab_plan* p, const T* vals, const T* x, const Epi& epi,
                            int64_t rb, int64_t re, void* stream, const glab_halo_step* h = nullptr) {
@@ -917,7 +988,7 @@ static int power_step(const glab_plan* p, const T* vals, const T* b_in, T* y, co
   int rc = check_common(p, vals, b_in, rb, re);
   if (rc) return rc;
   if (!y || !ss_out || !ws || y == b_in) return GLAB_E_ARG;
-  EpiPower<T> e{y, ss_in, ss_out, ws};
+  EpiPower<T> e{y, ss_in, ss_out, ws, peer_reduce_dev(h)};
   return launch_reducing<T>(p, vals, b_in, e, rb, re, stream, h);
 }
 
@@ -928,7 +999,7 @@ static int rayleigh(const glab_plan* p, const T* vals, const T* b_in, T* b_out, 
   int rc = check_common(p, vals, b_in, rb, re);
   if (rc) return rc;
   if (!b_out || !y_out || !sums_out || !ws || b_out == b_in) return GLAB_E_ARG;
-  EpiRayleigh<T> e{b_in, b_out, y_out, ss_in, sums_out, ws};
+  EpiRayleigh<T> e{b_in, b_out, y_out, ss_in, sums_out, ws, peer_reduce_dev(h)};
   return launch_reducing<T>(p, vals, b_in, e, rb, re, stream, h);
 }
 

@@ -285,6 +285,7 @@ k_row_pipe(TileArgs<T> a, const T* __restrict__ x, Epi epi, int ntiles, PipeLayo
   pdl_launch_dependents();
 
   typename Epi::State st;
+  if constexpr (has_prologue<Epi>::value) epi.prologue(st);   // CTA-wide (e.g. the norm summed over the ranks)
 
   // logical tile -> (physical tile, reads-halo flag); boundary tiles come first
   auto phys = [&](int t, bool& boundary) -> int {

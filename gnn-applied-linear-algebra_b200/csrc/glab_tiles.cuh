@@ -14,7 +14,12 @@
 #pragma once
 #include "glab_common.cuh"
 
+
 namespace glab {
+
+// Epilogues with a CTA-wide prologue (run by every thread before the roles split) specialise this.
+template <class E> struct has_prologue { static constexpr bool value = false; };
+
 
 template <typename T> struct TileArgs {
   const int32_t* __restrict__ rowptr;
@@ -44,6 +49,7 @@ k_row_tiles(TileArgs<T> a, const T* __restrict__ x, Epi epi, int ntiles) {
   constexpr int R = kThreads * RPT;
   const int tid = threadIdx.x;
   typename Epi::State st;
+  if constexpr (has_prologue<Epi>::value) epi.prologue(st);
   epi.init(st);
 
   for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
@@ -99,7 +105,20 @@ k_row_tiles(TileArgs<T> a, const T* __restrict__ x, Epi epi, int ntiles) {
 // slots in a fixed order and writes out[0..1].  ws layout: [0] ticket (uint32), doubles from
 // byte 64: partial[2*cta + {0,1}].
 // ------------------------------------------------------------------------------------------
-__device__ __forceinline__ void grid_reduce2(double s0, double s1, void* ws, double* out) {
+// Device-side copy of glab_peer_reduce (passed by value inside the epilogue).
+struct PeerReduceDev {
+  int world, rank;
+  double* mail_local;
+  uint32_t* flag_local;
+  double* mail_peer[GLAB_MAX_PEERS];
+  uint32_t* flag_peer[GLAB_MAX_PEERS];
+  uint32_t* parity_counter;
+  uint32_t* status;
+  unsigned long long timeout_ns;
+};
+
+__device__ __forceinline__ void grid_reduce2(double s0, double s1, void* ws, double* out,
+                                             const PeerReduceDev* pr = nullptr) {
   __shared__ double red[2][16];  // up to 16 warps per CTA
   __shared__ bool is_last;
   unsigned int* ticket = reinterpret_cast<unsigned int*>(ws);
@@ -137,6 +156,20 @@ __device__ __forceinline__ void grid_reduce2(double s0, double s1, void* ws, dou
       out[0] = u0;
       out[1] = u1;
       *ticket = 0u;  // re-arm for the next stream-ordered call
+      if (pr != nullptr && pr->world > 0) {
+        // publish this rank's partial sums into every rank's mailbox (peer stores), then bump the
+        // arrival counters with a system-scope release
+        const uint32_t par = *pr->parity_counter & 1u;
+        for (int q = 0; q < pr->world; ++q) {
+          double* m = pr->mail_peer[q] + ((size_t)par * GLAB_MAX_PEERS + pr->rank) * 2;
+          m[0] = u0;
+          m[1] = u1;
+        }
+        __threadfence_system();
+        for (int q = 0; q < pr->world; ++q)
+          asm volatile("red.release.sys.global.add.u32 [%0], 1;" ::"l"(pr->flag_peer[q] + 4 * pr->rank) : "memory");
+        *pr->parity_counter += 1u;
+      }
     }
   }
 }

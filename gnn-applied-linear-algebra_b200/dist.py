@@ -25,6 +25,8 @@ tests/test_dist_cpu.py with world_size-2 gloo.
 """
 import ctypes
 
+import os
+
 import torch
 import torch.distributed as dist
 
@@ -260,6 +262,7 @@ class PeerHalo:
         self.flag_index = {nm: i for i, nm in enumerate(names)}
         self.flags = PeerBuffer((2 * len(names) * world + 4) * 4, torch.int32, device, group)
         self._steps = {}
+        self._reduce = None
         offs = [None] * world
         if world > 1:
             dist.all_gather_object(offs, halo.recv_offsets, group=group)
@@ -303,11 +306,35 @@ class PeerHalo:
         if world > 1:
             dist.barrier(group=group)
 
-    def step(self, name_in, name_out, interior):
+    def reduce_desc(self):
+        """glab_peer_reduce of this rank (mailboxes + arrival counters in peer memory, created on first
+        use -- collective): the reducing step kernels sum their two partial sums over the ranks
+        themselves, no NCCL call per iteration."""
+        if self._reduce is None:
+            from ._lib import PeerReduce, MAX_PEERS as MP
+            world = self.halo.part.world
+            if world > MP:
+                raise GlabError("in-kernel reduction handles %d ranks, world is %d" % (MP, world))
+            mail = PeerBuffer(2 * MP * 2, torch.float64, self.device, self.group)
+            flag = PeerBuffer((MP + 1) * 4, torch.int32, self.device, self.group)    # [MP] = publish count
+            d = PeerReduce()
+            d.world, d.rank = world, self.rank
+            d.mail_local, d.flag_local = mail.peer_ptr[self.rank], flag.peer_ptr[self.rank]
+            for q in range(world):
+                d.mail_peer[q] = mail.peer_ptr[q]
+                d.flag_peer[q] = flag.peer_ptr[q]
+            d.parity_counter = flag.peer_ptr[self.rank] + MP * 16
+            self._reduce = (d, mail, flag)
+            if world > 1:
+                dist.barrier(group=self.group)
+        return self._reduce[0]
+
+    def step(self, name_in, name_out, interior, reduce=False):
         """glab_halo_step for a FUSED step that gathers vector `name_in` and produces `name_out`
-        (None: nothing to push): wait on the arrivals of name_in, push name_out from the kernel."""
+        (None: nothing to push): wait on the arrivals of name_in, push name_out from the kernel.
+        reduce: attach the in-kernel sum over the ranks (power_step / rayleigh)."""
         from ._lib import HaloStep
-        key = (name_in, name_out, interior)
+        key = (name_in, name_out, interior, reduce)
         hit = self._steps.get(key)
         if hit is not None:
             return hit
@@ -331,6 +358,7 @@ class PeerHalo:
         st.done_counter = self._spare_word(0)      # two counters, 16 bytes apart (words 0 and 1)
         st.status = self._spare_word(2)
         st.timeout_ms = 0                           # library default (GLAB_SPIN_TIMEOUT_MS)
+        st.reduce = ctypes.pointer(self.reduce_desc()) if reduce else None
         self._steps[key] = st
         return st
 
@@ -380,6 +408,11 @@ class PeerHalo:
         for b in self.bufs.values():
             b.close()
         self.flags.close()
+        if self._reduce is not None:
+            self._reduce[1].close()
+            self._reduce[2].close()
+            self._reduce = None
+            self._steps = {}
 
 
 class DistOperator:
@@ -581,9 +614,13 @@ class DistOperator:
         return x, r, cur
 
     def power_method(self, num_iter, start="v0"):
-        """Power iteration + Rayleigh quotient on the partitioned operator; the squared norms are
-        all-reduced (2 fp64 scalars) once per iteration.  Returns (lambda, n, n_A) as a device
-        fp64 tensor [3] and the name of the vector holding the normalised iterate."""
+        """Power iteration + Rayleigh quotient on the partitioned operator.  Engine "peer": the squared
+        norm of every iterate is summed over the ranks INSIDE the step kernels (glab_peer_reduce:
+        mailboxes in peer memory, rank-ordered sum, identical on every rank) -- one NCCL all-reduce in
+        total, for the three reported numbers.  Other engines: one all-reduce (2 fp64 scalars) per
+        iteration.  Returns (lambda, n, n_A) as a device fp64 tensor [3] and the last b, y blocks."""
+        if self.halo.part.world > 1 and self.engine == "peer" and os.environ.get("GLAB_DIST_FUSED_REDUCE", "1") != "0":
+            return self._power_method_fused(num_iter, start)
         n = self.n_local
         cur = start
         sums = torch.zeros(2 * (num_iter + 2), dtype=torch.float64, device=self.device)
@@ -620,6 +657,25 @@ class DistOperator:
             dist.all_reduce(part, group=self.group)
         norm = torch.sqrt(prev[0]) if prev is not None else torch.ones((), dtype=torch.float64, device=self.device)
         return torch.stack([part[0] / part[1], norm, part[0]]), bout, yout
+
+    def _power_method_fused(self, num_iter, start):
+        n, rng = self.n_local, self._ranges()[0]
+        cur = start
+        part = torch.zeros(2 * (num_iter + 1), dtype=torch.float64, device=self.device)   # rank-local sums
+        prev = None
+        for it in range(num_iter):
+            nxt = "va" if cur != "va" else "vb"
+            rt.power_step(self.plan, self.vals, self.vec[cur], self.vec[nxt], prev, part[2 * it:2 * it + 2],
+                          halo=self.peer.step(cur, nxt, rng, reduce=True))
+            cur, prev = nxt, part[2 * it:2 * it + 2]
+        bout = torch.empty(n, self.k, dtype=self.dtype, device=self.device)
+        yout = torch.empty_like(bout)
+        last = part[2 * num_iter:2 * num_iter + 2]
+        rt.rayleigh(self.plan, self.vals, self.vec[cur], bout, yout, prev, last,
+                    halo=self.peer.step(cur, None, rng, reduce=True))
+        tot = torch.stack([last[0], last[1], prev[0] if prev is not None else last[1] * 0 + 1.0 / self.halo.part.world])
+        dist.all_reduce(tot, group=self.group)
+        return torch.stack([tot[0] / tot[1], torch.sqrt(tot[2]), tot[0]]), bout, yout
 
     def _reduced_step(self, name_in, launch, total):
         """Reducing kernels write their partial sums per launch; ranges are accumulated."""

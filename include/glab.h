@@ -48,7 +48,8 @@
 extern "C" {
 #endif
 
-#define GLAB_VERSION 100
+#define GLAB_VERSION 200
+#define GLAB_MAX_PEERS 8
 
 #define GLAB_E_ARG      (-1)  /* null pointer / negative size / unsupported k                    */
 #define GLAB_E_RANGE    (-2)  /* nnz >= 2^31, row/col index outside [0, n)                       */
@@ -338,7 +339,6 @@ int glab_ipc_free(void* dev_ptr);
  * vector, device resident).  Counters only ever count up and live on the device, so a CUDA
  * graph that contains pushes and waits can be replayed any number of times.
  * `descs` is a HOST array, copied at launch.  n_peers == 0 still bumps *pushed_local. */
-#define GLAB_MAX_PEERS 8
 typedef struct glab_push_desc {
   const int32_t* send_idx;   /* device: local row ids to send to this peer        */
   int64_t first_row;         /* >= 0: send_idx[i] == first_row + i for all i (contiguous block:
@@ -370,6 +370,25 @@ int glab_halo_wait(int n_flags, uint32_t* const* flags, const uint32_t* pushed_l
  * interior_begin / interior_end must be multiples of 256.  All arrays are HOST arrays copied at
  * launch; done_counter is a zero-initialised device word owned by the caller.
  * ------------------------------------------------------------------------------------------ */
+/* Sum of per-rank partial sums over peer memory, fused into the reducing step kernels (power method):
+ * every rank owns a mailbox  double mail[2][GLAB_MAX_PEERS][2]  and arrival counters
+ * uint32 flag[GLAB_MAX_PEERS] (16 bytes apart), both peer-mapped.  The grid's last CTA stores this rank's
+ * two partial sums into slot [parity][rank] of EVERY rank's mailbox (its own included) and
+ * release-increments flag[rank] there; parity alternates per publishing launch (*parity_counter, a
+ * device word the kernel advances).  A launch that CONSUMES sums (sumsq_in != NULL in
+ * glab_power_step_halo_* / glab_rayleigh_halo_*) waits until all `world` counters have reached this
+ * rank's own count, then adds the `world` partials of the previous parity in rank order -- the same
+ * order on every rank, so all ranks use bit-identical norms.  Replaces one NCCL all-reduce per
+ * iteration. */
+typedef struct glab_peer_reduce {
+  int32_t world, rank;
+  double* mail_local;                    /* this rank's mailbox                                   */
+  uint32_t* flag_local;                  /* this rank's arrival counters                          */
+  double* mail_peer[GLAB_MAX_PEERS];     /* every rank's mailbox (peer-mapped; [rank] = local)    */
+  uint32_t* flag_peer[GLAB_MAX_PEERS];   /* every rank's counters (peer-mapped)                   */
+  uint32_t* parity_counter;              /* device word: number of publishes so far (local)       */
+} glab_peer_reduce;
+
 typedef struct glab_halo_step {
   int64_t interior_begin, interior_end;
   int32_t n_wait;
@@ -384,6 +403,9 @@ typedef struct glab_halo_step {
                               wait gave up after timeout_ms; the results of that launch are undefined */
   int64_t timeout_ms;      /* bound of every in-kernel wait on a flag written by another CTA / GPU;
                               0 = the library default (GLAB_SPIN_TIMEOUT_MS, else 20000), < 0 = forever */
+  const glab_peer_reduce* reduce;   /* power_step / rayleigh only, may be NULL: sum the partial sums over
+                              the ranks inside the kernels (see glab_peer_reduce) instead of leaving
+                              sumsq_out rank-local                                                  */
 } glab_halo_step;
 #define GLAB_STATUS_TIMEOUT_PEER   1u  /* a neighbour's arrival counter did not reach its target   */
 #define GLAB_STATUS_TIMEOUT_TILES  2u  /* this GPU's own boundary tiles did not finish             */

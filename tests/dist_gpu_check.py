@@ -75,6 +75,17 @@ def main():
             lam, bout, yout = op.power_method(20, "v0")
             tol = 1e-5 if dt == torch.float32 else 1e-12
             e3 = abs(lam[0].item() - g_ref[2].item()) <= tol * abs(g_ref[2].item())
+            # again (odd number of publishes in between: the mailbox parity carries over), and every rank must
+            # hold the same bits (rank-ordered in-kernel sum / NCCL sum)
+            op.load("v0", x0[r0:r1])
+            lam2, _, _ = op.power_method(7, "v0")
+            op.load("v0", x0[r0:r1])
+            lam3, _, _ = op.power_method(20, "v0")
+            allr = [torch.zeros_like(lam3) for _ in range(world)]
+            dist.all_gather(allr, lam3)
+            e3 = e3 and torch.equal(lam3, lam) and all(torch.equal(a, lam3) for a in allr) and \
+                bool(torch.isfinite(lam2).all())
+            op.check()
             torch.cuda.synchronize()
             print("rank %d %s N=%d engine=%s halo=%d interior=[%d,%d) idx16 tiles %d/%d: jacobi %s cheby %s power %s "
                   "(%.9g vs %.9g)" % (rank, str(dt)[6:], N, engine, halo.n_halo, op.lo, op.hi, t16[0], t16[1], e1, e2, e3,

@@ -27,7 +27,7 @@ def test_python_binds_every_symbol(G):
 
 
 def test_version_and_error_strings(G):
-    assert G.lib.glab_version() == 100
+    assert G.lib.glab_version() == 200
     assert b"invalid argument" in G.lib.glab_error_string(-1)
     assert G.lib.glab_error_string(0) == b"ok"
     # argument validation happens before any CUDA call
