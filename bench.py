@@ -240,6 +240,28 @@ def e2e_phases(prob, reps=3):
                     "neighbouring steps, so its step time is bounded below by the largest phase" % reps}
 
 
+def e2e_timeline(prob, steps=8, keep=4):
+    """Timeline of the OVERLAPPED e2e loop (after the timed region): per step the start / end of its H2D,
+    layer calls and D2H on the device clock and the host's issue window, ms since the first traced step."""
+    if not hasattr(prob, "step_e2e"):
+        return None
+    torch.cuda.synchronize()
+    base = torch.cuda.Event(enable_timing=True)
+    prob.trace = []
+    base.record()
+    t_base = time.perf_counter()
+    for _ in range(steps):
+        prob.step_e2e()
+    torch.cuda.synchronize()
+    rows = []
+    for ev, h0, h1 in prob.trace[-keep:]:
+        t = [round(base.elapsed_time(e), 3) for e in ev]
+        rows.append({"h2d": t[0:2], "layers": t[2:4], "d2h": t[4:6],
+                     "host_issue": [round((h0 - t_base) * 1e3, 3), round((h1 - t_base) * 1e3, 3)]})
+    prob.trace = None
+    return {"steps_traced": steps, "last_steps_ms": rows}
+
+
 def jacobi_bytes(n, z, s=4, k=1):
     return z * (4 + s) + 4 * (n + 1) + (3 * k + 1) * n * s
 
@@ -426,6 +448,8 @@ def main_gpu(args):
     # ---------------- parity of the measured path (outside the timed regions), phases of an e2e step
     parity = prob.parity()
     phases = e2e_phases(prob)
+    if phases is not None:
+        phases["overlapped_timeline"] = e2e_timeline(prob)
     if world > 1 and getattr(prob, "op", None) is not None:
         prob.op.check()                      # bounded in-kernel waits: raises if one gave up
 

@@ -5,6 +5,26 @@ import time
 import torch
 
 
+class _Trace:
+    """Optional per-step timeline of step_e2e (events on the three streams + host clock); a no-op
+    unless the smoother's `trace` attribute is a list (bench.e2e_timeline sets it AFTER the timed region)."""
+
+    def __init__(self, sink):
+        self.sink = sink
+        if sink is not None:
+            self.ev, self.t0 = [], time.perf_counter()
+
+    def mark(self, stream):
+        if self.sink is not None:
+            e = torch.cuda.Event(enable_timing=True)
+            e.record(stream)
+            self.ev.append(e)
+
+    def done(self):
+        if self.sink is not None:
+            self.sink.append((self.ev, self.t0, time.perf_counter()))
+
+
 class SingleGpuSmoother:
     """BASELINE config 2 on one GPU: 10 Jacobi sweeps + Chebyshev degree 4, fp32, k = 1."""
 
@@ -136,22 +156,30 @@ class SingleGpuSmoother:
             self._e2e_setup()
         i = self.e2e_i % 2
         self.e2e_i += 1
+        tr = _Trace(getattr(self, "trace", None))
         cur = torch.cuda.current_stream(self.dev)
         with torch.cuda.stream(self.s_in):
             self.s_in.wait_event(self.ev_comp[i])            # the step that last read this buffer is done
+            tr.mark(self.s_in)
             self.va_dev[i].copy_(self.va_host, non_blocking=True)   # H2D of this step's inputs
+            tr.mark(self.s_in)
             self.ev_in[i].record(self.s_in)
         cur.wait_event(self.ev_in[i])
         cur.wait_event(self.ev_out[i])                       # this result buffer has been downloaded
+        tr.mark(cur)
         va = self.va_dev[i]
         x1 = self.jac(self.N_JACOBI, va, self.ei, self.ea2, self.gw)
         v, e, g = self.cheb(self.rt.pack([va[:, 1:2].contiguous(), x1]), self.ei, self.ev, self.gc)
         self.res_dev[i].copy_(v[:, 1:2])
+        tr.mark(cur)
         self.ev_comp[i].record(cur)
         with torch.cuda.stream(self.s_out):
             self.s_out.wait_event(self.ev_comp[i])
+            tr.mark(self.s_out)
             self.out_hosts[i].copy_(self.res_dev[i], non_blocking=True)   # D2H of this step's result
+            tr.mark(self.s_out)
             self.ev_out[i].record(self.s_out)
+        tr.done()
         return self.out_hosts[i]
 
 
@@ -306,19 +334,27 @@ class PartitionedSmoother:
             self._e2e_setup()
         i = self.e2e_i % 2
         self.e2e_i += 1
+        tr = _Trace(getattr(self, "trace", None))
         cur = torch.cuda.current_stream(self.dev)
         with torch.cuda.stream(self.s_in):
             self.s_in.wait_event(self.ev_comp[i])
+            tr.mark(self.s_in)
             self.va_dev[i].copy_(self.va_host, non_blocking=True)
+            tr.mark(self.s_in)
             self.ev_in[i].record(self.s_in)
         cur.wait_event(self.ev_in[i])
         cur.wait_event(self.ev_out[i])
+        tr.mark(cur)
         self.res_dev[i].copy_(self.layer_pass(self.va_dev[i]))
+        tr.mark(cur)
         self.ev_comp[i].record(cur)
         with torch.cuda.stream(self.s_out):
             self.s_out.wait_event(self.ev_comp[i])
+            tr.mark(self.s_out)
             self.out_hosts[i].copy_(self.res_dev[i], non_blocking=True)
+            tr.mark(self.s_out)
             self.ev_out[i].record(self.s_out)
+        tr.done()
         return self.out_hosts[i]
 
     def parity(self):

@@ -457,6 +457,8 @@ def pack(parts):
     """torch.cat(parts, 1) for dense [n, w_j] device tensors, as one coalesced kernel."""
     n = parts[0].shape[0]
     dt, dev = parts[0].dtype, parts[0].device
+    if n == 0:
+        return torch.cat([p_.reshape(0, p_.shape[1] if p_.dim() > 1 else 1) for p_ in parts], 1)
     parts = [p_.view(n, -1) for p_ in parts]
     widths = [p_.shape[1] for p_ in parts]
     ld = sum(widths)
@@ -480,6 +482,9 @@ def unpack(src, spans, outs=None):
     outs: optional list with a preallocated dense [n, width] destination (or None) per span."""
     n, ld = src.shape
     given = list(outs) if outs is not None else [None] * len(spans)
+    if n == 0:
+        return [torch.empty((0, w), dtype=src.dtype, device=src.device) if t is None else t
+                for (_, w), t in zip(spans, given)]
     if len(spans) > 8 or ld > 64:
         res = []
         for (o, w), t in zip(spans, given):

@@ -148,7 +148,34 @@ __global__ void k_edge_messages(const int32_t* __restrict__ colidx, const T* __r
                                 int64_t nnz, T* __restrict__ out, int64_t ld, int64_t column) {
   const bool packed = WriteA && K == 1 && ld == 2 && column == 1 &&
                       (reinterpret_cast<uintptr_t>(out) % (2 * sizeof(T)) == 0);
-  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < nnz;
+  int64_t done = 0;
+  if constexpr (WriteA && K == 1) {
+    // slot order == edge order (no permutation): four edges per thread -- 16-byte index / value loads,
+    // four gathers in flight, one 8-element store -- so that the pass is limited by HBM, not by the
+    // dependent load chain of one edge per thread
+    constexpr int E = 4;
+    if (packed && perm == nullptr && (reinterpret_cast<uintptr_t>(out) % 16 == 0) &&
+        (reinterpret_cast<uintptr_t>(vals) % 16 == 0) && (reinterpret_cast<uintptr_t>(colidx) % 16 == 0)) {
+      const int64_t groups = nnz / E;
+      for (int64_t g = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; g < groups;
+           g += (int64_t)gridDim.x * blockDim.x) {
+        int32_t c[E];
+        T v[E], o[2 * E];
+        load_vec<int32_t, E>(c, colidx + g * E);
+        load_vec<T, E>(v, vals + g * E);
+#pragma unroll
+        for (int e = 0; e < E; ++e) o[2 * e + 1] = __ldg(x + c[e]);
+#pragma unroll
+        for (int e = 0; e < E; ++e) {
+          o[2 * e] = v[e];
+          o[2 * e + 1] = v[e] * o[2 * e + 1];
+        }
+        store_vec<T, 2 * E>(out + g * (2 * E), o);
+      }
+      done = groups * E;
+    }
+  }
+  for (int64_t i = done + blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < nnz;
        i += (int64_t)gridDim.x * blockDim.x) {
     const int col = __ldg(colidx + i);
     const T v = __ldg(vals + i);

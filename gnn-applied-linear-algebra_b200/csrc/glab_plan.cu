@@ -154,7 +154,7 @@ template <typename T> struct PackArgs {
 // One CTA moves a tile of 256 rows through shared memory so that both sides are coalesced:
 // the interleaved side is one contiguous run of 256*ld elements, each dense part a run of 256*w.
 template <typename T, bool Pack>
-__global__ void __launch_bounds__(256) k_pack(PackArgs<T> a, int64_t n, int ld, T* __restrict__ inter) {
+__global__ void __launch_bounds__(256) k_pack_narrow(PackArgs<T> a, int64_t n, int ld, T* __restrict__ inter) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   T* tile = reinterpret_cast<T*>(smem_raw);  // [256][ld]
   const int64_t r0 = (int64_t)blockIdx.x * 256;
@@ -182,6 +182,110 @@ __global__ void __launch_bounds__(256) k_pack(PackArgs<T> a, int64_t n, int ld, 
 }
 
 template <typename T, bool Pack>
+static int pack_launch_narrow(const PackArgs<T>& a, int64_t n, int ld, T* inter, void* stream) {
+  const int64_t blocks = (n + 255) / 256;
+  if (blocks > INT32_MAX) return GLAB_E_RANGE;
+  const size_t smem = (size_t)256 * ld * sizeof(T);
+  auto kern = k_pack_narrow<T, Pack>;
+  if (smem > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+  }
+  kern<<<(unsigned)blocks, 256, smem, as_stream(stream)>>>(a, n, (int)ld, inter);
+  return (int)cudaGetLastError();
+}
+
+// One CTA moves a tile of kPackRows rows through shared memory so that both sides are coalesced: the
+// interleaved side is one contiguous run of rows*ld elements, each dense part a run of rows*w.  Full,
+// 16-byte-aligned runs move as 16-byte vectors with every load of a phase issued before the first
+// store (a copy kernel lives on bytes in flight: 12-48 KB per CTA here).
+constexpr int kPackRows = 1024;
+
+template <typename T> __device__ __forceinline__ bool aligned16(const T* p) {
+  return (reinterpret_cast<uintptr_t>(p) & 15) == 0;
+}
+
+// global run -> shared run (count elements, both 16-byte aligned when vec)
+template <typename T> __device__ __forceinline__ void run_to_smem(T* dst, const T* __restrict__ src, int count, bool vec) {
+  constexpr int V = 16 / sizeof(T);
+  if (vec) {
+    const int nv = count / V;
+    const uint4* __restrict__ s4 = reinterpret_cast<const uint4*>(src);
+    uint4* d4 = reinterpret_cast<uint4*>(dst);
+    int i = threadIdx.x;
+    for (; i + 3 * 256 < nv; i += 4 * 256) {
+      const uint4 a = __ldcs(s4 + i), b = __ldcs(s4 + i + 256), c = __ldcs(s4 + i + 512), d = __ldcs(s4 + i + 768);
+      d4[i] = a; d4[i + 256] = b; d4[i + 512] = c; d4[i + 768] = d;
+    }
+    for (; i < nv; i += 256) d4[i] = __ldcs(s4 + i);
+    for (int j = nv * V + threadIdx.x; j < count; j += 256) dst[j] = src[j];
+  } else {
+    for (int i = threadIdx.x; i < count; i += 256) dst[i] = src[i];
+  }
+}
+template <typename T> __device__ __forceinline__ void smem_to_run(T* __restrict__ dst, const T* src, int count, bool vec) {
+  constexpr int V = 16 / sizeof(T);
+  if (vec) {
+    const int nv = count / V;
+    const uint4* s4 = reinterpret_cast<const uint4*>(src);
+    uint4* d4 = reinterpret_cast<uint4*>(dst);
+    for (int i = threadIdx.x; i < nv; i += 256) __stcs(d4 + i, s4[i]);
+    for (int j = nv * V + threadIdx.x; j < count; j += 256) dst[j] = src[j];
+  } else {
+    for (int i = threadIdx.x; i < count; i += 256) dst[i] = src[i];
+  }
+}
+
+// Shared layout: the interleaved tile [rows][ld] first, then one dense staging run per part, so that
+// both global sides move as vectors and the transposition happens inside shared memory.
+template <typename T, bool Pack>
+__global__ void __launch_bounds__(256) k_pack(PackArgs<T> a, int64_t n, int ld, T* __restrict__ inter) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  T* tile = reinterpret_cast<T*>(smem_raw);                 // [kPackRows][ld]
+  T* stage = tile + (size_t)kPackRows * ld;                 // dense parts back to back: part j at kPackRows*offset[j]
+  const int64_t r0 = (int64_t)blockIdx.x * kPackRows;
+  const int rows = (int)min((int64_t)kPackRows, n - r0);
+  const int total = rows * ld;
+  T* gi = inter + r0 * ld;
+  const bool vi = aligned16(gi);
+  if (Pack) {
+    for (int j = 0; j < a.n_parts; ++j) {
+      const T* src = a.part[j] + r0 * a.width[j];
+      run_to_smem(stage + (size_t)kPackRows * a.offset[j], src, rows * a.width[j], aligned16(src));
+    }
+    __syncthreads();
+    for (int j = 0; j < a.n_parts; ++j) {
+      const int w = a.width[j], off = a.offset[j];
+      const T* st = stage + (size_t)kPackRows * off;
+      if (w == 1) {
+        for (int i = threadIdx.x; i < rows; i += 256) tile[i * ld + off] = st[i];
+      } else {
+        for (int i = threadIdx.x; i < rows * w; i += 256) tile[(i / w) * ld + off + (i % w)] = st[i];
+      }
+    }
+    __syncthreads();
+    smem_to_run(gi, tile, total, vi);
+  } else {
+    run_to_smem(tile, gi, total, vi);
+    __syncthreads();
+    for (int j = 0; j < a.n_parts; ++j) {
+      const int w = a.width[j], off = a.offset[j];
+      T* st = stage + (size_t)kPackRows * off;
+      if (w == 1) {
+        for (int i = threadIdx.x; i < rows; i += 256) st[i] = tile[i * ld + off];
+      } else {
+        for (int i = threadIdx.x; i < rows * w; i += 256) st[i] = tile[(i / w) * ld + off + (i % w)];
+      }
+    }
+    __syncthreads();
+    for (int j = 0; j < a.n_parts; ++j) {
+      T* dst = a.part[j] + r0 * a.width[j];
+      smem_to_run(dst, stage + (size_t)kPackRows * a.offset[j], rows * a.width[j], aligned16(dst));
+    }
+  }
+}
+
+template <typename T, bool Pack>
 static int pack_launch(int64_t n, int64_t ld, int n_parts, T* const* parts, const int32_t* widths,
                        const int32_t* offsets, T* inter, void* stream) {
   if (n < 0 || ld < 1 || ld > 64 || n_parts < 0 || n_parts > GLAB_MAX_PARTS) return GLAB_E_ARG;
@@ -195,9 +299,12 @@ static int pack_launch(int64_t n, int64_t ld, int n_parts, T* const* parts, cons
     a.width[j] = widths[j];
     a.offset[j] = offsets[j];
   }
-  const int64_t blocks = (n + 255) / 256;
+  // tile height: kPackRows while two copies of the tile fit 64 KB of shared memory, else fewer rows --
+  // wide interleaved blocks (ld up to 64) keep the old 256-row tiles
+  const size_t smem = (size_t)2 * kPackRows * ld * sizeof(T);
+  if (smem > 96 * 1024) return pack_launch_narrow<T, Pack>(a, n, (int)ld, inter, stream);
+  const int64_t blocks = (n + kPackRows - 1) / kPackRows;
   if (blocks > INT32_MAX) return GLAB_E_RANGE;
-  const size_t smem = (size_t)256 * ld * sizeof(T);
   auto kern = k_pack<T, Pack>;
   if (smem > 48 * 1024) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

@@ -994,3 +994,38 @@ def test_fused_four_way_aggregation_and_batched_graphs(G, dev, dt):
     # (c) one plan per index tensor
     p1 = rt._index_plan(row_d, n)
     assert rt._index_plan(row_d, n) is p1
+
+
+@pytest.mark.parametrize("dt", [torch.float32, torch.float64])
+@pytest.mark.parametrize("n", [0, 1, 255, 1024, 1025, 5000, 70001])
+def test_pack_unpack_layout_glue(G, dev, dt, n):
+    """rt.pack == torch.cat(parts, 1) and rt.unpack == dense column slices, bit for bit: ragged tails,
+    widths 1..8, partial spans, 16-byte-misaligned parts (views at odd offsets), wide blocks that take the
+    narrow-tile kernel."""
+    rt = G.runtime
+    torch.manual_seed(n + 17)
+    for widths in ([1, 1, 1], [1, 2], [3, 1, 4], [8, 8, 8], [1], [5, 7, 2, 1], [16, 24, 8]):
+        parts = [torch.rand(n, w, dtype=dt, device=dev) for w in widths]
+        cat = torch.cat(parts, 1)
+        assert torch.equal(rt.pack(parts), cat)
+        spans, o = [], 0
+        for w in widths:
+            spans.append((o, w))
+            o += w
+        for got, want in zip(rt.unpack(cat, spans), parts):
+            assert torch.equal(got.reshape(n, want.shape[1]), want)
+        # a subset of the column blocks, into preallocated destinations
+        if len(spans) > 1:
+            dst = torch.full((n, spans[-1][1]), -1.0, dtype=dt, device=dev)
+            got = rt.unpack(cat, [spans[0], spans[-1]], outs=[None, dst])
+            assert torch.equal(got[0].reshape(n, parts[0].shape[1]), parts[0]) and torch.equal(dst, parts[-1])
+    if n > 0:
+        # misaligned dense parts: views starting one element into a larger buffer
+        big = [torch.rand(n * 2 + 3, dtype=dt, device=dev) for _ in range(3)]
+        parts = [b_[1:1 + n].view(n, 1) for b_ in big]
+        cat = torch.cat(parts, 1)
+        assert torch.equal(rt.pack(parts), cat)
+        outs = [torch.zeros(n + 1, dtype=dt, device=dev)[1:].view(n, 1) for _ in range(3)]
+        rt.unpack(cat, [(0, 1), (1, 1), (2, 1)], outs=outs)
+        for got, want in zip(outs, parts):
+            assert torch.equal(got, want)
