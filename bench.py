@@ -511,7 +511,32 @@ def main_gpu(args):
         import gc
         gc.collect()
         torch.cuda.empty_cache()
-        line["extra"] = run_extras(G, dev, rank, world, peak, extras, not args.no_cpu_baseline)
+        # The headline numbers above are complete.  The sub-results must never cost the driver its JSON
+        # line: if they overrun their budget (a stuck collective cannot be interrupted from Python), a
+        # watchdog prints the line with what has finished and ends every rank.
+        done_extras = {}
+        line["extra"] = done_extras
+        budget = float(os.environ.get("GLAB_BENCH_EXTRAS_BUDGET_S", "240"))
+
+        def give_up():
+            import faulthandler
+            faulthandler.dump_traceback(file=sys.stderr, all_threads=True)
+            if rank == 0:
+                done_extras["_watchdog"] = {"error": "sub-results exceeded %.0f s; the remaining ones were abandoned" % budget}
+                try:
+                    sys.stdout.write(json.dumps(line) + "\n")
+                    sys.stdout.flush()
+                finally:
+                    os._exit(0)
+            time.sleep(2.0)          # let rank 0 print before the launcher sees ranks leave
+            os._exit(0)
+
+        import threading
+        dog = threading.Timer(budget, give_up)
+        dog.daemon = True
+        dog.start()
+        run_extras(G, dev, rank, world, peak, extras, not args.no_cpu_baseline, done_extras)
+        dog.cancel()
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         r = run_cpu_reference(args.workload, 1, 0)
         line["cpu_baseline"] = {"value": r["value"], "unit": "nnz/s", "cores": r["cores"], "kind": r["kind"],
@@ -525,11 +550,11 @@ def main_gpu(args):
     return 0
 
 
-def run_extras(G, dev, rank, world, peak, names, cpu_baseline):
+def run_extras(G, dev, rank, world, peak, names, cpu_baseline, out=None):
     """bench_extra.* one by one; every rank takes part in the partitioned ones.  The single-GPU-only
     sub-results (the 67 M-row layer table and the AMG setup kernels) run on rank 0's GPU at N = 1 only."""
     import bench_extra as X
-    out = {}
+    out = {} if out is None else out
     grid_big = int(os.environ.get("GLAB_BENCH_BIG", "8192"))       # shrink for smoke runs of the bench itself
     grid_amg = int(os.environ.get("GLAB_BENCH_AMG", "4096"))
     for name in names:
@@ -547,6 +572,8 @@ def run_extras(G, dev, rank, world, peak, names, cpu_baseline):
                 res = {"error": "unknown extra %r" % name}
         except Exception as exc:       # noqa: BLE001 -- reported in the JSON line
             import traceback
+            sys.stderr.write("[bench extras] rank %d: %s failed\n%s\n" % (rank, name, traceback.format_exc()))
+            sys.stderr.flush()
             res = {"error": "%s: %s" % (type(exc).__name__, str(exc)[:300]),
                    "where": traceback.format_exc().strip().splitlines()[-3:]}
             torch.cuda.synchronize()

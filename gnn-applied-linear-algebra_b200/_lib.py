@@ -40,6 +40,7 @@ def _sig(name, restype, *argtypes):
 
 
 _sig("glab_version", c_int)
+_sig("glab_halo_fits", c_int, P, c_int, c_int)
 _sig("glab_error_string", c_char_p, c_int)
 _sig("glab_plan_create", c_int, _I64, _I64, _I64, P, P, P, POINTER(P))
 _sig("glab_plan_create_csr", c_int, _I64, _I64, _I64, P, P, P, POINTER(P))

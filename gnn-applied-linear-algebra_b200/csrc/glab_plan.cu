@@ -429,6 +429,18 @@ using namespace glab;
 
 extern "C" int glab_version(void) { return GLAB_VERSION; }
 
+// Mirrors make_pipe_layout / launch_pipe_halo_impl (glab_layers_impl.cuh) with the widest epilogue
+// (six k-wide vertex streams) and a margin for the kernels' static shared memory.
+extern "C" int glab_halo_fits(const glab_plan* p, int k, int elem_bytes) {
+  if (!p || k < 1 || (elem_bytes != 4 && elem_bytes != 8)) return 0;
+  auto up = [](int64_t v) { return (v + 127) / 128 * 128; };
+  const int64_t slots = (int64_t)256 * (p->max_row_nnz > 0 ? p->max_row_nnz : 1);
+  if (slots > 24576) return 0;
+  const int64_t stage = up(257 * 4 + 32) + up(slots * 4 + 32) + up(slots * elem_bytes + 32) +
+                        6 * up((int64_t)256 * k * elem_bytes + 32);
+  return 2 * stage + 128 <= 227 * 1024 - 2048 ? 1 : 0;
+}
+
 extern "C" const char* glab_error_string(int code) {
   switch (code) {
     case 0: return "ok";

@@ -459,6 +459,11 @@ class DistOperator:
         import os
         self.multi_sweep = os.environ.get("GLAB_DIST_MS", "1") != "0"
         self._entry = 0
+        # engine "peer": the one-kernel steps need a 256-row tile of the operator in two shared-memory stages;
+        # operators with very wide rows (deep coarse levels) take the separate wait / boundary / push kernels,
+        # which speak the same counters, so neighbours may differ in their choice
+        esz = torch.empty(0, dtype=self.dtype).element_size()
+        self.fused = engine == "peer" and self.square and bool(lib.glab_halo_fits(self.plan.handle, k, esz))
 
     def entry(self):
         """Name of the vector the next layer call loads its input into: "v0" and "v1" alternate.
@@ -512,7 +517,7 @@ class DistOperator:
             if name_out is not None:
                 self.publish(name_out)
             return
-        if self.engine == "peer":
+        if self.fused:
             launch(halo=self.peer.step(name_in, name_out, interior))
             return
         main = torch.cuda.current_stream(self.device)
@@ -557,7 +562,7 @@ class DistOperator:
         vector holding the result."""
         cur = start
         todo = n_iters
-        if self.engine == "peer" and self.halo.part.world > 1 and self.multi_sweep and n_iters > 1:
+        if self.fused and self.halo.part.world > 1 and self.multi_sweep and n_iters > 1:
             # One launch for all sweeps (glab_jacobi_sweeps_halo_*).  The multi-sweep kernel overwrites both
             # of its buffers, so a start vector that must stay intact ("v0") takes one ordinary sweep first.
             if cur in self.ENTRY:
@@ -619,7 +624,7 @@ class DistOperator:
         mailboxes in peer memory, rank-ordered sum, identical on every rank) -- one NCCL all-reduce in
         total, for the three reported numbers.  Other engines: one all-reduce (2 fp64 scalars) per
         iteration.  Returns (lambda, n, n_A) as a device fp64 tensor [3] and the last b, y blocks."""
-        if self.halo.part.world > 1 and self.engine == "peer" and os.environ.get("GLAB_DIST_FUSED_REDUCE", "1") != "0":
+        if self.halo.part.world > 1 and self.fused and os.environ.get("GLAB_DIST_FUSED_REDUCE", "1") != "0":
             return self._power_method_fused(num_iter, start)
         n = self.n_local
         cur = start
@@ -631,7 +636,7 @@ class DistOperator:
             ss = sums[2 * it:2 * it + 2]
             bin_, yout = self.vec[cur], self.vec[nxt]
             part = torch.zeros(2, dtype=torch.float64, device=self.device)
-            if multi and self.engine == "peer":
+            if multi and self.fused:
                 rt.power_step(self.plan, self.vals, bin_, yout, prev, part,
                               halo=self.peer.step(cur, nxt, self._ranges()[0]))
             else:
@@ -647,7 +652,7 @@ class DistOperator:
         yout = torch.empty_like(bout)
         part = torch.zeros(2, dtype=torch.float64, device=self.device)
         bin_ = self.vec[cur]
-        if multi and self.engine == "peer":
+        if multi and self.fused:
             rt.rayleigh(self.plan, self.vals, bin_, bout, yout, prev, part,
                         halo=self.peer.step(cur, None, self._ranges()[0]))
         else:

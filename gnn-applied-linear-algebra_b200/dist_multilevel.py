@@ -70,7 +70,7 @@ class DistMultilevel:
             c0, c1 = parts[l + 1].bounds(rank)
             ai, av, ah = partition_coo(src.edge_index, src.edge_val, parts[l], rank, group)
             D.A = DistOperator(ai, av.contiguous(), ah, k=k, engine=engine, group=group)
-            D.diag = src.diag[f0:f1].contiguous()
+            D.diag = src.diag[f0:f1].clone()          # own allocation: the kernels need 16-byte aligned streams
             D.w = src.w
             D.nf, D.nc = f1 - f0, c1 - c0
             pidx, pval = src.P_index, src.P_vals.reshape(-1, 1)

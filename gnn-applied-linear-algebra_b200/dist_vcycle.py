@@ -76,7 +76,7 @@ class DistTwoGrid:
         lap("partition_and_operators_P_PT")
         self.nnz = {"A": int(op.edge_index.shape[1]), "P": int(pidx.shape[1]), "Ac": int(cop.edge_index.shape[1])}
         # ---- per-rank data of the cycle
-        self.diag = op.diag.to(dt).reshape(-1)[f0:f1].contiguous()
+        self.diag = op.diag.to(dt).reshape(-1)[f0:f1].clone()
         self.w = torch.tensor(0.7).reshape(-1).to(device=dev, dtype=dt)                  # VCycle.py:195
         rows, _ = _recurrence(V.cheb_deg, torch.tensor([-3.4, -4.0]))                    # VCycle.py:221-222
         self.table = torch.stack([torch.stack(r_) for r_ in rows]).to(device=dev, dtype=dt).contiguous()

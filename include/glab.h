@@ -370,6 +370,13 @@ int glab_halo_wait(int n_flags, uint32_t* const* flags, const uint32_t* pushed_l
  * interior_begin / interior_end must be multiples of 256.  All arrays are HOST arrays copied at
  * launch; done_counter is a zero-initialised device word owned by the caller.
  * ------------------------------------------------------------------------------------------ */
+/* 1 if the fused halo steps (glab_*_halo_*) can take this operator with k right-hand-side columns of
+ * `elem_bytes`-wide values: a 256-row tile of max_row_nnz slots plus the vertex streams must fit two
+ * shared-memory stages.  0: use the separate kernels (glab_halo_wait, the row-range launches,
+ * glab_halo_push_*) -- the fused entry points return GLAB_E_ARG for such operators (coarse-level
+ * operators with very wide rows). */
+int glab_halo_fits(const glab_plan* plan, int k, int elem_bytes);
+
 /* Sum of per-rank partial sums over peer memory, fused into the reducing step kernels (power method):
  * every rank owns a mailbox  double mail[2][GLAB_MAX_PEERS][2]  and arrival counters
  * uint32 flag[GLAB_MAX_PEERS] (16 bytes apart), both peer-mapped.  The grid's last CTA stores this rank's

@@ -178,7 +178,7 @@ def main():
             dist.barrier()
     # ---- row-partitioned MULTILEVEL cycle vs VCycle.runVCycleML on one GPU: bit-identical
     from glab_b200.dist_multilevel import DistMultilevel
-    for k, N, below in ((1, 96, 1500), (8, 128, 4000)):
+    for k, N, below in ((1, 96, 1500), (8, 128, 4000), (8, 128, 1000), (2, 256, 1000)):
         n = N * N
         ei, ev = G.UtilsGNN.laplacianfun_torch(N, device=dev)
         A = torch.sparse_coo_tensor(ei, ev.flatten().float(), (n, n))
