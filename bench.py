@@ -10,7 +10,7 @@ One "step" = one smoothing pass = 14 fused SpMV-bearing layer launches (10 glab_
   e2e       through the drop-in layer API: per step the vectors are copied from PINNED HOST
             memory to the GPU, JacobiGNN.forward + ChebyRelaxGNN.forward run (including the
             returned edge_attr message column), and the result x is read back to the host
-            (double-buffered, so consecutive steps overlap their PCIe copies with compute).
+            (three staging buffers, so consecutive steps overlap their PCIe copies with compute).
             The operator (edge list + CSR plan) is step-invariant and stays resident, like
             model weights.
   roofline  dominant kernel = glab_jacobi: algorithmic bytes z(4+s)+4(n+1)+4ns per launch over
@@ -491,7 +491,7 @@ def main_gpu(args):
                         "JacobiGNN.forward(10, vertex_attr_slab, dist.PartitionedGraph, ...) + ChebyRelaxGNN(4).forward(...) "
                         "on each rank's slab, device copies of pinned host vectors"),
                 "uploaded_per_step": "vertex_attr = [A_ii, b, x] (3 vectors) of every rank's rows",
-                "pipelining": "double-buffered: step i+1's H2D and step i-1's D2H overlap step i's compute",
+                "pipelining": "3 staging buffers: the H2D of the next steps and the D2H of the previous one overlap step i's compute",
                 "phases": phases, "numa": numa},
         "parity": parity,
         "gpu_launches": launches,
