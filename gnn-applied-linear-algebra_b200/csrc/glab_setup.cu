@@ -150,20 +150,28 @@ static int interp_fill(const glab_plan* A, const T* w, const T* cflag, int mode,
 // Z = X * Y.  Two paths that produce bit-identical results (each entry's products are added one
 // at a time in expansion order: X slot order, then Y slot order, first product not added to 0):
 //
-//   row-local  one thread per output row keeps the row's distinct columns sorted in a private
-//              shared-memory strip (insert / accumulate), once to count (symbolic) and once to
-//              fill (numeric).  Every input and output byte crosses HBM once; used whenever no
-//              row has more than kRowCap distinct columns (all stencil / Galerkin operators).
+//   row-local  one thread per output row keeps the row's distinct columns AND their sums sorted in a
+//              private shared-memory strip (insert / accumulate) -- ONE pass: the finished strip is
+//              parked at the row's product offset in the workspace (a row has at most as many
+//              distinct columns as products) together with its length; the numeric call only
+//              compacts the parked rows into the COO output.  The strip height is a template
+//              parameter (16 / 32 / 64 distinct columns): shared memory per CTA, and with it the
+//              number of rows in flight per SM, follows the operator instead of the worst case
+//              (the kernel is a chain of dependent gathers -- rows in flight are its throughput).
+//              Used whenever no row has more than kRowCap distinct columns (all stencil /
+//              Galerkin operators).
 //   ESC        expand - stable radix sort - compress through a caller workspace of ~24 B per
 //              product; the general fallback (dense-ish rows).
 //
 // Workspace header: hdr[0] = number of distinct (row, col) keys (ESC), hdr[1] = sorted buffer
 // selector (ESC), hdr[2] = row-local overflow flag, hdr[3] = path taken (1 = row-local, 2 = ESC).
+// The row-local path computes the VALUES during the symbolic call: the numeric call must be given
+// the same operands (include/glab.h says so).
 constexpr int kRowCap = 64;       // distinct columns per output row on the row-local path
 constexpr int kRowThreads = 128;  // rows (threads) per CTA on the row-local path
 
 struct SpgemmWs {
-  size_t hdr, rowoff, keys[2], vals[2], cub, total;
+  size_t hdr, rowoff, rowcnt, keys[2], vals[2], cub, total;
   size_t cub_bytes;
   bool esc;  // the workspace is large enough for the ESC path
 };
@@ -184,7 +192,8 @@ static int spgemm_layout(int64_t n_rows_x, int64_t n_products, int64_t max_row_p
   GLAB_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, scan_b, (int64_t*)nullptr, (int64_t*)nullptr,
                                           (int)(n_rows_x + 1), (cudaStream_t)0));
   size_t cb = scan_b;
-  const size_t P = L->esc ? (size_t)n_products + 2 : 0;
+  const size_t P = (size_t)n_products + 2;          // parked rows (row-local) / expanded products (ESC)
+  const size_t P2 = L->esc ? P : 0;                  // second buffers: ESC only
   if (L->esc) {
     size_t sort_b = 0, sel_b = 0;
     cub::DoubleBuffer<uint64_t> dk(nullptr, nullptr);
@@ -199,10 +208,11 @@ static int spgemm_layout(int64_t n_rows_x, int64_t n_products, int64_t max_row_p
   size_t o = 0;
   L->hdr = o;      o += 256;
   L->rowoff = o;   o += align256((size_t)(n_rows_x + 2) * 8);
-  L->keys[0] = o;  o += align256(P * 8);
-  L->keys[1] = o;  o += align256(P * 8);
+  L->rowcnt = o;   o += align256((size_t)(n_rows_x + 2) * 4);
+  L->keys[0] = o;  o += align256(P * (L->esc ? 8 : 4));   // row-local: int32 columns of the parked rows
+  L->keys[1] = o;  o += align256(P2 * 8);
   L->vals[0] = o;  o += align256(P * sizeof(T));
-  L->vals[1] = o;  o += align256(P * sizeof(T));
+  L->vals[1] = o;  o += align256(P2 * sizeof(T));
   L->cub = o;      o += align256(cb + 16);
   L->cub_bytes = cb;
   L->total = o;
@@ -245,79 +255,145 @@ __global__ void k_spgemm_count(const int32_t* __restrict__ xrp, const int32_t* _
 // ---- row-local path ---------------------------------------------------------------------------
 // Thread `tid` owns strip element s at cols[s * kRowThreads + tid] (conflict-free when the threads
 // of a warp touch the same s).  Columns arrive mostly ascending, so the insertion point is searched
-// from the top.  NUMERIC = false only counts the distinct columns of each row.
-template <typename T, bool NUMERIC>
+// from the top.  The finished strip goes to park_col / park_val at the row's product offset.
+template <typename T, int CAP>
 __global__ void __launch_bounds__(kRowThreads)
 k_spgemm_rows(const int32_t* __restrict__ xrp, const int32_t* __restrict__ xci, const T* __restrict__ xv,
               const int32_t* __restrict__ yrp, const int32_t* __restrict__ yci, const T* __restrict__ yv,
-              int64_t n, int32_t* __restrict__ rowcnt, const int32_t* __restrict__ zrp,
-              int64_t* __restrict__ out_row, int64_t* __restrict__ out_col, T* __restrict__ out_val,
-              int64_t* __restrict__ hdr) {
+              int64_t n, const int64_t* __restrict__ poff, int32_t* __restrict__ rowcnt,
+              int32_t* __restrict__ park_col, T* __restrict__ park_val, int64_t* __restrict__ hdr) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  int32_t* cols = reinterpret_cast<int32_t*>(smem_raw);                                  // [kRowCap][kRowThreads]
-  T* vals = reinterpret_cast<T*>(smem_raw + (size_t)kRowCap * kRowThreads * sizeof(int32_t));  // same shape
+  int32_t* cols = reinterpret_cast<int32_t*>(smem_raw);                                  // [CAP][kRowThreads]
+  T* vals = reinterpret_cast<T*>(smem_raw + (size_t)CAP * kRowThreads * sizeof(int32_t));    // same shape
   const int tid = threadIdx.x;
   for (int64_t r = blockIdx.x * (int64_t)kRowThreads + tid; r <= n; r += (int64_t)gridDim.x * kRowThreads) {
     if (r == n) {
-      if (!NUMERIC) rowcnt[n] = 0;  // sentinel: the exclusive scan leaves nnz(Z) here
+      rowcnt[n] = 0;  // sentinel: the exclusive scan leaves nnz(Z) here
       continue;
     }
     int cnt = 0;
     bool over = false;
-    const int e1 = xrp[r + 1];
-    for (int e = xrp[r]; e < e1 && !over; ++e) {
-      const int j = xci[e];
-      T a = T(0);
-      if (NUMERIC) a = xv[e];
-      const int y1 = yrp[j + 1];
-      for (int t = yrp[j]; t < y1; ++t) {
-        const int c = yci[t];
-        int pos = cnt;
-        while (pos > 0 && cols[(pos - 1) * kRowThreads + tid] >= c) --pos;
-        if (pos < cnt && cols[pos * kRowThreads + tid] == c) {
-          if (NUMERIC) vals[pos * kRowThreads + tid] = vals[pos * kRowThreads + tid] + a * yv[t];
-          continue;
+    const int e1 = __ldg(xrp + r + 1);
+    // The row is a chain of dependent gathers (X slot -> Y row bounds -> Y entries); four X slots are
+    // resolved together and the next Y entry is fetched while the current one is inserted, so that the
+    // chain costs ~3 memory latencies per batch instead of 3 per slot.
+    for (int eb = __ldg(xrp + r); eb < e1 && !over; eb += 4) {
+      int y0[4], y1[4];
+      T a[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const bool live = eb + q < e1;
+        y0[q] = live ? __ldg(xci + eb + q) : -1;
+        a[q] = live ? __ldg(xv + eb + q) : T(0);
+      }
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int j = y0[q];
+        y0[q] = j >= 0 ? __ldg(yrp + j) : 0;
+        y1[q] = j >= 0 ? __ldg(yrp + j + 1) : 0;
+      }
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        int t = y0[q];
+        const int tend = y1[q];
+        int cn = 0;
+        T vn = T(0);
+        if (t < tend) {
+          cn = __ldg(yci + t);
+          vn = __ldg(yv + t);
         }
-        if (cnt == kRowCap) {
-          over = true;
-          break;
+        while (t < tend && !over) {
+          const int c = cn;
+          const T prod = a[q] * vn;
+          ++t;
+          if (t < tend) {
+            cn = __ldg(yci + t);
+            vn = __ldg(yv + t);
+          }
+          int pos = cnt;
+          while (pos > 0 && cols[(pos - 1) * kRowThreads + tid] >= c) --pos;
+          if (pos < cnt && cols[pos * kRowThreads + tid] == c) {
+            vals[pos * kRowThreads + tid] = vals[pos * kRowThreads + tid] + prod;
+            continue;
+          }
+          if (cnt == CAP) {
+            over = true;
+            break;
+          }
+          for (int s = cnt; s > pos; --s) {
+            cols[s * kRowThreads + tid] = cols[(s - 1) * kRowThreads + tid];
+            vals[s * kRowThreads + tid] = vals[(s - 1) * kRowThreads + tid];
+          }
+          cols[pos * kRowThreads + tid] = c;
+          vals[pos * kRowThreads + tid] = prod;
+          ++cnt;
         }
-        for (int s = cnt; s > pos; --s) {
-          cols[s * kRowThreads + tid] = cols[(s - 1) * kRowThreads + tid];
-          if (NUMERIC) vals[s * kRowThreads + tid] = vals[(s - 1) * kRowThreads + tid];
-        }
-        cols[pos * kRowThreads + tid] = c;
-        if (NUMERIC) vals[pos * kRowThreads + tid] = a * yv[t];
-        ++cnt;
       }
     }
-    if (!NUMERIC) {
-      rowcnt[r] = cnt;
-      if (over) atomicOr(reinterpret_cast<unsigned long long*>(hdr + 2), 1ull);
+    rowcnt[r] = cnt;
+    if (over) {
+      atomicOr(reinterpret_cast<unsigned long long*>(hdr + 2), 1ull);
     } else {
-      int64_t o = zrp[r];
+      int64_t o = poff[r];
       for (int s = 0; s < cnt; ++s, ++o) {
-        out_row[o] = r;
-        out_col[o] = cols[s * kRowThreads + tid];
-        out_val[o] = vals[s * kRowThreads + tid];
+        park_col[o] = cols[s * kRowThreads + tid];
+        park_val[o] = vals[s * kRowThreads + tid];
       }
     }
   }
 }
 
-template <typename T, bool NUMERIC>
-static int spgemm_rows_launch(const glab_plan* X, const T* xv, const glab_plan* Y, const T* yv, int32_t* rowcnt,
-                              int64_t* out_row, int64_t* out_col, T* out_val, int64_t* hdr, cudaStream_t st) {
-  const size_t smem = (size_t)kRowCap * kRowThreads * (sizeof(int32_t) + (NUMERIC ? sizeof(T) : 0));
-  auto kern = k_spgemm_rows<T, NUMERIC>;
+template <typename T, int CAP>
+static int spgemm_rows_launch(const glab_plan* X, const T* xv, const glab_plan* Y, const T* yv, const int64_t* poff,
+                              int32_t* rowcnt, int32_t* park_col, T* park_val, int64_t* hdr, cudaStream_t st) {
+  const size_t smem = (size_t)CAP * kRowThreads * (sizeof(int32_t) + sizeof(T));
+  auto kern = k_spgemm_rows<T, CAP>;
   GLAB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int64_t n = X->n_rows;
   int64_t blocks = (n + 1 + kRowThreads - 1) / kRowThreads;
-  const int64_t cap = (int64_t)X->sm_count * 16;
+  const int64_t cap = (int64_t)X->sm_count * 32;
   if (blocks > cap) blocks = cap;
-  kern<<<(unsigned)blocks, kRowThreads, smem, st>>>(X->rowptr, X->colidx, xv, Y->rowptr, Y->colidx, yv, n, rowcnt,
-                                                     rowcnt, out_row, out_col, out_val, hdr);
+  kern<<<(unsigned)blocks, kRowThreads, smem, st>>>(X->rowptr, X->colidx, xv, Y->rowptr, Y->colidx, yv, n, poff,
+                                                     rowcnt, park_col, park_val, hdr);
   return (int)cudaGetLastError();
+}
+
+// Parked rows -> COO output (row, col as int64).  One warp per 32 consecutive rows: the lanes hold the
+// rows' output and parking offsets, walk the rows' OUTPUT range 32 entries at a time (coalesced stores,
+// near-contiguous loads) and find each entry's row by a shuffle binary search over the 32 offsets.
+template <typename T>
+__global__ void __launch_bounds__(256)
+k_spgemm_unpark(const int64_t* __restrict__ poff, const int32_t* __restrict__ zrp,
+                const int32_t* __restrict__ park_col, const T* __restrict__ park_val, int64_t n,
+                int64_t* __restrict__ out_row, int64_t* __restrict__ out_col, T* __restrict__ out_val) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t r0 = warp * 32; r0 < n; r0 += nwarps * 32) {
+    const int64_t rl = r0 + lane;
+    const int64_t rend = r0 + 32 < n ? r0 + 32 : n;
+    const int zend = __ldg(zrp + rend);
+    const int zl = rl < n ? __ldg(zrp + rl) : zend;
+    const int64_t pl = rl < n ? __ldg(poff + rl) : 0;
+    const int zbeg = __shfl_sync(0xffffffffu, zl, 0);
+    for (int base = zbeg; base < zend; base += 32) {
+      const int z = base + lane;
+      int lo = 0;  // largest i with zrp[r0 + i] <= z  (empty rows share a start: the last one owns the entry)
+#pragma unroll
+      for (int step = 16; step > 0; step >>= 1) {
+        const int zc = __shfl_sync(0xffffffffu, zl, lo + step);   // lo + step <= 31
+        if (zc <= z) lo += step;
+      }
+      const int zrow = __shfl_sync(0xffffffffu, zl, lo);
+      const int64_t prow = __shfl_sync(0xffffffffu, pl, lo);
+      if (z < zend) {
+        const int64_t p = prow + (z - zrow);
+        out_row[z] = r0 + lo;
+        out_col[z] = (int64_t)__ldg(park_col + p);
+        out_val[z] = __ldg(park_val + p);
+      }
+    }
+  }
 }
 
 // ---- ESC path ---------------------------------------------------------------------------------
@@ -399,7 +475,9 @@ static int spgemm_symbolic(const glab_plan* X, const T* xv, const glab_plan* Y, 
   char* base = reinterpret_cast<char*>(ws);
   int64_t* hdr = reinterpret_cast<int64_t*>(base + L.hdr);
   int64_t* rowoff = reinterpret_cast<int64_t*>(base + L.rowoff);
-  int32_t* rowcnt = reinterpret_cast<int32_t*>(base + L.rowoff);  // row-local path: int32 view
+  int32_t* rowcnt = reinterpret_cast<int32_t*>(base + L.rowcnt);
+  int32_t* park_col = reinterpret_cast<int32_t*>(base + L.keys[0]);
+  T* park_val = reinterpret_cast<T*>(base + L.vals[0]);
   void* ctmp = base + L.cub;
   size_t cb = L.cub_bytes;
   GLAB_CUDA(cudaMemsetAsync(hdr, 0, 256, st));
@@ -408,30 +486,46 @@ static int spgemm_symbolic(const glab_plan* X, const T* xv, const glab_plan* Y, 
     return 0;
   }
   const int64_t n = X->n_rows;
-  // ---- row-local attempt: count the distinct columns of every row
-  rc = spgemm_rows_launch<T, false>(X, xv, Y, yv, rowcnt, nullptr, nullptr, nullptr, hdr, st);
-  if (rc) return rc;
-  GLAB_CUDA(cub::DeviceScan::ExclusiveSum(ctmp, cb, rowcnt, rowcnt, (int)(n + 1), st));
-  int32_t total = 0;
-  int64_t overflow = 0;
-  GLAB_CUDA(cudaMemcpyAsync(&total, rowcnt + n, 4, cudaMemcpyDeviceToHost, st));
-  GLAB_CUDA(cudaMemcpyAsync(&overflow, hdr + 2, 8, cudaMemcpyDeviceToHost, st));
-  GLAB_CUDA(cudaStreamSynchronize(st));
-  if (!overflow) {
-    k_spgemm_store_hdr<<<1, 1, 0, st>>>(hdr, 3, 1);
-    GLAB_CUDA(cudaGetLastError());
-    *nnz_out = total;
-    return 0;
+  // product offset of every row (the parking slot of its strip; also the expansion offsets of ESC)
+  k_spgemm_count<<<grid1d(n + 1, X->sm_count), 256, 0, st>>>(X->rowptr, X->colidx, Y->rowptr, n, rowoff, nullptr);
+  GLAB_CUDA(cudaGetLastError());
+  GLAB_CUDA(cub::DeviceScan::ExclusiveSum(ctmp, cb, rowoff, rowoff, (int)(n + 1), st));
+  // ---- row-local attempts: the smallest strip that can hold the rows, one size up on overflow
+  const int ladder[3] = {16, 32, kRowCap};
+  int first = max_row_products <= 16 ? 0 : 1;      // more than 16 products: most stencil products fit 32 columns
+  if (const char* e = getenv("GLAB_SPGEMM_CAP")) {  // tuning knob: 16 / 32 / 64
+    const int v = atoi(e);
+    first = v >= 64 ? 2 : v >= 32 ? 1 : 0;
+    if (max_row_products > ladder[first] && first < 1) first = 1;
+  }
+  for (int step = first; step < 3; ++step) {
+    GLAB_CUDA(cudaMemsetAsync(hdr + 2, 0, 8, st));
+    switch (ladder[step]) {
+      case 16: rc = spgemm_rows_launch<T, 16>(X, xv, Y, yv, rowoff, rowcnt, park_col, park_val, hdr, st); break;
+      case 32: rc = spgemm_rows_launch<T, 32>(X, xv, Y, yv, rowoff, rowcnt, park_col, park_val, hdr, st); break;
+      default: rc = spgemm_rows_launch<T, kRowCap>(X, xv, Y, yv, rowoff, rowcnt, park_col, park_val, hdr, st); break;
+    }
+    if (rc) return rc;
+    cb = L.cub_bytes;
+    GLAB_CUDA(cub::DeviceScan::ExclusiveSum(ctmp, cb, rowcnt, rowcnt, (int)(n + 1), st));
+    int32_t total = 0;
+    int64_t overflow = 0;
+    GLAB_CUDA(cudaMemcpyAsync(&total, rowcnt + n, 4, cudaMemcpyDeviceToHost, st));
+    GLAB_CUDA(cudaMemcpyAsync(&overflow, hdr + 2, 8, cudaMemcpyDeviceToHost, st));
+    GLAB_CUDA(cudaStreamSynchronize(st));
+    if (!overflow) {
+      k_spgemm_store_hdr<<<1, 1, 0, st>>>(hdr, 3, 1);
+      GLAB_CUDA(cudaGetLastError());
+      *nnz_out = total;
+      return 0;
+    }
+    if (max_row_products <= ladder[step]) return GLAB_E_ARG;  // cannot happen: <= CAP products cannot overflow
   }
   if (!L.esc) return GLAB_E_ARG;  // cannot happen: <= kRowCap products per row cannot overflow
   // ---- ESC fallback
   uint64_t* k[2] = {reinterpret_cast<uint64_t*>(base + L.keys[0]), reinterpret_cast<uint64_t*>(base + L.keys[1])};
   T* v[2] = {reinterpret_cast<T*>(base + L.vals[0]), reinterpret_cast<T*>(base + L.vals[1])};
-  k_spgemm_count<<<grid1d(n + 1, X->sm_count), 256, 0, st>>>(X->rowptr, X->colidx, Y->rowptr, n, rowoff, nullptr);
-  GLAB_CUDA(cudaGetLastError());
-  cb = L.cub_bytes;
-  GLAB_CUDA(cub::DeviceScan::ExclusiveSum(ctmp, cb, rowoff, rowoff, (int)(n + 1), st));
-  const int col_bits = bits_for(Y->n_cols);
+  const int col_bits = bits_for(Y->n_cols);   // (rowoff already holds the expansion offsets)
   k_spgemm_expand<T><<<grid1d(n * 8, X->sm_count), 256, 0, st>>>(X->rowptr, X->colidx, xv, Y->rowptr, Y->colidx,
                                                               yv, n, rowoff, col_bits, k[0], v[0]);
   GLAB_CUDA(cudaGetLastError());
@@ -475,9 +569,13 @@ static int spgemm_numeric(const glab_plan* X, const T* xv, const glab_plan* Y, c
   int64_t path = 0;  // which path the symbolic phase took (it left the row offsets / sorted runs)
   GLAB_CUDA(cudaMemcpyAsync(&path, hdr + 3, 8, cudaMemcpyDeviceToHost, st));
   GLAB_CUDA(cudaStreamSynchronize(st));
-  if (path == 1)
-    return spgemm_rows_launch<T, true>(X, xv, Y, yv, reinterpret_cast<int32_t*>(base + L.rowoff), out_row, out_col,
-                                       out_val, hdr, st);
+  if (path == 1) {
+    k_spgemm_unpark<T><<<grid1d(X->n_rows, X->sm_count), 256, 0, st>>>(
+        reinterpret_cast<const int64_t*>(base + L.rowoff), reinterpret_cast<const int32_t*>(base + L.rowcnt),
+        reinterpret_cast<const int32_t*>(base + L.keys[0]), reinterpret_cast<const T*>(base + L.vals[0]), X->n_rows,
+        out_row, out_col, out_val);
+    return (int)cudaGetLastError();
+  }
   if (path != 2 || !L.esc) return GLAB_E_ARG;  // symbolic phase did not run on this workspace
   k_spgemm_compress<T><<<grid1d(nnz_out, X->sm_count), 256, 0, st>>>(
       hdr, reinterpret_cast<const uint64_t*>(base + L.keys[0]), reinterpret_cast<const uint64_t*>(base + L.keys[1]),

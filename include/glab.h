@@ -510,19 +510,22 @@ int glab_interp_fill_f64(const glab_plan* A_off, const double* w_slots, const do
  * operator.  Products that meet in one entry are added sequentially in expansion order (X slot
  * order, then Y slot order): deterministic and independent of the launch geometry and of the
  * path taken.  Two paths: "row-local" (one thread per output row keeps the row's distinct columns
- * sorted in shared memory; taken when no row has more than 64 distinct columns, i.e. for every
- * stencil / Galerkin operator; every byte crosses HBM once) and "ESC" (expand - stable radix
- * sort - compress through the workspace; the fallback for dense-ish rows).
+ * and their sums sorted in a shared-memory strip of 16 / 32 / 64 entries -- the smallest that holds
+ * the rows -- in ONE pass during the symbolic call, parks the finished rows in the workspace, and
+ * the numeric call compacts them; taken when no row has more than 64 distinct columns, i.e. for
+ * every stencil / Galerkin operator) and "ESC" (expand - stable radix sort - compress through the
+ * workspace; the fallback for dense-ish rows).
  *   products (host-synchronous): number of scalar multiplications sum_{(i,j) in X} nnz(Y_j*) and
  *     the largest such count of a single row; scratch16 = 16 bytes of device memory.
  *     n_products must be < 2^31 - 64 (GLAB_E_RANGE otherwise).
  *   workspace_bytes: size of the caller-owned device workspace (elem_size 4 or 8); negative =
- *     error code.  8 bytes per X row when max_row_products <= 64 (row-local path guaranteed),
- *     else about (16 + 2 * elem_size) bytes per product.
- *   symbolic (host-synchronous): returns nnz(Z) and leaves the row offsets / sorted runs in the
- *     workspace.
- *   numeric (host-synchronous): writes the nnz(Z) entries; same X, Y, values, workspace and counts
- *     as symbolic. */
+ *     error code.  12 bytes per X row + (4 + elem_size) bytes per product when
+ *     max_row_products <= 64 (row-local path guaranteed), else about (16 + 2 * elem_size) bytes
+ *     per product.
+ *   symbolic (host-synchronous): returns nnz(Z) and leaves the parked rows / sorted runs in the
+ *     workspace.  It reads the VALUES: the row-local path finishes the arithmetic here.
+ *   numeric (host-synchronous): writes the nnz(Z) entries; MUST be given the same X, Y, values,
+ *     workspace and counts as the symbolic call (a new set of values needs a new symbolic call). */
 int glab_spgemm_products(const glab_plan* X, const glab_plan* Y, void* scratch16, int64_t* n_products,
                          int64_t* max_row_products, void* stream);
 int64_t glab_spgemm_workspace_bytes(int64_t n_rows_x, int64_t n_products, int64_t max_row_products,

@@ -37,6 +37,7 @@ def main():
     ap.add_argument("--reps", type=int, default=3)
     ap.add_argument("--split", default="alternating", choices=["pmis", "alternating"])
     ap.add_argument("--no-library", action="store_true")
+    ap.add_argument("--profile", action="store_true", help="kernel list (torch.profiler) of the two SpGEMMs")
     args = ap.parse_args()
     dev = torch.device("cuda:0")
     rt, V = G.runtime, G.VCycle
@@ -92,6 +93,17 @@ def main():
         res["galerkin_max_abs_diff_vs_library"] = d
         res["nnz_Ac_library"] = int(Ac_lib._nnz())
     print(json.dumps(res))
+    if args.profile:
+        from torch.profiler import profile, ProfilerActivity
+        with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU]) as prof:
+            rt.spgemm(plan_A, vals_A, plan_P, pv)
+            torch.cuda.synchronize()
+            rt.spgemm(plan_PT, vals_PT, plan_AP, ap_v)
+            torch.cuda.synchronize()
+        rows = sorted((e.time_range.start, e.name[:100], e.device_time) for e in prof.events()
+                      if e.device_type == torch.autograd.DeviceType.CUDA)
+        for st, nm, us in rows:
+            print("%9.1f us  %8.1f us  %s" % (st - rows[0][0], us, nm))
 
 
 if __name__ == "__main__":
