@@ -72,9 +72,29 @@ template <typename T> struct OpDirectInterp {
 static inline int round_up128(int x) { return (x + 127) / 128 * 128; }
 
 // TMA pipeline variant; returns -1000 when the operator does not fit (caller falls back).
+template <typename T, class Op, bool IDX16>
+static int launch_edge_pipe_impl(const glab_plan* p, const T* vals, const T* aux, const Op& op, T* out, void* stream);
+
+// Operators that read the column index can stream 16-bit row-relative indices on every tile whose
+// columns lie within +-32767 of their rows (plan: coldelta / tile16).  OFF by default (GLAB_EDGE_IDX16=1
+// enables it): measured on D4096 fp32 (B200, profiles/r02_kernel_notes.md) soc_sa 0.3075 ms and
+// direct_interp 0.3997 ms with 16-bit indices vs 0.3049 / 0.3848 ms with int32 -- these passes are bound by
+// the dependent diag[col] gather and the IEEE divisions (issue slots), not by HBM bytes, so streaming
+// 2 bytes per edge less buys nothing and the per-tile branch costs a little.
 template <typename T, class Op>
 static int launch_edge_pipe(const glab_plan* p, const T* vals, const T* aux, const Op& op, T* out,
                             void* stream) {
+  if constexpr (Op::kNeedCol) {
+    static const bool allow = [] { const char* e = getenv("GLAB_EDGE_IDX16"); return e && atoi(e) != 0; }();
+    if (allow && p->coldelta && p->tile16 && p->tiles16 > 0)
+      return launch_edge_pipe_impl<T, Op, true>(p, vals, aux, op, out, stream);
+  }
+  return launch_edge_pipe_impl<T, Op, false>(p, vals, aux, op, out, stream);
+}
+
+template <typename T, class Op, bool IDX16>
+static int launch_edge_pipe_impl(const glab_plan* p, const T* vals, const T* aux, const Op& op, T* out,
+                                 void* stream) {
   if (getenv("GLAB_PIPE") && atoi(getenv("GLAB_PIPE")) == 0) return -1000;
   if (reinterpret_cast<uintptr_t>(p->rowptr) & 15) return -1000;
   const int64_t slots = (int64_t)kThreads * (p->max_row_nnz > 0 ? p->max_row_nnz : 1);
@@ -86,7 +106,7 @@ static int launch_edge_pipe(const glab_plan* p, const T* vals, const T* aux, con
   L.off_col = off; if (Op::kNeedCol) off += round_up128((int)slots * 4 + 32);
   L.off_aux = off; if (Op::kNarr > 1) off += round_up128((int)slots * (int)sizeof(T) + 32);
   L.stage_bytes = off;
-  auto kern = k_edge_pipe<T, Op>;
+  auto kern = k_edge_pipe<T, Op, IDX16>;
   static int max_smem_dev[kMaxDevices] = {};
   int& max_smem = max_smem_dev[p->device % kMaxDevices];
   if (!max_smem) {
@@ -108,7 +128,8 @@ static int launch_edge_pipe(const glab_plan* p, const T* vals, const T* aux, con
   const int ntiles = (int)((p->n_rows + kThreads - 1) / kThreads);
   int grid = p->sm_count * occ;
   if (grid > ntiles) grid = ntiles;
-  TileArgs<T> a{p->rowptr, p->colidx, vals, 0, (int)p->n_rows, (int)slots};
+  TileArgs<T> a{p->rowptr, p->colidx, vals, 0, (int)p->n_rows, (int)slots, IDX16 ? p->coldelta : nullptr,
+                IDX16 ? p->tile16 : nullptr};
   kern<<<grid, kPipeThreads, smem, as_stream(stream)>>>(a, aux ? aux : vals, p->perm, op, out, ntiles, L);
   return (int)cudaGetLastError();
 }

@@ -446,6 +446,32 @@ static int launch_pdl(Kern kern, int grid, int block, size_t smem, cudaStream_t 
   cfg.numAttrs = 1;
   return (int)cudaLaunchKernelEx(&cfg, kern, args...);
 }
+// Cooperative launch: the driver starts the grid only when ALL of its CTAs can be resident at once and
+// rejects one that can never be (cudaErrorCooperativeLaunchTooLarge).  For the kernels whose CTAs wait on
+// each other (the fused halo steps) this turns "a CTA was not scheduled because another context / stream
+// holds SMs" from a spin into a queued launch.  It excludes programmatic dependent launch.
+template <typename Kern, typename... Args>
+static int launch_coop(Kern kern, int grid, int block, size_t smem, cudaStream_t st, Args... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3((unsigned)grid);
+  cfg.blockDim = dim3((unsigned)block);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeCooperative;
+  attr[0].val.cooperative = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return (int)cudaLaunchKernelEx(&cfg, kern, args...);
+}
+// GLAB_HALO_COOP=1: launch the fused halo steps cooperatively (shared GPUs: MPS, concurrent streams, green
+// contexts).  Default 0: on a GPU the process owns, grid = SMs x occupancy is resident by construction and
+// the programmatic dependent launch between consecutive steps is worth ~2 us per step; the in-kernel waits
+// are bounded either way (GLAB_STATUS_TIMEOUT_*).
+static bool halo_coop() {
+  static const bool v = [] { const char* e = getenv("GLAB_HALO_COOP"); return e && atoi(e) != 0; }();
+  return v;
+}
 static inline int round_up(int x, int m) { return (x + m - 1) / m * m; }
 template <typename T, int K, int U, class Epi>
 static int launch_pipe_halo(const glab_plan*, const T*, const T*, const Epi&, void*, const glab_halo_step*);
@@ -591,6 +617,7 @@ static int launch_pipe_halo_impl(const glab_plan* p, const T* vals, const T* x, 
   if (grid < 2 && hs->n_push > 0) grid = 2;   // a block without rows still has to publish its arrival
   TileArgs<T> a{p->rowptr, p->colidx, vals, 0, (int)n, (int)slots, IDX ? p->coldelta : nullptr,
                 IDX == 2 ? p->tile16 : nullptr};
+  if (halo_coop()) return launch_coop(kern, grid, kPipeThreads, smem, as_stream(stream), a, x, epi, ntiles, L, h);
   return launch_pdl(kern, grid, kPipeThreads, smem, as_stream(stream), tuning().pdl != 0, a, x, epi, ntiles, L, h);
 }
 

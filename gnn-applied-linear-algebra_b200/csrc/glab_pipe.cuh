@@ -633,7 +633,11 @@ template <typename E, int V> __device__ __forceinline__ void sts_vec(E* p, const
   }
 }
 
-template <typename T, class Op>
+// IDX16: tiles flagged in a.tile16 stream 16-bit row-relative column indices (a.coldelta: col - row) in
+// place of the int32 ones -- 2 bytes per edge less HBM traffic for the operators that read the column
+// (soc_sa, direct_interp); the other tiles (wrap-around / far columns) keep int32.  The flag is per tile,
+// so the consumer branches once per tile around two straight-line row bodies.
+template <typename T, class Op, bool IDX16 = false>
 __global__ void __launch_bounds__(kPipeThreads, 4)
 k_edge_pipe(TileArgs<T> a, const T* __restrict__ aux, const int32_t* __restrict__ perm, Op op,
             T* __restrict__ out, int ntiles, EdgePipeLayout L) {
@@ -685,7 +689,8 @@ k_edge_pipe(TileArgs<T> a, const T* __restrict__ aux, const int32_t* __restrict_
           align16(a.vals + e0, (e1 - e0) * (int)sizeof(T), src_v, nb_v);
           total += nb_v;
           if (Op::kNeedCol) {
-            align16(a.colidx + e0, (e1 - e0) * 4, src_c, nb_c);
+            if (IDX16 && __ldg(a.tile16 + tile)) align16(a.coldelta + e0, (e1 - e0) * 2, src_c, nb_c);
+            else align16(a.colidx + e0, (e1 - e0) * 4, src_c, nb_c);
             total += nb_c;
           }
           if (Op::kNarr > 1) {
@@ -716,6 +721,52 @@ k_edge_pipe(TileArgs<T> a, const T* __restrict__ aux, const int32_t* __restrict_
       T* sval = reinterpret_cast<T*>(sb + L.off_val) + lead_elems(a.vals + e0, sizeof(T)) - e0;
       const int32_t* scol = reinterpret_cast<const int32_t*>(sb + L.off_col) + lead_elems(a.colidx + e0, 4) - e0;
       const T* saux = reinterpret_cast<const T*>(sb + L.off_aux) + lead_elems(aux + e0, sizeof(T)) - e0;
+      bool t16 = false;
+      if constexpr (IDX16 && Op::kNeedCol) t16 = __ldg(a.tile16 + tile) != 0;
+      if (t16) {
+        if constexpr (IDX16 && Op::kNeedCol) {
+          const int16_t* sdel = reinterpret_cast<const int16_t*>(sb + L.off_col) + lead_elems(a.coldelta + e0, 2) - e0;
+          if (r < r1) {
+            const int rs = srow[tid], re = srow[tid + 1];
+            typename Op::RowState st;
+            op.begin_row(st, r);
+            const bool vec = ((re - rs) % V == 0) && ((reinterpret_cast<uintptr_t>(sval + rs) & 15) == 0) &&
+                             ((reinterpret_cast<uintptr_t>(sdel + rs) & (V * 2 - 1)) == 0) &&
+                             (Op::kNarr < 2 || (reinterpret_cast<uintptr_t>(saux + rs) & 15) == 0);
+            if (vec) {
+              if (Op::kReduce) {
+                for (int j = rs; j < re; j += V) {
+                  T v[V], x2[V];
+                  int16_t d[V];
+                  lds_vec<T, V>(v, sval + j);
+                  lds_vec<int16_t, V>(d, sdel + j);
+                  if (Op::kNarr > 1) lds_vec<T, V>(x2, saux + j);
+#pragma unroll
+                  for (int u = 0; u < V; ++u) op.accumulate(st, v[u], Op::kNarr > 1 ? x2[u] : T(0), r + (int)d[u]);
+                }
+              }
+              op.end_row(st, r);
+              for (int j = rs; j < re; j += V) {
+                T v[V], x2[V], o[V];
+                int16_t d[V];
+                lds_vec<T, V>(v, sval + j);
+                lds_vec<int16_t, V>(d, sdel + j);
+                if (Op::kNarr > 1) lds_vec<T, V>(x2, saux + j);
+#pragma unroll
+                for (int u = 0; u < V; ++u) o[u] = op.edge(st, v[u], Op::kNarr > 1 ? x2[u] : T(0), r + (int)d[u]);
+                sts_vec<T, V>(sval + j, o);
+              }
+            } else {
+              if (Op::kReduce)
+                for (int j = rs; j < re; ++j)
+                  op.accumulate(st, sval[j], Op::kNarr > 1 ? saux[j] : T(0), r + (int)sdel[j]);
+              op.end_row(st, r);
+              for (int j = rs; j < re; ++j)
+                sval[j] = op.edge(st, sval[j], Op::kNarr > 1 ? saux[j] : T(0), r + (int)sdel[j]);
+            }
+          }
+        }
+      } else
       if (r < r1) {
         const int rs = srow[tid], re = srow[tid + 1];
         typename Op::RowState st;

@@ -369,6 +369,15 @@ int glab_halo_wait(int n_flags, uint32_t* const* flags, const uint32_t* pushed_l
  * peer-mapped pointers of `push`, release-increments their arrival counters and ++*pushed_counter.
  * interior_begin / interior_end must be multiples of 256.  All arrays are HOST arrays copied at
  * launch; done_counter is a zero-initialised device word owned by the caller.
+ *
+ * Residency: the CTAs of a fused step wait on each other (boundary tiles on the communication CTA's
+ * counters), so the whole grid (SMs x occupancy) must be resident at once.  On a GPU the process owns
+ * that holds by construction.  On a shared GPU (MPS, other streams, green contexts) set
+ * GLAB_HALO_COOP=1: the steps are then launched with cudaLaunchAttributeCooperative -- the driver
+ * starts the grid only when all of it fits -- at the price of the programmatic dependent launch
+ * between consecutive steps.  Either way every in-kernel wait is bounded (`timeout_ms`): a step that
+ * gives up sets GLAB_STATUS_TIMEOUT_* bits in *status instead of hanging, and its results are
+ * undefined.  The multi-sweep entry points (glab_jacobi_sweeps_*) are always launched cooperatively.
  * ------------------------------------------------------------------------------------------ */
 /* 1 if the fused halo steps (glab_*_halo_*) can take this operator with k right-hand-side columns of
  * `elem_bytes`-wide values: a 256-row tile of max_row_nnz slots plus the vertex streams must fit two

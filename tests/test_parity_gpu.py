@@ -1029,3 +1029,22 @@ def test_pack_unpack_layout_glue(G, dev, dt, n):
         rt.unpack(cat, [(0, 1), (1, 1), (2, 1)], outs=outs)
         for got, want in zip(outs, parts):
             assert torch.equal(got, want)
+
+
+def test_config2_full_size_layer_pass_vs_independent_fp64_grid_stencil(G, dev):
+    """BASELINE config 2 at FULL size through the drop-in layers (JacobiGNN(10) + ChebyRelaxGNN(4) on the
+    4096^2 Laplacian) against an INDEPENDENT formulation: the same 10 sweeps and the degree-4 Chebyshev
+    recurrence evaluated in fp64 with shifted [N, N] grid slices -- no CSR, no plan, no kernel of this
+    package on the checking side (the check bench.py's parity block runs; <= 1e-5 relative)."""
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    if root not in sys.path:
+        sys.path.insert(0, root)
+    from bench_support import SingleGpuSmoother
+    prob = SingleGpuSmoother(G, 4096, dev)
+    res = prob.parity()
+    assert res["ok"], res
+    assert res["jacobi10_rel_err"] <= 1e-5 and res["chebyshev4_x_rel_err"] <= 1e-5, res
+    assert res["rows_checked"] == 4096 * 4096
+    del prob
+    torch.cuda.empty_cache()
