@@ -3,7 +3,9 @@
 
     python scripts/ncu_summary.py gpurun_out/prof.ncu-rep profiles/r01_jacobi_full.txt [--traffic-json profiles/traffic.json]
 
-Reads the report with `ncu -i ... --page raw --csv` (works without a GPU)."""
+Reads the report with `ncu -i ... --page raw --csv` (works without a GPU); a first argument ending in
+`.csv` is taken as that export itself (reports are ~30 MB each: on the GPU box they are written to /tmp
+and only the CSV pages travel back)."""
 import csv
 import io
 import json
@@ -32,7 +34,10 @@ WANT = [
 def main():
     rep, out = sys.argv[1], sys.argv[2]
     tj = sys.argv[sys.argv.index("--traffic-json") + 1] if "--traffic-json" in sys.argv else None
-    raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    if rep.endswith(".csv"):
+        raw = open(rep).read()
+    else:
+        raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(io.StringIO(raw)))
     hdr, units, data = rows[0], rows[1], rows[2:]
     ki = hdr.index("Kernel Name")
