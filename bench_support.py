@@ -238,8 +238,10 @@ class PartitionedSmoother(_Staged):
         frac16 = self.op.plan.index16_tiles / max(self.op.plan.tiles, 1)
         self.index_bytes = 4 - 2.0 * frac16 if (halo16 or engine != "peer") else 4.0
         self.setup_info["halo_kernels_use_index16"] = bool(halo16 and engine == "peer")
-        self.setup_info["jacobi_sweeps_per_launch"] = "multi-sweep kernel" if getattr(self.op, "multi_sweep", False) \
-            and engine == "peer" else "one launch per sweep"
+        # glab_jacobi_sweeps_halo_* runs all sweeps in one launch only for row blocks of <= 4096 tiles (kMsAutoTiles)
+        ms = getattr(self.op, "multi_sweep", False) and getattr(self.op, "fused", False) and \
+            (self.op.plan.tiles <= 4096 or os.environ.get("GLAB_MS", "1") == "2") and os.environ.get("GLAB_MS", "1") != "0"
+        self.setup_info["jacobi_sweeps_per_launch"] = "multi-sweep kernel" if ms else "one launch per sweep"
         from bench_extra import hashed_uniform
         self.b_host = hashed_uniform(r0, r1, 1, "cpu").pin_memory()
         self.x_host = hashed_uniform(r0, r1, 2, "cpu").pin_memory()
