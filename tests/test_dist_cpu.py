@@ -30,6 +30,19 @@ def _problem(kind):
         N = 12
         ei, ev = port.laplacian_2d(N)
         return N * N, ei, ev
+    if kind == "upwind":
+        # structurally NON-symmetric: row i couples to i and i + N only, so rank q reads rows of rank q + 1 but
+        # sends nothing back -- one-directional neighbours (peers = union of send and receive sides)
+        N = 12
+        n = N * N
+        i_ = torch.arange(n)
+        up = i_[: n - N]
+        ei = torch.cat([torch.stack([i_, i_]), torch.stack([up, up + N])], 1)
+        order = torch.argsort(ei[0] * n + ei[1])
+        ei = ei[:, order].contiguous()
+        ev = torch.where(ei[0] == ei[1], torch.tensor(4.0, dtype=torch.float64),
+                         torch.tensor(-1.0, dtype=torch.float64)).view(-1, 1)
+        return n, ei, ev
     # random sparse operator: every rank talks to every other rank
     n, z = 157, 1500
     g = torch.Generator().manual_seed(3)
@@ -95,6 +108,11 @@ def _worker(rank, world, port_no, kind, q):
         ss = (y_loc ** 2).sum(0)
         dist.all_reduce(ss)
         assert torch.allclose(ss, (y_ref ** 2).sum(0), rtol=1e-13)
+        if kind == "upwind":
+            # receive only from the next rank, send only to the previous one; both are peers
+            assert halo.peers_recv == ([rank + 1] if rank + 1 < world else [])
+            assert halo.peers_send == ([rank - 1] if rank > 0 else [])
+            assert halo.peers == sorted(set(halo.peers_recv) | set(halo.peers_send))
         q.put((rank, "ok", halo.n_halo, halo.peers_recv))
     except Exception as e:  # pragma: no cover
         import traceback
@@ -103,7 +121,8 @@ def _worker(rank, world, port_no, kind, q):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("kind,world", [("laplacian", 2), ("laplacian", 3), ("random", 2), ("random", 3)])
+@pytest.mark.parametrize("kind,world", [("laplacian", 2), ("laplacian", 3), ("random", 2), ("random", 3),
+                                        ("upwind", 2), ("upwind", 3)])
 def test_partition_and_halo_exchange(kind, world):
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
