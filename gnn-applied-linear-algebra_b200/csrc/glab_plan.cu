@@ -285,6 +285,78 @@ __global__ void __launch_bounds__(256) k_pack(PackArgs<T> a, int64_t n, int ld, 
   }
 }
 
+// Single-column parts (k = 1: vertex_attr = [A_ii, b, x], [b, x], [b, x, r, p]): a register transpose, no
+// shared memory, no barriers.  A thread owns R = 16 / sizeof(T) consecutive rows: one 16-byte vector per
+// part on the dense side, LD vectors (R * LD contiguous elements) on the interleaved side -- both sides
+// perfectly coalesced.  col[c] = the part that holds column c (NULL: column not wanted / not written).
+template <typename T, int LD> struct ColArgs { T* col[LD]; };
+
+template <typename T, int LD, bool Pack>
+__global__ void __launch_bounds__(256) k_pack_cols(ColArgs<T, LD> a, int64_t n, T* __restrict__ inter) {
+  constexpr int R = 16 / (int)sizeof(T);
+  const int64_t groups = n / R;
+  for (int64_t g = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; g < groups; g += (int64_t)gridDim.x * blockDim.x) {
+    union { uint4 q[LD]; T e[R * LD]; } w;   // interleaved side: row-major [R][LD]
+    if (Pack) {
+#pragma unroll
+      for (int c = 0; c < LD; ++c) {
+        union { uint4 q; T e[R]; } v;
+        v.q = __ldcs(reinterpret_cast<const uint4*>(a.col[c] + g * R));
+#pragma unroll
+        for (int r = 0; r < R; ++r) w.e[r * LD + c] = v.e[r];
+      }
+      uint4* dst = reinterpret_cast<uint4*>(inter + g * R * LD);
+#pragma unroll
+      for (int i = 0; i < LD; ++i) __stcs(dst + i, w.q[i]);
+    } else {
+      const uint4* src = reinterpret_cast<const uint4*>(inter + g * R * LD);
+#pragma unroll
+      for (int i = 0; i < LD; ++i) w.q[i] = __ldcs(src + i);
+#pragma unroll
+      for (int c = 0; c < LD; ++c) {
+        if (a.col[c] == nullptr) continue;
+        union { uint4 q; T e[R]; } v;
+#pragma unroll
+        for (int r = 0; r < R; ++r) v.e[r] = w.e[r * LD + c];
+        __stcs(reinterpret_cast<uint4*>(a.col[c] + g * R), v.q);
+      }
+    }
+  }
+  // ragged tail: fewer than R rows
+  if (blockIdx.x == 0) {
+#pragma unroll
+    for (int c = 0; c < LD; ++c)   // (static indices: the pointer array stays in the parameter space)
+      if (threadIdx.x == c && a.col[c] != nullptr)
+        for (int64_t r = groups * R; r < n; ++r) {
+          if (Pack) inter[r * LD + c] = a.col[c][r];
+          else a.col[c][r] = inter[r * LD + c];
+        }
+  }
+}
+
+// Returns -1000 when the call is not of the single-column shape (caller takes the tiled kernel).
+template <typename T, int LD, bool Pack>
+static int pack_cols_launch(int64_t n, int n_parts, T* const* parts, const int32_t* widths, const int32_t* offsets,
+                            T* inter, void* stream) {
+  ColArgs<T, LD> a;
+  for (int c = 0; c < LD; ++c) a.col[c] = nullptr;
+  if (reinterpret_cast<uintptr_t>(inter) & 15) return -1000;
+  for (int j = 0; j < n_parts; ++j) {
+    if (widths[j] != 1 || offsets[j] < 0 || offsets[j] >= LD || a.col[offsets[j]] != nullptr) return -1000;
+    if (!parts[j] || (reinterpret_cast<uintptr_t>(parts[j]) & 15)) return -1000;
+    a.col[offsets[j]] = parts[j];
+  }
+  if (Pack)
+    for (int c = 0; c < LD; ++c)
+      if (a.col[c] == nullptr) return -1000;   // a packed block has no holes
+  constexpr int R = 16 / (int)sizeof(T);
+  int64_t blocks = (n / R + 255) / 256;
+  if (blocks < 1) blocks = 1;
+  if (blocks > (int64_t)148 * 64) blocks = (int64_t)148 * 64;
+  k_pack_cols<T, LD, Pack><<<(unsigned)blocks, 256, 0, as_stream(stream)>>>(a, n, inter);
+  return (int)cudaGetLastError();
+}
+
 template <typename T, bool Pack>
 static int pack_launch(int64_t n, int64_t ld, int n_parts, T* const* parts, const int32_t* widths,
                        const int32_t* offsets, T* inter, void* stream) {
@@ -298,6 +370,15 @@ static int pack_launch(int64_t n, int64_t ld, int n_parts, T* const* parts, cons
     a.part[j] = parts[j];
     a.width[j] = widths[j];
     a.offset[j] = offsets[j];
+  }
+  if (ld >= 2 && ld <= 4) {
+    int rc = -1000;
+    switch ((int)ld) {
+      case 2: rc = pack_cols_launch<T, 2, Pack>(n, n_parts, parts, widths, offsets, inter, stream); break;
+      case 3: rc = pack_cols_launch<T, 3, Pack>(n, n_parts, parts, widths, offsets, inter, stream); break;
+      default: rc = pack_cols_launch<T, 4, Pack>(n, n_parts, parts, widths, offsets, inter, stream); break;
+    }
+    if (rc != -1000) return rc;
   }
   // tile height: kPackRows while two copies of the tile fit 64 KB of shared memory, else fewer rows --
   // wide interleaved blocks (ld up to 64) keep the old 256-row tiles
