@@ -358,6 +358,149 @@ static int spgemm_rows_launch(const glab_plan* X, const T* xv, const glab_plan* 
   return (int)cudaGetLastError();
 }
 
+// ---- row-local path, CTA-cooperative variant ------------------------------------------------------
+// The thread-per-row kernel above interleaves its gathers with the insertion: every load of a warp
+// touches 32 different sectors and waits for the previous insertion.  Here a CTA of 128 threads takes
+// 128 consecutive X rows and separates the two:
+//   1. the rows' X slots are ONE contiguous range: loaded coalesced, with the Y row bounds of every slot;
+//   2. a block scan of the Y row lengths gives every slot the offset of its products -- slot order, then Y
+//      order: exactly the documented expansion order, and equal to poff[r] - poff[r0] for each row;
+//   3. all threads expand all slots into a shared product list (column, a * y): independent loads, no
+//      insertion in between, as many in flight as the LSU takes;
+//   4. thread-per-row insertion sort IN PLACE inside the row's own segment of the list (a row has at most
+//      as many distinct columns as products, and product t is read before anything is written at
+//      index <= t): shared memory only, same sequential sums as the strip kernel -> same bits;
+//   5. the whole list goes to the parking area at poff[r0] with coalesced stores (the entries behind a
+//      row's distinct count are dead and never read).
+// No strip height, no overflow: taken whenever 128 rows' slots and products fit kCoopSmem.
+constexpr int kCoopRows = 128;
+constexpr int kCoopSmem = 64 * 1024;
+
+template <typename T> __host__ __device__ inline size_t coop_smem_bytes(int s_max, int p_max) {
+  return (size_t)(p_max + s_max) * sizeof(T) + (size_t)(p_max + 2 * s_max + kCoopRows + 8 + 8) * 4;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kCoopRows)
+k_spgemm_rows_coop(const int32_t* __restrict__ xrp, const int32_t* __restrict__ xci, const T* __restrict__ xv,
+                   const int32_t* __restrict__ yrp, const int32_t* __restrict__ yci, const T* __restrict__ yv,
+                   int64_t n, const int64_t* __restrict__ poff, int32_t* __restrict__ rowcnt,
+                   int32_t* __restrict__ park_col, T* __restrict__ park_val, int s_max, int p_max) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  T* pval = reinterpret_cast<T*>(smem_raw);          // [p_max] products: value
+  T* sa = pval + p_max;                              // [s_max] X value of the slot
+  int32_t* pcol = reinterpret_cast<int32_t*>(sa + s_max);   // [p_max] products: column
+  int32_t* sy0 = pcol + p_max;                       // [s_max] first Y slot of the X slot's row
+  int32_t* soff = sy0 + s_max;                       // [s_max + 1] Y row length, then exclusive product offset
+  int32_t* rstart = soff + s_max + 4;                // [kCoopRows + 1] first product of each row
+  int32_t* wsum = rstart + kCoopRows + 4;            // [4] warp totals of the scan
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (blockIdx.x == 0 && tid == 0) rowcnt[n] = 0;    // sentinel: the exclusive scan leaves nnz(Z) here
+  for (int64_t r0 = (int64_t)blockIdx.x * kCoopRows; r0 < n; r0 += (int64_t)gridDim.x * kCoopRows) {
+    const int rows = (int)min((int64_t)kCoopRows, n - r0);
+    const int e0 = __ldg(xrp + r0), e1 = __ldg(xrp + r0 + rows);
+    const int S = e1 - e0;
+    // 1. X slots and the bounds of their Y rows
+    for (int i = tid; i < S; i += kCoopRows) {
+      const int j = __ldg(xci + e0 + i);
+      const int y0 = __ldg(yrp + j);
+      sy0[i] = y0;
+      soff[i] = __ldg(yrp + j + 1) - y0;
+      sa[i] = __ldg(xv + e0 + i);
+    }
+    __syncthreads();
+    // 2. exclusive scan of the lengths (thread t owns a chunk of consecutive slots)
+    const int chunk = (S + kCoopRows - 1) / kCoopRows;
+    const int c0 = min(S, tid * chunk), c1 = min(S, c0 + chunk);
+    int mine = 0;
+    for (int i = c0; i < c1; ++i) mine += soff[i];
+    int incl = mine;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int up = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += up;
+    }
+    if (lane == 31) wsum[warp] = incl;
+    __syncthreads();
+    int base = incl - mine;
+    for (int w = 0; w < warp; ++w) base += wsum[w];
+    const int P = wsum[0] + wsum[1] + wsum[2] + wsum[3];
+    for (int i = c0; i < c1; ++i) {
+      const int len = soff[i];
+      soff[i] = base;
+      base += len;
+    }
+    if (tid == 0) soff[S] = P;
+    __syncthreads();
+    if (tid <= rows) rstart[tid] = tid < rows ? soff[__ldg(xrp + r0 + tid) - e0] : P;
+    if (tid == 0 && rows == kCoopRows) rstart[kCoopRows] = P;
+    // 3. expansion: slot order, then Y order
+    for (int i = tid; i < S; i += kCoopRows) {
+      const int o = soff[i], len = soff[i + 1] - o, y0 = sy0[i];
+      const T a = sa[i];
+      for (int t = 0; t < len; ++t) {
+        pcol[o + t] = __ldg(yci + y0 + t);
+        pval[o + t] = a * __ldg(yv + y0 + t);
+      }
+    }
+    __syncthreads();
+    // 4. in-place insertion inside the row's segment
+    if (tid < rows) {
+      const int b = rstart[tid], len = rstart[tid + 1] - b;
+      int cnt = 0;
+      for (int t = 0; t < len; ++t) {
+        const int c = pcol[b + t];
+        const T v = pval[b + t];
+        int pos = cnt;
+        while (pos > 0 && pcol[b + pos - 1] >= c) --pos;
+        if (pos < cnt && pcol[b + pos] == c) {
+          pval[b + pos] = pval[b + pos] + v;
+          continue;
+        }
+        for (int q = cnt; q > pos; --q) {
+          pcol[b + q] = pcol[b + q - 1];
+          pval[b + q] = pval[b + q - 1];
+        }
+        pcol[b + pos] = c;
+        pval[b + pos] = v;
+        ++cnt;
+      }
+      rowcnt[r0 + tid] = cnt;
+    }
+    __syncthreads();
+    // 5. park the list (row r's entries land at poff[r] + s because poff[r] - poff[r0] == rstart[r - r0])
+    const int64_t pb = __ldg(poff + r0);
+    for (int i = tid; i < P; i += kCoopRows) {
+      park_col[pb + i] = pcol[i];
+      park_val[pb + i] = pval[i];
+    }
+    __syncthreads();
+  }
+}
+
+// Returns -1000 if 128 rows' slots / products do not fit the shared-memory budget.
+template <typename T>
+static int spgemm_rows_coop_launch(const glab_plan* X, const T* xv, const glab_plan* Y, const T* yv,
+                                   const int64_t* poff, int32_t* rowcnt, int32_t* park_col, T* park_val,
+                                   int64_t max_row_products, cudaStream_t st) {
+  const int64_t s_need = (int64_t)kCoopRows * (X->max_row_nnz > 0 ? X->max_row_nnz : 1);
+  const int64_t p_need = (int64_t)kCoopRows * (max_row_products > 0 ? max_row_products : 1);
+  if (s_need > (1 << 20) || p_need > (1 << 20)) return -1000;
+  const int s_max = (int)((s_need + 3) & ~3), p_max = (int)((p_need + 3) & ~3);
+  const size_t smem = coop_smem_bytes<T>(s_max, p_max);
+  if (smem > (size_t)kCoopSmem) return -1000;
+  auto kern = k_spgemm_rows_coop<T>;
+  GLAB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kCoopSmem));
+  const int64_t n = X->n_rows;
+  int64_t blocks = (n + kCoopRows - 1) / kCoopRows;
+  const int64_t cap = (int64_t)X->sm_count * 32;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  kern<<<(unsigned)blocks, kCoopRows, smem, st>>>(X->rowptr, X->colidx, xv, Y->rowptr, Y->colidx, yv, n, poff, rowcnt,
+                                                  park_col, park_val, s_max, p_max);
+  return (int)cudaGetLastError();
+}
+
 // Parked rows -> COO output (row, col as int64).  One warp per 32 consecutive rows: the lanes hold the
 // rows' output and parking offsets, walk the rows' OUTPUT range 32 entries at a time (coalesced stores,
 // near-contiguous loads) and find each entry's row by a shuffle binary search over the 32 offsets.
@@ -490,6 +633,24 @@ static int spgemm_symbolic(const glab_plan* X, const T* xv, const glab_plan* Y, 
   k_spgemm_count<<<grid1d(n + 1, X->sm_count), 256, 0, st>>>(X->rowptr, X->colidx, Y->rowptr, n, rowoff, nullptr);
   GLAB_CUDA(cudaGetLastError());
   GLAB_CUDA(cub::DeviceScan::ExclusiveSum(ctmp, cb, rowoff, rowoff, (int)(n + 1), st));
+  // ---- row-local, CTA-cooperative (no strip, no overflow) when 128 rows fit the shared-memory budget
+  {
+    static const bool coop_ok = [] { const char* e = getenv("GLAB_SPGEMM_COOP"); return !(e && atoi(e) == 0); }();
+    rc = coop_ok ? spgemm_rows_coop_launch<T>(X, xv, Y, yv, rowoff, rowcnt, park_col, park_val, max_row_products, st)
+                 : -1000;
+    if (rc != -1000) {
+      if (rc) return rc;
+      cb = L.cub_bytes;
+      GLAB_CUDA(cub::DeviceScan::ExclusiveSum(ctmp, cb, rowcnt, rowcnt, (int)(n + 1), st));
+      int32_t total = 0;
+      GLAB_CUDA(cudaMemcpyAsync(&total, rowcnt + n, 4, cudaMemcpyDeviceToHost, st));
+      k_spgemm_store_hdr<<<1, 1, 0, st>>>(hdr, 3, 1);
+      GLAB_CUDA(cudaStreamSynchronize(st));
+      GLAB_CUDA(cudaGetLastError());
+      *nnz_out = total;
+      return 0;
+    }
+  }
   // ---- row-local attempts: the smallest strip that can hold the rows, one size up on overflow
   const int ladder[3] = {16, 32, kRowCap};
   int first = max_row_products <= 16 ? 0 : 1;      // more than 16 products: most stencil products fit 32 columns

@@ -518,11 +518,12 @@ int glab_interp_fill_f64(const glab_plan* A_off, const double* w_slots, const do
  * (UtilsGNN.py:74-78), so it can be handed to glab_plan_create and to every layer as the next
  * operator.  Products that meet in one entry are added sequentially in expansion order (X slot
  * order, then Y slot order): deterministic and independent of the launch geometry and of the
- * path taken.  Two paths: "row-local" (one thread per output row keeps the row's distinct columns
- * and their sums sorted in a shared-memory strip of 16 / 32 / 64 entries -- the smallest that holds
- * the rows -- in ONE pass during the symbolic call, parks the finished rows in the workspace, and
- * the numeric call compacts them; taken when no row has more than 64 distinct columns, i.e. for
- * every stencil / Galerkin operator) and "ESC" (expand - stable radix sort - compress through the
+ * path taken.  Two paths: "row-local" (ONE pass during the symbolic call: a CTA expands the products
+ * of 128 consecutive rows into shared memory and every thread insertion-sorts its row's segment in
+ * place -- or, for rows too wide for that, one thread per row keeps the row's distinct columns and
+ * sums in a shared-memory strip of 16 / 32 / 64 entries; the finished rows are parked in the
+ * workspace and the numeric call compacts them; taken when no row has more than 64 distinct columns
+ * or 128 rows' products fit 64 KB, i.e. for every stencil / Galerkin operator) and "ESC" (expand - stable radix sort - compress through the
  * workspace; the fallback for dense-ish rows).
  *   products (host-synchronous): number of scalar multiplications sum_{(i,j) in X} nnz(Y_j*) and
  *     the largest such count of a single row; scratch16 = 16 bytes of device memory.
