@@ -564,6 +564,10 @@ def run_extras(G, dev, rank, world, peak, names, cpu_baseline, out=None):
                 res = X.l8192_layers(G, dev, peak, N=grid_big) if world == 1 else None
             elif name == "config3_power":
                 res = X.config3_power(G, dev, rank, world, peak, N=grid_big, cpu_baseline=cpu_baseline)
+                # config 3 in fp32 AND fp64 -- the fp64 run as a compact sub-result
+                r64 = X.config3_power(G, dev, rank, world, peak, N=grid_big, cpu_baseline=False, dtype=torch.float64)
+                res["fp64"] = {k_: r64[k_] for k_ in ("ms_per_iteration", "value_nnz_per_s", "lambda", "norm", "roofline",
+                                                      "parity") if k_ in r64}
             elif name == "config4_amg":
                 res = X.config4_amg(G, dev, peak, N=grid_amg, cpu_baseline=cpu_baseline) if world == 1 else None
             elif name == "config5_vcycle":

@@ -178,7 +178,7 @@ def _grid_power(b0_grid, iters):
     return float(((b * ab).sum() / (b * b).sum()).item()), float(nrm.item()), b
 
 
-def config3_power(G, dev, rank, world, peak, N=8192, iters=100, cpu_baseline=True):
+def config3_power(G, dev, rank, world, peak, N=8192, iters=100, cpu_baseline=True, dtype=torch.float32):
     rt = G.runtime
     from glab_b200 import dist as gd
     import torch.distributed as dist
@@ -186,12 +186,14 @@ def config3_power(G, dev, rank, world, peak, N=8192, iters=100, cpu_baseline=Tru
     part = gd.RowPartition(n, world, align=256)
     r0, r1 = part.bounds(rank)
     t0 = time.perf_counter()
-    ei, ev = G.generators.heat_fem_2d((N + 1, N + 1), (1.0, 1.0), torch.float32, dev, rows=(r0, r1))
+    f64 = dtype == torch.float64
+    tol = 1e-12 if f64 else TOL32
+    ei, ev = G.generators.heat_fem_2d((N + 1, N + 1), (1.0, 1.0), dtype, dev, rows=(r0, r1))
     ei, ev = ei.contiguous(), ev.contiguous()
-    b0 = hashed_uniform(r0, r1, 3, dev)
+    b0 = hashed_uniform(r0, r1, 3, dev).to(dtype)          # the same fp32-representable start vector in both precisions
     va = torch.cat([b0, torch.zeros_like(b0)], 1)
     ea = torch.cat([ev, torch.zeros_like(ev)], 1)
-    g0 = torch.zeros(3, device=dev)
+    g0 = torch.zeros(3, device=dev, dtype=dtype)
     layer = G.PowerMethodGNN.PowerMethodGNN(iters)
     graph = ei if world == 1 else gd.PartitionedGraph(ei, n, part, rank, world)
     torch.cuda.synchronize()
@@ -228,8 +230,10 @@ def config3_power(G, dev, rank, world, peak, N=8192, iters=100, cpu_baseline=Tru
     else:
         z = int(ei.shape[1])
     spmvs = iters + 1
-    s = 4
-    out = {"workload": "H%d: PowerMethodGNN(%d) on the %dx%d heat-equation FEM operator (9-point), fp32" % (N, iters, N, N),
+    s = 8 if f64 else 4
+    sfx = "f64" if f64 else "f32"
+    out = {"workload": "H%d: PowerMethodGNN(%d) on the %dx%d heat-equation FEM operator (9-point), %s"
+                       % (N, iters, N, N, "fp64" if f64 else "fp32"),
            "api": "PowerMethodGNN(%d).forward(vertex_attr, %s, edge_attr, g) incl. the returned edge_attr column"
                   % (iters, "edgeij_pair" if world == 1 else "dist.PartitionedGraph"),
            "n_gpus": world, "rows": n, "nnz": z, "ms_total": ms, "ms_per_iteration": ms / spmvs,
@@ -238,22 +242,24 @@ def config3_power(G, dev, rank, world, peak, N=8192, iters=100, cpu_baseline=Tru
     # roofline of the dominant kernel: glab_power_step on this rank's rows (kernel-only loop)
     if world == 1:
         plan = rt.get_plan(ei, n)
-        vals = rt.get_vals(plan, ea, 0, torch.float32)
-        xa, xb = b0.view(-1).clone(), torch.empty(n, device=dev)
+        vals = rt.get_vals(plan, ea, 0, dtype)
+        xa, xb = b0.view(-1).clone(), torch.empty(n, device=dev, dtype=dtype)
         ss = torch.zeros(4, dtype=torch.float64, device=dev)
         ms_k = timed_ms(lambda: rt.power_step(plan, vals, xa, xb, None, ss[0:2]), reps=10)
-        out["roofline"] = dict(kernel="glab_power_step_f32", bound="hbm", peak=peak, unit="GB/s",
-                               **roof(ms_k, z * (4 + s) + 4 * (n + 1) + 2 * n * s, z, peak, plan.index_bytes))
+        out["roofline"] = dict(kernel="glab_power_step_" + sfx, bound="hbm", peak=peak, unit="GB/s",
+                               **roof(ms_k, z * (4 + s) + 4 * (n + 1) + 2 * n * s, z, peak,
+                                      4 if f64 else plan.index_bytes))   # fp64 9-point kernels keep int32 indices
         del plan, vals, xa, xb
     else:
         nl, zl = r1 - r0, int(ei.shape[1])
         per_iter = ms / spmvs
-        out["roofline"] = dict(kernel="glab_power_step_halo_f32 (whole iteration incl. the 2-scalar reduction over ranks)",
+        out["roofline"] = dict(kernel="glab_power_step_halo_%s (whole iteration incl. the 2-scalar reduction over ranks)" % sfx,
                                bound="hbm", peak=peak, unit="GB/s",
                                **roof(per_iter, zl * (4 + s) + 4 * (nl + 1) + 2 * nl * s, zl, peak, 4))
     # ---- parity: independent fp64 power iteration on the grid (rank 0), lambda / norm / iterate
     if world > 1:
-        full = [torch.empty(part.bounds(q)[1] - part.bounds(q)[0], device=dev) for q in range(world)] if rank == 0 else None
+        full = [torch.empty(part.bounds(q)[1] - part.bounds(q)[0], device=dev, dtype=dtype) for q in range(world)] \
+            if rank == 0 else None
         dist.gather(v[:, 0].contiguous(), full, dst=0)
     else:
         full = [v[:, 0]]
@@ -263,7 +269,7 @@ def config3_power(G, dev, rank, world, peak, N=8192, iters=100, cpu_baseline=Tru
         e_vec = relerr(torch.cat(full), b_ref)
         e_lam = abs(float(g[2].item()) - lam_ref) / abs(lam_ref)
         e_nrm = abs(float(g[0].item()) - nrm_ref) / abs(nrm_ref)
-        out["parity"] = {"ok": bool(max(e_lam, e_nrm, e_vec) <= TOL32), "tolerance": TOL32, "lambda_rel_err": e_lam,
+        out["parity"] = {"ok": bool(max(e_lam, e_nrm, e_vec) <= tol), "tolerance": tol, "lambda_rel_err": e_lam,
                          "norm_rel_err": e_nrm, "iterate_rel_err": e_vec, "lambda_reference": lam_ref,
                          "against": "independent fp64 power iteration applying the closed-form 9-point stencil with "
                                     "shifted grid slices on rank 0 (all %d rows)" % n}
