@@ -470,6 +470,7 @@ def main_gpu(args):
         "config": workload_config(args.workload, n_global, z_global, world),
         "roofline": {"bound": "hbm", "kernel": "glab_jacobi_f32 (k_row_pipe<float,1,5,EpiJacobi>: TMA-fed persistent pipeline)",
                      "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                     "frac_of_nominal_8TBps": achieved / 8000.0,
                      "peak_source": peak_src, "bytes_per_launch": bytes_jac, "ms_per_launch": jac_ms,
                      "index_bytes_streamed": idx_bytes, "bytes_moved_per_launch": moved_jac,
                      "moved_gbs": moved_jac / (jac_ms * 1e-3) / 1e9, "moved_frac": moved_jac / (jac_ms * 1e-3) / 1e9 / peak,

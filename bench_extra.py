@@ -52,6 +52,7 @@ def roof(ms, alg_bytes, z, peak, index_bytes=4):
     moved = alg_bytes - (4 - index_bytes) * z
     return {"ms": ms, "gnnz_per_s": z / ms / 1e6, "algorithmic_GBps": alg_bytes / ms / 1e6,
             "frac": alg_bytes / ms / 1e6 / peak, "moved_frac": moved / ms / 1e6 / peak,
+            "frac_of_nominal_8TBps": alg_bytes / ms / 1e6 / 8000.0,       # north_star quotes ~8 TB/s
             "bytes_per_launch": int(alg_bytes), "index_bytes_streamed": index_bytes}
 
 
