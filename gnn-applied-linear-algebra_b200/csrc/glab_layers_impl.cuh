@@ -374,6 +374,19 @@ struct Tuning {
 // publishing completions (an L2 read-back per tile) outweighs the saved launch ramps.
 constexpr int kMsAutoTiles = 4096;
 
+// Ring depth chosen automatically: at most 4 stages, 3 for the single-column Jacobi sweep.  Measured on B200
+// (profiles/r02_kernel_rooflines_stages{3,4}.jsonl, L4096 fp32, registers allow 4 CTAs per SM either way): Jacobi
+// 4 stages 0.1347 ms, 3 stages 0.1285 ms, 2 stages 0.1347 ms per sweep -- the fourth stage buys no more bytes in
+// flight than the memory system needs, but its 11 KB x 4 CTAs come out of the L1 that serves the x[col] gathers
+// (shared memory and L1 share one 256 KB array).  Capping EVERY epilogue at 3 made the isolated kernels faster too
+// (cheby_next 0.154 -> 0.145 ms) but the chained smoothing pass SLOWER (2.10 vs 1.95 ms per step: the Chebyshev
+// launches that follow the sweeps lose more than the sweeps gain), so only the sweep is capped: 1.88 ms per step,
+// 624 Gnnz/s (bench.py).  GLAB_STAGES overrides everything.
+constexpr int kMaxAutoStages = 4;
+template <class Epi> struct auto_stage_cap { static constexpr int value = kMaxAutoStages; };
+// single-column Jacobi sweep: 3 stages (see the measurements in the comment above)
+template <typename T> struct auto_stage_cap<EpiJacobi<T, 1>> { static constexpr int value = 3; };
+
 // Bound of the in-kernel waits: caller's value, else GLAB_SPIN_TIMEOUT_MS, else 20 s; < 0 = forever.
 static unsigned long long spin_timeout_ns(int64_t timeout_ms) {
   static const int64_t dflt = [] {
@@ -581,6 +594,7 @@ static int launch_pipe_halo_impl(const glab_plan* p, const T* vals, const T* x, 
   if (2 * L.stage_bytes + 128 > max_smem) return GLAB_E_ARG;
   int want_ctas = tuning().ctas ? tuning().ctas : 4;  // measured: shallow rings + more CTAs win for wide k too
   int stages = tuning().stages ? tuning().stages : (max_smem / want_ctas - 128) / L.stage_bytes;
+  if (!tuning().stages && stages > auto_stage_cap<Epi>::value) stages = auto_stage_cap<Epi>::value;
   if (stages > 4) stages = 4;
   while (stages > 2 && (size_t)stages * L.stage_bytes + 128 > (size_t)max_smem) --stages;
   if (stages < 2) stages = 2;
@@ -676,7 +690,7 @@ static int launch_pipe_impl(const glab_plan* p, const T* vals, const T* x, const
   int stages = tuning().stages;
   if (!stages) {
     stages = (max_smem / want_ctas - 128) / L.stage_bytes;
-    if (stages > 4) stages = 4;
+    if (stages > auto_stage_cap<Epi>::value) stages = auto_stage_cap<Epi>::value;
   }
   while (stages > 2 && (size_t)stages * L.stage_bytes + 128 > (size_t)max_smem) --stages;
   if (stages < 2) stages = 2;
@@ -835,6 +849,7 @@ static int launch_jacobi_ms_impl(const glab_plan* p, const T* vals, const T* dia
   if (2 * L.stage_bytes + 128 > max_smem) return kNoPipe;
   const int want_ctas = tuning().ctas ? tuning().ctas : 4;
   int stages = tuning().stages ? tuning().stages : (max_smem / want_ctas - 128) / L.stage_bytes;
+  if (!tuning().stages && stages > kMaxAutoStages) stages = kMaxAutoStages;
   if (stages > 4) stages = 4;
   while (stages > 2 && (size_t)stages * L.stage_bytes + 128 > (size_t)max_smem) --stages;
   if (stages < 2) stages = 2;
