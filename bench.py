@@ -327,7 +327,8 @@ def main_reference(args):
         return 0
     steps = max(1, min(args.steps, 3))
     warm = max(0, min(args.warmup, 1))
-    r = run_cpu_reference(args.workload, steps, warm)
+    # the reference arm runs the WHOLE pass (10 sweeps + degree 4 = 14 GN blocks, ~6 s per step on 16 cores)
+    r = run_cpu_reference(args.workload, steps, warm, sample_jacobi=N_JACOBI, sample_cheb=CHEB_DEG)
     line = {"impl": "reference", "metric": "fused SpMV-layer nnz/s", "value": r["value"], "unit": "nnz/s",
             "n_gpus": args.gpus, "steps": steps, "warmup": warm, "ms_per_step": r["ms_per_step"],
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
