@@ -17,6 +17,12 @@ aggregates = PMIS (oracle/cf_split.py) on the distance-2 strength graph, every o
 root with the largest index among its strong neighbours (else among its distance-2 neighbours),
 P = (I - (omega_p/rho) D^-1 A) P_tentative.  All index arithmetic is integer and deterministic, so the
 device must reproduce aggregates bit for bit; floating-point stages are compared to tolerance.
+
+What IS pinned: every building block above against oracle/port.py (itself pinned bit for bit to the unmodified
+reference layers): strength values and mask, Jacobi sweeps, residual, restriction / prolongation through the
+scatter-sum seam, the Galerkin product and the power-method estimate of rho
+(tests/test_oracle_multilevel.py::test_*_reference_*).  What stays unpinned is the composition: the aggregation
+rule, the prolongator smoothing and the recursion.
 """
 import numpy as np
 import scipy.sparse as sp
